@@ -1,0 +1,91 @@
+"""ctypes loader of libsdfcontact_b200.so (the C-ABI in include/sdfcontact_b200.h).
+
+There is no fallback: if the CUDA library is missing this raises, and every
+compute call raises when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdfcontact_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_uint8_p = C.POINTER(C.c_uint8)
+c_void_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/sdfcontact_b200.h one to one
+SIGNATURES = {
+    "sdfc_version": (C.c_int, []),
+    "sdfc_last_error": (C.c_char_p, []),
+    "sdfc_device_count": (C.c_int, []),
+    "sdfc_context_create": (C.c_int, [C.c_int, c_void_pp]),
+    "sdfc_context_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sdfc_context_synchronize": (C.c_int, [C.c_void_p]),
+    "sdfc_context_launch_count": (C.c_int64, [C.c_void_p]),
+    "sdfc_sdf_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, c_double_p, c_void_pp]),
+    "sdfc_sdf_set_col_th": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_sdf_is_fp32": (C.c_int, [C.c_void_p]),
+    "sdfc_sdf_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_sdf_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
+    "sdfc_sdf_min_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
+    "sdfc_sdf_distance_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdfc_points_create": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_void_pp]),
+    "sdfc_points_count": (C.c_int, [C.c_void_p]),
+    "sdfc_points_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_pair_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   c_void_pp]),
+    "sdfc_pair_set_stiffness": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "sdfc_pair_set_friction": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_pair_set_damping": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_pair_set_scale": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_pair_set_contact_scale": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_pair_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_pair_query": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_uint8_p, c_int32_p]),
+    "sdfc_pair_force": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "sdfc_pair_force_deriv": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                        c_double_p, c_double_p, c_int32_p]),
+    "sdfc_scatter_force": (None, [C.c_int, C.c_int, c_double_p, c_double_p]),
+    "sdfc_scatter_deriv": (None, [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "sdfc_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_void_pp, c_int32_p, c_int32_p, c_void_pp]),
+    "sdfc_batch_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_batch_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p,
+                                  c_int32_p]),
+    "sdfc_batch_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "sdfc_batch_detect_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdfc_batch_queries_per_eval": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class SdfContactError(RuntimeError):
+    """Mirrors the reference's `throw std::string` (Common.h:58-61)."""
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SdfContactError(
+            f"{LIB_PATH} is missing: build it with `python assemble-them-all_b200/build.py` "
+            "(there is no CPU fallback for the contact path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().sdfc_last_error()
+        raise SdfContactError(f"[Error] {msg.decode() if msg else 'unknown'} (status {status})")

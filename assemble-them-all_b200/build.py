@@ -1,0 +1,74 @@
+"""Build the CUDA library IN-TREE for sm_100a.
+
+    python assemble-them-all_b200/build.py [--force] [--verbose]
+
+Output: assemble-them-all_b200/libsdfcontact_b200.so (git-ignored; it travels to
+the GPU box with the gpurun snapshot). nvcc cross-compiles without a GPU.
+-fmad=false: the bit-critical part of the path must not contract a*b+c into an
+FMA (the reference's x86-64 build has none); see csrc/sdfc_device.cuh.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libsdfcontact_b200.so")
+SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu"]
+HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_step.cuh", os.path.join("..", "..", "include", "sdfcontact_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "--compiler-bindir", "/usr/bin/g++",
+]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found")
+    return nvcc
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and not _stale():
+        return OUT
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(objdir, os.path.basename(s) + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}")
+    cmd = [_nvcc(), "-shared", "-o", OUT, *objs, "--compiler-bindir", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference's SDF-contact plug-in, over the C-ABI.
+
+Names and semantics follow the reference (paths relative to
+/root/reference/simulation/redmax):
+
+  SdfGrid                  <- BodySDFObj's grid fields (Body/BodySDFObj.h:13-16) and
+                              SDFMesh.distance / min_distance (Mesh.cpp:143-198)
+  ContactPoints            <- Body::_contact_points (Body/Body.h:36)
+  ForceGeneralSDFContact   <- Force/ForceGeneralSDFContact.{h,cpp}: set_stiffness /
+                              set_friction / set_damping / set_scale, computeForce,
+                              computeForceWithDerivative with ACCUMULATE (+=) semantics
+                              into caller-owned fm / Km / Dm
+  ContactBatch             <- Robot::computeForce[WithDerivative]'s loop over _forces
+                              (Robot.cpp:513-551) for E environments at once
+
+All arithmetic runs in the CUDA library; this module only marshals numpy arrays.
+Poses are numpy (4,4) matrices (converted to Eigen's column-major layout here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SdfContactError, check  # noqa: F401
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _colmajor44(E):
+    E = np.asarray(E, dtype=np.float64)
+    assert E.shape[-2:] == (4, 4)
+    return np.ascontiguousarray(np.swapaxes(E, -1, -2))
+
+
+class Context:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_context_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self._lib.sdfc_context_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        check(self._lib.sdfc_context_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.sdfc_context_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class SdfGrid:
+    def __init__(self, ctx, ni, nj, nk, min_box, max_box, dx, dy, dz, col_th, grid):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        g = _f64(np.asarray(grid).reshape(-1))
+        if g.size != int(ni) * int(nj) * int(nk):
+            raise SdfContactError("[Error] SDF grid size does not match ni*nj*nk")
+        mn, mx = _f64(min_box), _f64(max_box)
+        self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        self.min_box, self.max_box = mn.copy(), mx.copy()
+        self.dx, self.dy, self.dz, self.col_th = float(dx), float(dy), float(dz), float(col_th)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_sdf_create(ctx._h, self.ni, self.nj, self.nk, _dp(mn), _dp(mx), self.dx, self.dy, self.dz,
+                                        self.col_th, _dp(g), C.byref(self._h)))
+
+    @classmethod
+    def from_spec(cls, ctx, s):
+        return cls(ctx, s.ni, s.nj, s.nk, s.min_box, s.max_box, s.dx, s.dy, s.dz, s.col_th, s.grid)
+
+    @classmethod
+    def from_dict(cls, ctx, d):
+        return cls(ctx, d["ni"], d["nj"], d["nk"], d["min_box"], d["max_box"], d["dx"], d["dy"], d["dz"], d["col_th"],
+                   d["grid"])
+
+    @property
+    def is_fp32(self):
+        return bool(self._lib.sdfc_sdf_is_fp32(self._h))
+
+    def set_col_th(self, col_th):
+        self.col_th = float(col_th)
+        check(self._lib.sdfc_sdf_set_col_th(self._h, self.col_th))
+
+    def distance(self, X):
+        """SDFMesh.distance: X is (n,3) in the grid's frame -> (n,) raw SDF (FLT_MAX outside)."""
+        X = _f64(X)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise SdfContactError("[Error] distance expects an (n,3) array")
+        out = np.empty(len(X), dtype=np.float64)
+        check(self._lib.sdfc_sdf_distance(self._h, len(X), _dp(X), _dp(out)))
+        return out
+
+    def min_distance(self, X):
+        X = _f64(X)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise SdfContactError("[Error] min_distance expects an (n,3) array")
+        out = C.c_double()
+        check(self._lib.sdfc_sdf_min_distance(self._h, len(X), _dp(X), C.byref(out)))
+        return float(out.value)
+
+    def distance_device(self, n, dx_ptr, dy_ptr, dz_ptr, dout_ptr):
+        check(self._lib.sdfc_sdf_distance_device(self._h, int(n), dx_ptr, dy_ptr, dz_ptr, dout_ptr))
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_sdf_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class ContactPoints:
+    def __init__(self, ctx, xyz, morton_sort=True):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        X = _f64(xyz)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise SdfContactError("[Error] contact points must be an (n,3) array")
+        self.n = len(X)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_points_create(ctx._h, self.n, _dp(X), int(bool(morton_sort)), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_points_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class ForceGeneralSDFContact:
+    """One (contact body, SDF body) contact force; see module docstring."""
+
+    def __init__(self, ctx, contact_points, sdf, kn=1.0, kt=0.0, mu=0.0, damping=0.0, index_contact=0, index_sdf=6):
+        if not isinstance(sdf, SdfGrid):
+            # ForceGeneralSDFContact.cpp:17-20
+            raise SdfContactError("[Error] The second body in Contact should be SDF body.")
+        self.ctx, self._lib = ctx, ctx._lib
+        self.contact_points, self.sdf = contact_points, sdf
+        self._kn, self._kt, self._mu, self._damping, self._scale = float(kn), float(kt), float(mu), float(damping), 1.0
+        self.index_contact, self.index_sdf = int(index_contact), int(index_sdf)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_pair_create(ctx._h, contact_points._h, sdf._h, self._kn, self._kt, self._mu, self._damping,
+                                         C.byref(self._h)))
+        self.touched = False  # contact history flag (CollisionDetection.cpp:143-146)
+
+    # ---- setters (ForceGeneralSDFContact.h:28-31)
+    def set_stiffness(self, kn, kt):
+        self._kn, self._kt = float(kn), float(kt)
+        check(self._lib.sdfc_pair_set_stiffness(self._h, self._kn, self._kt))
+
+    def set_friction(self, mu):
+        self._mu = float(mu)
+        check(self._lib.sdfc_pair_set_friction(self._h, self._mu))
+
+    def set_damping(self, damping):
+        self._damping = float(damping)
+        check(self._lib.sdfc_pair_set_damping(self._h, self._damping))
+
+    def set_scale(self, scale):
+        self._scale = float(scale)
+        check(self._lib.sdfc_pair_set_scale(self._h, self._scale))
+
+    def set_contact_scale(self, contact_scale):
+        check(self._lib.sdfc_pair_set_contact_scale(self._h, float(contact_scale)))
+
+    # ---- detection only
+    def query(self, E1, E2, want_d=True, want_cell=True, want_active=True):
+        n = self.contact_points.n
+        e1, e2 = _colmajor44(E1), _colmajor44(E2)
+        d = np.empty(n, dtype=np.float64) if want_d else None
+        cell = np.empty((n, 3), dtype=np.int32) if want_cell else None
+        act = np.empty(n, dtype=np.uint8) if want_active else None
+        cnt = C.c_int32()
+        check(self._lib.sdfc_pair_query(
+            self._h, _dp(e1), _dp(e2), _dp(d) if want_d else None,
+            cell.ctypes.data_as(_lib.c_int32_p) if want_cell else None,
+            act.ctypes.data_as(_lib.c_uint8_p) if want_active else None, C.byref(cnt)))
+        return {"d": d, "cell": cell, "active": act, "n_active": int(cnt.value)}
+
+    # ---- pair blocks
+    def force_sub(self, E1, phi1, E2, phi2):
+        e1, e2, f1, f2 = _colmajor44(E1), _colmajor44(E2), _f64(phi1), _f64(phi2)
+        fm = np.empty(12)
+        cnt = C.c_int32()
+        check(self._lib.sdfc_pair_force(self._h, _dp(e1), _dp(f1), _dp(e2), _dp(f2), _dp(fm), C.byref(cnt)))
+        self.touched = self.touched or cnt.value > 0
+        return fm, int(cnt.value)
+
+    def force_deriv_sub(self, E1, phi1, E2, phi2):
+        e1, e2, f1, f2 = _colmajor44(E1), _colmajor44(E2), _f64(phi1), _f64(phi2)
+        fm, Km, Dm = np.empty(12), np.empty(144), np.empty(144)
+        cnt = C.c_int32()
+        check(self._lib.sdfc_pair_force_deriv(self._h, _dp(e1), _dp(f1), _dp(e2), _dp(f2), _dp(fm), _dp(Km), _dp(Dm),
+                                              C.byref(cnt)))
+        self.touched = self.touched or cnt.value > 0
+        return fm, Km.reshape(12, 12).T.copy(), Dm.reshape(12, 12).T.copy(), int(cnt.value)
+
+    # ---- the reference's public wrappers (ForceGeneralSDFContact.cpp:46-105): accumulate
+    def computeForce(self, fm, E1, phi1, E2, phi2):
+        sub, _ = self.force_sub(E1, phi1, E2, phi2)
+        fm[self.index_contact:self.index_contact + 6] += sub[:6]
+        fm[self.index_sdf:self.index_sdf + 6] += sub[6:]
+
+    def computeForceWithDerivative(self, fm, Km, Dm, E1, phi1, E2, phi2):
+        sub, K, D, _ = self.force_deriv_sub(E1, phi1, E2, phi2)
+        ia, ib = self.index_contact, self.index_sdf
+        fm[ia:ia + 6] += sub[:6]
+        fm[ib:ib + 6] += sub[6:]
+        for (r0, rs) in ((ia, 0), (ib, 6)):
+            for (c0, cs) in ((ia, 0), (ib, 6)):
+                Km[r0:r0 + 6, c0:c0 + 6] += K[rs:rs + 6, cs:cs + 6]
+                Dm[r0:r0 + 6, c0:c0 + 6] += D[rs:rs + 6, cs:cs + 6]
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_pair_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class ContactBatch:
+    """E environments x P pairs sharing geometry (device-resident)."""
+
+    def __init__(self, ctx, n_envs, n_bodies, pairs, body_a, body_b):
+        self.ctx, self._lib = ctx, ctx._lib
+        self.n_envs, self.n_bodies, self.n_pairs = int(n_envs), int(n_bodies), len(pairs)
+        self.pairs = list(pairs)
+        arr = (C.c_void_p * self.n_pairs)(*[p._h for p in pairs])
+        a = np.ascontiguousarray(body_a, dtype=np.int32)
+        b = np.ascontiguousarray(body_b, dtype=np.int32)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_batch_create(ctx._h, self.n_envs, self.n_bodies, self.n_pairs, arr,
+                                          a.ctypes.data_as(_lib.c_int32_p), b.ctypes.data_as(_lib.c_int32_p),
+                                          C.byref(self._h)))
+        self.ndof_m = 6 * self.n_bodies
+
+    @property
+    def queries_per_eval(self):
+        return int(self._lib.sdfc_batch_queries_per_eval(self._h))
+
+    def eval(self, E, phi, deriv=True):
+        """E: (n_envs, n_bodies, 4, 4); phi: (n_envs, n_bodies, 6). Host arrays in and out.
+        -> fm (n_envs, ndof_m), Km, Dm (n_envs, ndof_m, ndof_m) or None, n_active (n_envs, n_pairs)."""
+        Ec = _colmajor44(np.asarray(E).reshape(self.n_envs, self.n_bodies, 4, 4))
+        ph = _f64(np.asarray(phi).reshape(self.n_envs, self.n_bodies, 6))
+        nm = self.ndof_m
+        fm = np.empty((self.n_envs, nm))
+        Km = np.empty((self.n_envs, nm, nm)) if deriv else None
+        Dm = np.empty((self.n_envs, nm, nm)) if deriv else None
+        nact = np.empty((self.n_envs, self.n_pairs), dtype=np.int32)
+        check(self._lib.sdfc_batch_eval(self._h, _dp(Ec), _dp(ph), int(bool(deriv)), _dp(fm),
+                                        _dp(Km) if deriv else None, _dp(Dm) if deriv else None,
+                                        nact.ctypes.data_as(_lib.c_int32_p)))
+        if deriv:  # library writes column-major
+            Km = np.ascontiguousarray(np.swapaxes(Km, 1, 2))
+            Dm = np.ascontiguousarray(np.swapaxes(Dm, 1, 2))
+        return fm, Km, Dm, nact
+
+    def eval_device(self, E_ptr, phi_ptr, deriv, fm_ptr, Km_ptr, Dm_ptr, nact_ptr):
+        """Raw device pointers (ints). E is column-major per pose. Asynchronous."""
+        check(self._lib.sdfc_batch_eval_device(self._h, E_ptr, phi_ptr, int(bool(deriv)), fm_ptr, Km_ptr, Dm_ptr, nact_ptr))
+
+    def detect_device(self, E_ptr, nact_ptr):
+        check(self._lib.sdfc_batch_detect_device(self._h, E_ptr, nact_ptr))
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_batch_destroy(self._h)
+            self._h = C.c_void_p()

@@ -1,0 +1,674 @@
+// sdfc_capi.cu — host side of the C-ABI declared in include/sdfcontact_b200.h.
+// Owns device buffers, uploads geometry once, stages poses, launches the kernels
+// of sdfc_kernels.cu. No CPU compute path: every entry needs a CUDA device.
+#include "../../include/sdfcontact_b200.h"
+#include "sdfc_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sdfc;
+
+namespace {
+thread_local std::string g_last_error;
+
+sdfc_status fail(sdfc_status code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define SDFC_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(SDFC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+#define SDFC_REQUIRE(cond, msg) \
+    do {                        \
+        if (!(cond)) return fail(SDFC_ERR_INVALID, msg); \
+    } while (0)
+
+template <class T>
+sdfc_status dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return SDFC_OK;
+    SDFC_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return SDFC_OK;
+}
+}  // namespace
+
+struct sdfc_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+};
+
+struct sdfc_sdf {
+    sdfc_context* ctx = nullptr;
+    GridDev dev{};
+    double* d_g64 = nullptr;
+    float* d_g32 = nullptr;
+    size_t count = 0;
+    uint64_t version = 1;
+    // grow-only scratch for the host-buffer sampling entry
+    double* d_aos = nullptr; double* d_soa = nullptr; double* d_out = nullptr; double* d_red = nullptr;
+    int64_t scratch_n = 0;
+};
+
+struct sdfc_points {
+    sdfc_context* ctx = nullptr;
+    int n = 0;
+    double* d_o = nullptr;  // original order SoA: x[n] y[n] z[n]
+    double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
+    bool sorted = false;
+};
+
+struct sdfc_pair {
+    sdfc_context* ctx = nullptr;
+    sdfc_points* pts = nullptr;
+    sdfc_sdf* sdf = nullptr;
+    double kn = 1, kt = 0, mu = 0, damping = 0, scale = 1, contact_scale = 1;
+    uint64_t version = 1;
+    sdfc_batch* single = nullptr;  // lazily created 1-env batch behind the per-pair entries
+    // per-point query scratch
+    double* d_d = nullptr; int32_t* d_cell = nullptr; uint8_t* d_active = nullptr; int32_t* d_count = nullptr;
+    double* d_E = nullptr;  // 32 doubles
+};
+
+struct sdfc_batch {
+    sdfc_context* ctx = nullptr;
+    int n_envs = 0, n_bodies = 0, n_pairs = 0;
+    std::vector<sdfc_pair*> pairs;
+    std::vector<int32_t> body_a, body_b;
+    std::vector<uint64_t> seen_pair_version, seen_sdf_version;
+    BatchDev dev{};
+    PairDev* d_pairs = nullptr;
+    int* d_tile_pair = nullptr; int* d_tile_word0 = nullptr;
+    uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; double* d_partial = nullptr;
+    double* d_fm_sub = nullptr; double* d_Km_sub = nullptr; double* d_Dm_sub = nullptr;
+    bool any_fric = false, any_damp = false;
+    int64_t queries = 0;
+    // staging for the host-buffer entry
+    double* d_E = nullptr; double* d_phi = nullptr; double* d_fm = nullptr; double* d_Km = nullptr; double* d_Dm = nullptr;
+    double* h_in = nullptr;   // pinned: E then phi
+    double* h_out = nullptr;  // pinned: fm, Km, Dm
+    int32_t* h_nact = nullptr;
+};
+
+namespace {
+
+void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, PairDev* out) {
+    const sdfc_points* pts = p->pts;
+    out->sx = pts->d_s; out->sy = pts->d_s + pts->n; out->sz = pts->d_s + 2 * (size_t)pts->n;
+    out->ox = pts->d_o; out->oy = pts->d_o + pts->n; out->oz = pts->d_o + 2 * (size_t)pts->n;
+    out->n = pts->n;
+    out->n_words = (pts->n + 31) / 32;
+    out->word_offset = word_offset;
+    out->body_a = body_a; out->body_b = body_b;
+    out->grid = p->sdf->dev;
+    // ForceGeneralSDFContact.cpp:155-156 / 235-236
+    out->prm.kn = p->kn * p->scale * p->contact_scale;
+    out->prm.kt = p->kt * p->scale * p->contact_scale;
+    out->prm.mu = p->mu;
+    out->prm.damping = p->damping;
+}
+
+sdfc_status batch_refresh(sdfc_batch* b) {
+    bool dirty = false;
+    for (int i = 0; i < b->n_pairs; ++i)
+        if (b->seen_pair_version[i] != b->pairs[i]->version || b->seen_sdf_version[i] != b->pairs[i]->sdf->version) dirty = true;
+    if (!dirty) return SDFC_OK;
+    std::vector<PairDev> host(b->n_pairs);
+    int word_offset = 0;
+    b->any_fric = b->any_damp = false;
+    for (int i = 0; i < b->n_pairs; ++i) {
+        fill_pair_dev(b->pairs[i], b->body_a[i], b->body_b[i], word_offset, &host[i]);
+        word_offset += host[i].n_words;
+        if (host[i].prm.mu > kEps) b->any_fric = true;
+        if (host[i].prm.damping != 0.0) b->any_damp = true;
+        b->seen_pair_version[i] = b->pairs[i]->version;
+        b->seen_sdf_version[i] = b->pairs[i]->sdf->version;
+    }
+    SDFC_CUDA(cudaMemcpyAsync(b->d_pairs, host.data(), sizeof(PairDev) * b->n_pairs, cudaMemcpyHostToDevice, b->ctx->stream));
+    SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));  // `host` goes out of scope
+    return SDFC_OK;
+}
+
+sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, bool scatter, double* fm_dev,
+                      double* Km_dev, double* Dm_dev, int32_t* n_active_dev) {
+    sdfc_status st = batch_refresh(b);
+    if (st != SDFC_OK) return st;
+    cudaStream_t s = b->ctx->stream;
+    const bool dm = b->any_fric || b->any_damp;
+    launch_detect_mask(b->dev, E_dev, s);
+    launch_force(b->dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s);
+    launch_finalize_pairs(b->dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s);
+    b->ctx->launches += 3;
+    if (scatter) {
+        launch_scatter_system(b->dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
+        b->ctx->launches += 1;
+    }
+    if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
+        SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
+                                  cudaMemcpyDeviceToDevice, s));
+    SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+// 30-bit Morton code of a point quantised to 10 bits per axis inside [lo, hi].
+uint32_t expand10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+}  // namespace
+
+extern "C" {
+
+int sdfc_version(void) { return 100; }
+const char* sdfc_last_error(void) { return g_last_error.c_str(); }
+int sdfc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------- context
+sdfc_status sdfc_context_create(int device, sdfc_context** out) {
+    SDFC_REQUIRE(out != nullptr, "sdfc_context_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SDFC_ERR_NO_DEVICE, "sdfc_context_create: no CUDA device (this library has no CPU path)");
+    }
+    SDFC_REQUIRE(device >= 0 && device < n, "sdfc_context_create: bad device index");
+    SDFC_CUDA(cudaSetDevice(device));
+    sdfc_context* c = new sdfc_context();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(SDFC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    c->stream = c->own_stream;
+    *out = c;
+    return SDFC_OK;
+}
+sdfc_status sdfc_context_destroy(sdfc_context* ctx) {
+    if (!ctx) return SDFC_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SDFC_OK;
+}
+sdfc_status sdfc_context_set_stream(sdfc_context* ctx, void* cuda_stream) {
+    SDFC_REQUIRE(ctx != nullptr, "sdfc_context_set_stream: ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SDFC_OK;
+}
+sdfc_status sdfc_context_synchronize(sdfc_context* ctx) {
+    SDFC_REQUIRE(ctx != nullptr, "sdfc_context_synchronize: ctx is NULL");
+    SDFC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDFC_OK;
+}
+int64_t sdfc_context_launch_count(const sdfc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+// -------------------------------------------------------------------- sdf
+sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const double min_box[3], const double max_box[3],
+                            double dx, double dy, double dz, double col_th, const double* grid_host, sdfc_sdf** out) {
+    SDFC_REQUIRE(ctx && out && min_box && max_box && grid_host, "sdfc_sdf_create: NULL argument");
+    SDFC_REQUIRE(ni > 0 && nj > 0 && nk > 0, "sdfc_sdf_create: grid dimensions must be positive");
+    SDFC_REQUIRE(dx > 0 && dy > 0 && dz > 0, "sdfc_sdf_create: grid spacing must be positive");
+    *out = nullptr;
+    SDFC_CUDA(cudaSetDevice(ctx->device));
+    sdfc_sdf* s = new sdfc_sdf();
+    s->ctx = ctx;
+    s->count = (size_t)ni * nj * nk;
+    bool lossless = true;
+    std::vector<float> g32(s->count);
+    for (size_t i = 0; i < s->count; ++i) {
+        g32[i] = (float)grid_host[i];
+        if ((double)g32[i] != grid_host[i]) { lossless = false; break; }
+    }
+    sdfc_status st = dev_alloc(&s->d_g64, s->count);
+    if (st != SDFC_OK) { delete s; return st; }
+    cudaError_t e = cudaMemcpy(s->d_g64, grid_host, s->count * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && lossless) {
+        st = dev_alloc(&s->d_g32, s->count);
+        if (st == SDFC_OK) e = cudaMemcpy(s->d_g32, g32.data(), s->count * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess || st != SDFC_OK) {
+        cudaFree(s->d_g64); cudaFree(s->d_g32); delete s;
+        return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_create: upload failed: ") + cudaGetErrorString(e));
+    }
+    s->dev.g64 = s->d_g64; s->dev.g32 = s->d_g32;
+    s->dev.ni = ni; s->dev.nj = nj; s->dev.nk = nk;
+    for (int a = 0; a < 3; ++a) { s->dev.mn[a] = min_box[a]; s->dev.mx[a] = max_box[a]; }
+    s->dev.dx = dx; s->dev.dy = dy; s->dev.dz = dz; s->dev.col_th = col_th;
+    *out = s;
+    return SDFC_OK;
+}
+sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th) {
+    SDFC_REQUIRE(sdf != nullptr, "sdfc_sdf_set_col_th: sdf is NULL");
+    sdf->dev.col_th = col_th;
+    sdf->version++;
+    return SDFC_OK;
+}
+int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && sdf->d_g32) ? 1 : 0; }
+sdfc_status sdfc_sdf_destroy(sdfc_sdf* s) {
+    if (!s) return SDFC_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_g64); cudaFree(s->d_g32); cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
+    delete s;
+    return SDFC_OK;
+}
+
+static sdfc_status sdf_scratch(sdfc_sdf* s, int64_t n) {
+    if (n <= s->scratch_n) return SDFC_OK;
+    cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
+    s->d_aos = s->d_soa = s->d_out = s->d_red = nullptr; s->scratch_n = 0;
+    sdfc_status st;
+    if ((st = dev_alloc(&s->d_aos, (size_t)3 * n)) != SDFC_OK) return st;
+    if ((st = dev_alloc(&s->d_soa, (size_t)3 * n)) != SDFC_OK) return st;
+    if ((st = dev_alloc(&s->d_out, (size_t)n)) != SDFC_OK) return st;
+    if ((st = dev_alloc(&s->d_red, (size_t)1025)) != SDFC_OK) return st;
+    s->scratch_n = n;
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_sdf_distance_device(sdfc_sdf* sdf, int64_t n, const double* dx, const double* dy, const double* dz,
+                                     double* dout) {
+    SDFC_REQUIRE(sdf && (n == 0 || (dx && dy && dz && dout)), "sdfc_sdf_distance_device: NULL argument");
+    SDFC_REQUIRE(n >= 0, "sdfc_sdf_distance_device: negative n");
+    if (n == 0) return SDFC_OK;
+    SDFC_CUDA(cudaSetDevice(sdf->ctx->device));
+    launch_sdf_distance(sdf->dev, n, dx, dy, dz, dout, sdf->ctx->stream);
+    sdf->ctx->launches += 1;
+    SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_sdf_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_host) {
+    SDFC_REQUIRE(sdf && (n == 0 || (X_host && out_host)), "sdfc_sdf_distance: NULL argument");
+    SDFC_REQUIRE(n >= 0, "sdfc_sdf_distance: negative n");
+    if (n == 0) return SDFC_OK;
+    SDFC_CUDA(cudaSetDevice(sdf->ctx->device));
+    sdfc_status st = sdf_scratch(sdf, n);
+    if (st != SDFC_OK) return st;
+    cudaStream_t s = sdf->ctx->stream;
+    SDFC_CUDA(cudaMemcpyAsync(sdf->d_aos, X_host, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    launch_aos_to_soa(sdf->d_aos, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, s);
+    launch_sdf_distance(sdf->dev, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, sdf->d_out, s);
+    sdf->ctx->launches += 2;
+    SDFC_CUDA(cudaMemcpyAsync(out_host, sdf->d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    SDFC_CUDA(cudaStreamSynchronize(s));
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_sdf_min_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_min) {
+    SDFC_REQUIRE(sdf && out_min && (n == 0 || X_host), "sdfc_sdf_min_distance: NULL argument");
+    SDFC_REQUIRE(n > 0, "sdfc_sdf_min_distance: needs at least one point");
+    SDFC_CUDA(cudaSetDevice(sdf->ctx->device));
+    sdfc_status st = sdf_scratch(sdf, n);
+    if (st != SDFC_OK) return st;
+    cudaStream_t s = sdf->ctx->stream;
+    SDFC_CUDA(cudaMemcpyAsync(sdf->d_aos, X_host, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    launch_aos_to_soa(sdf->d_aos, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, s);
+    launch_sdf_distance(sdf->dev, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, sdf->d_out, s);
+    launch_min_reduce(sdf->d_out, n, sdf->d_red + 1024, sdf->d_red, s);
+    sdf->ctx->launches += 4;
+    SDFC_CUDA(cudaMemcpyAsync(out_min, sdf->d_red + 1024, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SDFC_CUDA(cudaStreamSynchronize(s));
+    return SDFC_OK;
+}
+
+// ----------------------------------------------------------------- points
+sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host, int morton_sort, sdfc_points** out) {
+    SDFC_REQUIRE(ctx && out && (n == 0 || xyz_host), "sdfc_points_create: NULL argument");
+    SDFC_REQUIRE(n >= 0, "sdfc_points_create: negative n");
+    *out = nullptr;
+    SDFC_CUDA(cudaSetDevice(ctx->device));
+    sdfc_points* p = new sdfc_points();
+    p->ctx = ctx; p->n = n;
+    if (n == 0) { *out = p; return SDFC_OK; }
+    std::vector<double> soa((size_t)3 * n);
+    for (int i = 0; i < n; ++i) { soa[i] = xyz_host[3 * i]; soa[(size_t)n + i] = xyz_host[3 * i + 1]; soa[2 * (size_t)n + i] = xyz_host[3 * i + 2]; }
+    sdfc_status st = dev_alloc(&p->d_o, (size_t)3 * n);
+    if (st != SDFC_OK) { delete p; return st; }
+    cudaError_t e = cudaMemcpy(p->d_o, soa.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice);
+    p->d_s = p->d_o;
+    if (e == cudaSuccess && morton_sort) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], xyz_host[3 * i + a]); hi[a] = std::max(hi[a], xyz_host[3 * i + a]); }
+        std::vector<std::pair<uint32_t, int>> keys(n);
+        for (int i = 0; i < n; ++i) {
+            uint32_t q[3];
+            for (int a = 0; a < 3; ++a) {
+                const double ext = hi[a] - lo[a];
+                const double t = ext > 0 ? (xyz_host[3 * i + a] - lo[a]) / ext : 0.0;
+                q[a] = (uint32_t)std::min(1023.0, std::max(0.0, std::floor(t * 1024.0)));
+            }
+            keys[i] = {expand10(q[0]) | (expand10(q[1]) << 1) | (expand10(q[2]) << 2), i};
+        }
+        std::stable_sort(keys.begin(), keys.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
+        std::vector<double> srt((size_t)3 * n);
+        for (int i = 0; i < n; ++i) {
+            const int o = keys[i].second;
+            srt[i] = soa[o]; srt[(size_t)n + i] = soa[(size_t)n + o]; srt[2 * (size_t)n + i] = soa[2 * (size_t)n + o];
+        }
+        st = dev_alloc(&p->d_s, (size_t)3 * n);
+        if (st == SDFC_OK) e = cudaMemcpy(p->d_s, srt.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice);
+        p->sorted = true;
+    }
+    if (e != cudaSuccess || st != SDFC_OK) {
+        if (p->d_s != p->d_o) cudaFree(p->d_s);
+        cudaFree(p->d_o); delete p;
+        return fail(SDFC_ERR_CUDA, std::string("sdfc_points_create: upload failed: ") + cudaGetErrorString(e));
+    }
+    *out = p;
+    return SDFC_OK;
+}
+int sdfc_points_count(const sdfc_points* pts) { return pts ? pts->n : 0; }
+sdfc_status sdfc_points_destroy(sdfc_points* p) {
+    if (!p) return SDFC_OK;
+    cudaSetDevice(p->ctx->device);
+    if (p->d_s != p->d_o) cudaFree(p->d_s);
+    cudaFree(p->d_o);
+    delete p;
+    return SDFC_OK;
+}
+
+// ------------------------------------------------------------------- pair
+sdfc_status sdfc_pair_create(sdfc_context* ctx, sdfc_points* contact_points, sdfc_sdf* sdf, double kn, double kt,
+                             double mu, double damping, sdfc_pair** out) {
+    SDFC_REQUIRE(ctx && contact_points && sdf && out, "sdfc_pair_create: NULL argument");
+    // ForceGeneralSDFContact.cpp:17-20 throws when the second body has no SDF.
+    SDFC_REQUIRE(contact_points->ctx == ctx && sdf->ctx == ctx, "sdfc_pair_create: objects belong to another context");
+    sdfc_pair* p = new sdfc_pair();
+    p->ctx = ctx; p->pts = contact_points; p->sdf = sdf;
+    p->kn = kn; p->kt = kt; p->mu = mu; p->damping = damping;
+    *out = p;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_set_stiffness(sdfc_pair* p, double kn, double kt) {
+    SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_stiffness: pair is NULL");
+    p->kn = kn; p->kt = kt; p->version++;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_set_friction(sdfc_pair* p, double mu) {
+    SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_friction: pair is NULL");
+    p->mu = mu; p->version++;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_set_damping(sdfc_pair* p, double damping) {
+    SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_damping: pair is NULL");
+    p->damping = damping; p->version++;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_set_scale(sdfc_pair* p, double scale) {
+    SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_scale: pair is NULL");
+    p->scale = scale; p->version++;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_set_contact_scale(sdfc_pair* p, double contact_scale) {
+    SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_contact_scale: pair is NULL");
+    p->contact_scale = contact_scale; p->version++;
+    return SDFC_OK;
+}
+sdfc_status sdfc_pair_destroy(sdfc_pair* p) {
+    if (!p) return SDFC_OK;
+    cudaSetDevice(p->ctx->device);
+    if (p->single) sdfc_batch_destroy(p->single);
+    cudaFree(p->d_d); cudaFree(p->d_cell); cudaFree(p->d_active); cudaFree(p->d_count); cudaFree(p->d_E);
+    delete p;
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_pair_query(sdfc_pair* p, const double E1[16], const double E2[16], double* d_out, int32_t* cell_out,
+                            uint8_t* active_out, int32_t* n_active) {
+    SDFC_REQUIRE(p && E1 && E2, "sdfc_pair_query: NULL argument");
+    SDFC_CUDA(cudaSetDevice(p->ctx->device));
+    const int n = p->pts->n;
+    if (n_active) *n_active = 0;
+    if (n == 0) return SDFC_OK;
+    sdfc_status st;
+    if (!p->d_d) {
+        if ((st = dev_alloc(&p->d_d, (size_t)n)) != SDFC_OK) return st;
+        if ((st = dev_alloc(&p->d_cell, (size_t)3 * n)) != SDFC_OK) return st;
+        if ((st = dev_alloc(&p->d_active, (size_t)n)) != SDFC_OK) return st;
+        if ((st = dev_alloc(&p->d_count, (size_t)1)) != SDFC_OK) return st;
+        if ((st = dev_alloc(&p->d_E, (size_t)32)) != SDFC_OK) return st;
+    }
+    cudaStream_t s = p->ctx->stream;
+    SDFC_CUDA(cudaMemcpyAsync(p->d_E, E1, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
+    SDFC_CUDA(cudaMemcpyAsync(p->d_E + 16, E2, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
+    PairDev pd;
+    fill_pair_dev(p, 0, 1, 0, &pd);
+    launch_query_points(pd, p->d_E, p->d_E + 16, d_out ? p->d_d : nullptr, cell_out ? p->d_cell : nullptr,
+                        active_out ? p->d_active : nullptr, p->d_count, s);
+    p->ctx->launches += 1;
+    SDFC_CUDA(cudaGetLastError());
+    if (d_out) SDFC_CUDA(cudaMemcpyAsync(d_out, p->d_d, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (cell_out) SDFC_CUDA(cudaMemcpyAsync(cell_out, p->d_cell, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, s));
+    if (active_out) SDFC_CUDA(cudaMemcpyAsync(active_out, p->d_active, n, cudaMemcpyDeviceToHost, s));
+    int32_t cnt = 0;
+    SDFC_CUDA(cudaMemcpyAsync(&cnt, p->d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SDFC_CUDA(cudaStreamSynchronize(s));
+    if (n_active) *n_active = cnt;
+    return SDFC_OK;
+}
+
+static sdfc_status pair_single(sdfc_pair* p) {
+    if (p->single) return SDFC_OK;
+    const int32_t a = 0, b = 1;
+    sdfc_pair* arr[1] = {p};
+    return sdfc_batch_create(p->ctx, 1, 2, 1, arr, &a, &b, &p->single);
+}
+
+static sdfc_status pair_eval(sdfc_pair* p, const double* E1, const double* phi1, const double* E2, const double* phi2,
+                             int deriv, double* fm_sub, double* Km_sub, double* Dm_sub, int32_t* n_active) {
+    SDFC_CUDA(cudaSetDevice(p->ctx->device));
+    sdfc_status st = pair_single(p);
+    if (st != SDFC_OK) return st;
+    sdfc_batch* b = p->single;
+    cudaStream_t s = p->ctx->stream;
+    std::memcpy(b->h_in, E1, 16 * sizeof(double));
+    std::memcpy(b->h_in + 16, E2, 16 * sizeof(double));
+    std::memcpy(b->h_in + 32, phi1, 6 * sizeof(double));
+    std::memcpy(b->h_in + 38, phi2, 6 * sizeof(double));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, 32 * sizeof(double), cudaMemcpyHostToDevice, s));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_phi, b->h_in + 32, 12 * sizeof(double), cudaMemcpyHostToDevice, s));
+    st = batch_run(b, b->d_E, b->d_phi, deriv, /*scatter=*/false, nullptr, nullptr, nullptr, nullptr);
+    if (st != SDFC_OK) return st;
+    SDFC_CUDA(cudaMemcpyAsync(b->h_out, b->d_fm_sub, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (deriv) {
+        SDFC_CUDA(cudaMemcpyAsync(b->h_out + 12, b->d_Km_sub, 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SDFC_CUDA(cudaMemcpyAsync(b->h_out + 156, b->d_Dm_sub, 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    SDFC_CUDA(cudaMemcpyAsync(b->h_nact, b->d_n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SDFC_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(fm_sub, b->h_out, 12 * sizeof(double));
+    if (deriv) {
+        std::memcpy(Km_sub, b->h_out + 12, 144 * sizeof(double));
+        std::memcpy(Dm_sub, b->h_out + 156, 144 * sizeof(double));
+    }
+    if (n_active) *n_active = b->h_nact[0];
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_pair_force(sdfc_pair* p, const double E1[16], const double phi1[6], const double E2[16],
+                            const double phi2[6], double fm_sub[12], int32_t* n_active) {
+    SDFC_REQUIRE(p && E1 && phi1 && E2 && phi2 && fm_sub, "sdfc_pair_force: NULL argument");
+    return pair_eval(p, E1, phi1, E2, phi2, 0, fm_sub, nullptr, nullptr, n_active);
+}
+sdfc_status sdfc_pair_force_deriv(sdfc_pair* p, const double E1[16], const double phi1[6], const double E2[16],
+                                  const double phi2[6], double fm_sub[12], double Km_sub[144], double Dm_sub[144],
+                                  int32_t* n_active) {
+    SDFC_REQUIRE(p && E1 && phi1 && E2 && phi2 && fm_sub && Km_sub && Dm_sub, "sdfc_pair_force_deriv: NULL argument");
+    return pair_eval(p, E1, phi1, E2, phi2, 1, fm_sub, Km_sub, Dm_sub, n_active);
+}
+
+void sdfc_scatter_force(int idx_contact, int idx_sdf, const double fm_sub[12], double* fm_sys) {
+    for (int r = 0; r < 6; ++r) { fm_sys[idx_contact + r] += fm_sub[r]; fm_sys[idx_sdf + r] += fm_sub[6 + r]; }
+}
+void sdfc_scatter_deriv(int ndof_m, int idx_contact, int idx_sdf, const double Km_sub[144], const double Dm_sub[144],
+                        double* Km_sys, double* Dm_sys) {
+    const int idx[2] = {idx_contact, idx_sdf};
+    for (int br = 0; br < 2; ++br)       // same block order as ForceGeneralSDFContact.cpp:91-99
+        for (int bc = 0; bc < 2; ++bc)
+            for (int c = 0; c < 6; ++c)
+                for (int r = 0; r < 6; ++r) {
+                    const size_t dst = (size_t)(idx[br] + r) + (size_t)ndof_m * (size_t)(idx[bc] + c);
+                    const int src = (6 * br + r) + 12 * (6 * bc + c);
+                    Km_sys[dst] += Km_sub[src];
+                    Dm_sys[dst] += Dm_sub[src];
+                }
+}
+
+// ------------------------------------------------------------------ batch
+sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n_pairs, sdfc_pair* const* pairs,
+                              const int32_t* body_a, const int32_t* body_b, sdfc_batch** out) {
+    SDFC_REQUIRE(ctx && pairs && body_a && body_b && out, "sdfc_batch_create: NULL argument");
+    SDFC_REQUIRE(n_envs > 0 && n_bodies > 0 && n_pairs > 0, "sdfc_batch_create: sizes must be positive");
+    *out = nullptr;
+    for (int i = 0; i < n_pairs; ++i) {
+        SDFC_REQUIRE(pairs[i] && pairs[i]->ctx == ctx, "sdfc_batch_create: pair is NULL or from another context");
+        SDFC_REQUIRE(body_a[i] >= 0 && body_a[i] < n_bodies && body_b[i] >= 0 && body_b[i] < n_bodies,
+                     "sdfc_batch_create: body index out of range");
+    }
+    SDFC_CUDA(cudaSetDevice(ctx->device));
+    sdfc_batch* b = new sdfc_batch();
+    b->ctx = ctx; b->n_envs = n_envs; b->n_bodies = n_bodies; b->n_pairs = n_pairs;
+    b->pairs.assign(pairs, pairs + n_pairs);
+    b->body_a.assign(body_a, body_a + n_pairs);
+    b->body_b.assign(body_b, body_b + n_pairs);
+    b->seen_pair_version.assign(n_pairs, 0);
+    b->seen_sdf_version.assign(n_pairs, 0);
+
+    std::vector<int> tile_pair, tile_word0;
+    int words = 0, max_words = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int nw = (pairs[i]->pts->n + 31) / 32;
+        for (int w = 0; w < nw; w += kDetectTileWords) { tile_pair.push_back(i); tile_word0.push_back(w); }
+        words += nw;
+        max_words = std::max(max_words, nw);
+        b->queries += pairs[i]->pts->n;
+    }
+    b->queries *= n_envs;
+    const int target_ctas = 148 * 4;
+    int splits = (target_ctas + n_envs * n_pairs - 1) / (n_envs * n_pairs);
+    splits = std::max(1, std::min(splits, std::max(1, (max_words + 7) / 8)));
+    const size_t ep = (size_t)n_envs * n_pairs;
+    const int nm = 6 * n_bodies;
+
+    sdfc_status st = SDFC_OK;
+    auto A = [&](sdfc_status s) { if (st == SDFC_OK) st = s; };
+    A(dev_alloc(&b->d_pairs, (size_t)n_pairs));
+    A(dev_alloc(&b->d_tile_pair, tile_pair.size()));
+    A(dev_alloc(&b->d_tile_word0, tile_word0.size()));
+    A(dev_alloc(&b->d_mask, (size_t)n_envs * std::max(words, 1)));
+    A(dev_alloc(&b->d_n_active, ep));
+    A(dev_alloc(&b->d_partial, ep * splits * kPartialDerivDM));
+    A(dev_alloc(&b->d_fm_sub, ep * 12));
+    A(dev_alloc(&b->d_Km_sub, ep * 144));
+    A(dev_alloc(&b->d_Dm_sub, ep * 144));
+    A(dev_alloc(&b->d_E, (size_t)n_envs * n_bodies * 16));
+    A(dev_alloc(&b->d_phi, (size_t)n_envs * n_bodies * 6));
+    A(dev_alloc(&b->d_fm, (size_t)n_envs * nm));
+    A(dev_alloc(&b->d_Km, (size_t)n_envs * nm * nm));
+    A(dev_alloc(&b->d_Dm, (size_t)n_envs * nm * nm));
+    if (st == SDFC_OK) {
+        cudaError_t e = cudaMallocHost((void**)&b->h_in, sizeof(double) * (size_t)n_envs * n_bodies * 22);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&b->h_out, sizeof(double) * std::max((size_t)n_envs * (nm + 2 * (size_t)nm * nm), (size_t)300));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&b->h_nact, sizeof(int32_t) * ep);
+        if (e == cudaSuccess && !tile_pair.empty()) e = cudaMemcpy(b->d_tile_pair, tile_pair.data(), sizeof(int) * tile_pair.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && !tile_pair.empty()) e = cudaMemcpy(b->d_tile_word0, tile_word0.data(), sizeof(int) * tile_word0.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(b->d_mask, 0, sizeof(uint32_t) * (size_t)n_envs * std::max(words, 1));
+        if (e == cudaSuccess) e = cudaMemset(b->d_Dm_sub, 0, sizeof(double) * ep * 144);
+        if (e != cudaSuccess) st = fail(SDFC_ERR_CUDA, std::string("sdfc_batch_create: ") + cudaGetErrorString(e));
+    }
+    if (st != SDFC_OK) { sdfc_batch_destroy(b); return st; }
+    b->dev.pairs = b->d_pairs;
+    b->dev.n_pairs = n_pairs; b->dev.n_bodies = n_bodies; b->dev.n_envs = n_envs;
+    b->dev.words_per_env = std::max(words, 1);
+    b->dev.tile_pair = b->d_tile_pair; b->dev.tile_word0 = b->d_tile_word0;
+    b->dev.n_tiles = (int)tile_pair.size();
+    b->dev.splits = splits;
+    b->dev.mask = b->d_mask; b->dev.n_active = b->d_n_active; b->dev.partial = b->d_partial;
+    *out = b;
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
+    if (!b) return SDFC_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaFree(b->d_pairs); cudaFree(b->d_tile_pair); cudaFree(b->d_tile_word0); cudaFree(b->d_mask);
+    cudaFree(b->d_n_active); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
+    cudaFree(b->d_E); cudaFree(b->d_phi); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
+    if (b->h_in) cudaFreeHost(b->h_in);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->h_nact) cudaFreeHost(b->h_nact);
+    delete b;
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_eval_device(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, double* fm_dev,
+                                   double* Km_dev, double* Dm_dev, int32_t* n_active_dev) {
+    SDFC_REQUIRE(b && E_dev && phi_dev && fm_dev, "sdfc_batch_eval_device: NULL argument");
+    SDFC_REQUIRE(!deriv || Km_dev, "sdfc_batch_eval_device: Km_dev is NULL with deriv != 0");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    return batch_run(b, E_dev, phi_dev, deriv, /*scatter=*/true, fm_dev, Km_dev, deriv ? Dm_dev : nullptr, n_active_dev);
+}
+
+sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t* n_active_dev) {
+    SDFC_REQUIRE(b && E_dev, "sdfc_batch_detect_device: NULL argument");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    sdfc_status st = batch_refresh(b);
+    if (st != SDFC_OK) return st;
+    launch_detect_mask(b->dev, E_dev, b->ctx->stream);
+    b->ctx->launches += 1;
+    if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
+        SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
+                                  cudaMemcpyDeviceToDevice, b->ctx->stream));
+    SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* phi_host, int deriv, double* fm_out,
+                            double* Km_out, double* Dm_out, int32_t* n_active_out) {
+    SDFC_REQUIRE(b && E_host && phi_host && fm_out, "sdfc_batch_eval: NULL argument");
+    SDFC_REQUIRE(!deriv || (Km_out && Dm_out), "sdfc_batch_eval: Km_out/Dm_out NULL with deriv != 0");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t nE = (size_t)b->n_envs * b->n_bodies * 16, nP = (size_t)b->n_envs * b->n_bodies * 6;
+    const size_t nm = 6 * (size_t)b->n_bodies, nF = b->n_envs * nm, nK = b->n_envs * nm * nm;
+    std::memcpy(b->h_in, E_host, nE * sizeof(double));
+    std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, nE * sizeof(double), cudaMemcpyHostToDevice, s));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_phi, b->h_in + nE, nP * sizeof(double), cudaMemcpyHostToDevice, s));
+    sdfc_status st = batch_run(b, b->d_E, b->d_phi, deriv, /*scatter=*/true, b->d_fm, b->d_Km, deriv ? b->d_Dm : nullptr, nullptr);
+    if (st != SDFC_OK) return st;
+    SDFC_CUDA(cudaMemcpyAsync(b->h_out, b->d_fm, nF * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (deriv) {
+        SDFC_CUDA(cudaMemcpyAsync(b->h_out + nF, b->d_Km, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SDFC_CUDA(cudaMemcpyAsync(b->h_out + nF + nK, b->d_Dm, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    SDFC_CUDA(cudaMemcpyAsync(b->h_nact, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs, cudaMemcpyDeviceToHost, s));
+    SDFC_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(fm_out, b->h_out, nF * sizeof(double));
+    if (deriv) {
+        std::memcpy(Km_out, b->h_out + nF, nK * sizeof(double));
+        std::memcpy(Dm_out, b->h_out + nF + nK, nK * sizeof(double));
+    }
+    if (n_active_out) std::memcpy(n_active_out, b->h_nact, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs);
+    return SDFC_OK;
+}
+
+int64_t sdfc_batch_queries_per_eval(const sdfc_batch* b) { return b ? b->queries : 0; }
+
+}  // extern "C"

@@ -1,0 +1,688 @@
+// sdfc_device.cuh — device-side arithmetic of the SDF-contact hot path (sm_100a).
+//
+// Two groups of functions:
+//   * bit-critical: pose transforms, cell index, trilinear sample and the
+//     finite-difference stencils. They use only IEEE + - * / sqrt floor in the
+//     evaluation order the reference's x86-64 build executes (no FMA; the whole
+//     library is compiled with -fmad=false), so cell indices, active masks and
+//     per-point distances are bit-identical to the reference:
+//       Body/BodySDFObj.cpp:123-213,379-383, CollisionDetection.cpp:136-138.
+//   * contact algebra: BodySDFObj::collision (Body/BodySDFObj.cpp:239-377) and
+//     the per-contact terms of ForceGeneralSDFContact::computeForce
+//     [WithDerivative] (Force/ForceGeneralSDFContact.cpp:147-447), restated on
+//     fixed-size register arrays. Agreement target: 1e-9 relative (fp64).
+//
+// Paths are relative to simulation/redmax/ of the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cstdint>
+
+namespace sdfc {
+
+constexpr double kEps = 1e-8;     // constants::eps, Utils.h:9
+constexpr double kFdEps = 1e-5;   // BodySDFObj.cpp:178,191
+
+// Fields of BodySDFObj (Body/BodySDFObj.h:13-16) as the kernels see them.
+struct GridDev {
+    const double* g64;
+    const float* g32;  // fp32-lossless copy or nullptr
+    int ni, nj, nk;
+    double mn[3], mx[3];
+    double dx, dy, dz;
+    double col_th;
+};
+
+template <bool F32>
+__device__ __forceinline__ double grid_at(const GridDev& G, int i, int j, int k) {
+    const size_t idx = (size_t)i + (size_t)G.ni * ((size_t)j + (size_t)G.nj * (size_t)k);
+    if (F32) return (double)__ldg(G.g32 + idx);
+    return __ldg(G.g64 + idx);
+}
+
+// The 8 corners of cell (i,j,k) with the reference's upper clamp
+// (BodySDFObj.cpp:137-140). Index clamps to [0,n-1] only guard memory.
+template <bool F32>
+__device__ __forceinline__ void load_cell(const GridDev& G, int i, int j, int k, double v[8]) {
+    i = max(0, min(i, G.ni - 1)); j = max(0, min(j, G.nj - 1)); k = max(0, min(k, G.nk - 1));
+    const int ip = (i == G.ni - 1) ? i : i + 1;
+    const int jp = (j == G.nj - 1) ? j : j + 1;
+    const int kp = (k == G.nk - 1) ? k : k + 1;
+    v[0] = grid_at<F32>(G, i, j, k);   v[1] = grid_at<F32>(G, ip, j, k);
+    v[2] = grid_at<F32>(G, i, jp, k);  v[3] = grid_at<F32>(G, ip, jp, k);
+    v[4] = grid_at<F32>(G, i, j, kp);  v[5] = grid_at<F32>(G, ip, j, kp);
+    v[6] = grid_at<F32>(G, i, jp, kp); v[7] = grid_at<F32>(G, ip, jp, kp);
+}
+
+// Lerp order i, then j, then k; form (1-c)*a + c*b   (BodySDFObj.cpp:143-153)
+__device__ __forceinline__ double lerp8(const double v[8], double ci, double cj, double ck) {
+    const double v00 = (1 - ci) * v[0] + ci * v[1];
+    const double v10 = (1 - ci) * v[2] + ci * v[3];
+    const double v01 = (1 - ci) * v[4] + ci * v[5];
+    const double v11 = (1 - ci) * v[6] + ci * v[7];
+    const double w0 = (1 - cj) * v00 + cj * v10;
+    const double w1 = (1 - cj) * v01 + cj * v11;
+    return (1 - ck) * w0 + ck * w1;
+}
+
+__device__ __forceinline__ bool in_box(const GridDev& G, double x, double y, double z) {
+    return x >= G.mn[0] && x <= G.mx[0] && y >= G.mn[1] && y <= G.mx[1] && z >= G.mn[2] && z <= G.mx[2];
+}
+
+// A cell whose corners are held in registers: the 7 / 26 stencil samples of an
+// active contact lie within 1e-5 of x and almost always hit the same cell.
+struct CellCache {
+    int i, j, k;
+    double v[8];
+};
+
+// query_SDF for a point known to be inside the box (BodySDFObj.cpp:130-155).
+template <bool F32>
+__device__ __forceinline__ double sample_inside(const GridDev& G, double x, double y, double z,
+                                                const CellCache* cache) {
+    double ci = (x - G.mn[0]) / G.dx, cj = (y - G.mn[1]) / G.dy, ck = (z - G.mn[2]) / G.dz;
+    const int i = (int)floor(ci), j = (int)floor(cj), k = (int)floor(ck);
+    ci = ci - i; cj = cj - j; ck = ck - k;
+    if (cache != nullptr && i == cache->i && j == cache->j && k == cache->k) return lerp8(cache->v, ci, cj, ck);
+    double v[8];
+    load_cell<F32>(G, i, j, k, v);
+    return lerp8(v, ci, cj, ck);
+}
+
+// BodySDFObj::query_SDF(x, outside_accurate)   (BodySDFObj.cpp:123-174)
+template <bool F32>
+__device__ __forceinline__ double query_sdf(const GridDev& G, double x, double y, double z, bool outside_accurate,
+                                            const CellCache* cache) {
+    if (in_box(G, x, y, z)) return sample_inside<F32>(G, x, y, z, cache);
+    if (!outside_accurate) return (double)FLT_MAX;
+    // closest boundary point: std::min(std::max(x, min), max)
+    double bx = (x < G.mn[0]) ? G.mn[0] : x; bx = (G.mx[0] < bx) ? G.mx[0] : bx;
+    double by = (y < G.mn[1]) ? G.mn[1] : y; by = (G.mx[1] < by) ? G.mx[1] : by;
+    double bz = (z < G.mn[2]) ? G.mn[2] : z; bz = (G.mx[2] < bz) ? G.mx[2] : bz;
+    const double ex = x - bx, ey = y - by, ez = z - bz;
+    return sqrt((ex * ex + ey * ey) + ez * ez) + sample_inside<F32>(G, bx, by, bz, cache);
+}
+
+// xw = R*xi + p, rows evaluated left to right   (CollisionDetection.cpp:136)
+// R row-major 3x3.
+__device__ __forceinline__ void to_world(const double* R, const double* p, double x0, double x1, double x2,
+                                         double xw[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) xw[r] = ((R[r * 3] * x0 + R[r * 3 + 1] * x1) + R[r * 3 + 2] * x2) + p[r];
+}
+// x = R^T (xw - p)   (BodySDFObj.cpp:209-211)
+__device__ __forceinline__ void to_local(const double* R, const double* p, const double xw[3], double x[3]) {
+    const double d0 = xw[0] - p[0], d1 = xw[1] - p[1], d2 = xw[2] - p[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x[r] = (R[r] * d0 + R[3 + r] * d1) + R[6 + r] * d2;
+}
+
+// ------------------------------------------------------------ small algebra
+template <int R, int K, int C>
+__device__ __forceinline__ void mm(const double* A, const double* B, double* O) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            double s = A[r * K] * B[c];
+#pragma unroll
+            for (int k = 1; k < K; ++k) s = s + A[r * K + k] * B[k * C + c];
+            O[r * C + c] = s;
+        }
+}
+__device__ __forceinline__ void transpose3(const double* A, double* T) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[j * 3 + i] = A[i * 3 + j];
+}
+__device__ __forceinline__ void skew3(const double* v, double* S) {  // math::skew, Utils.h:25-33
+    S[0] = 0;     S[1] = -v[2]; S[2] = v[1];
+    S[3] = v[2];  S[4] = 0;     S[5] = -v[0];
+    S[6] = -v[1]; S[7] = v[0];  S[8] = 0;
+}
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+// Poses and parameters of one (environment, pair), staged in shared memory.
+struct PairPose {
+    double R1[9], p1[3], R2[9], p2[3];  // row-major rotations
+    double phi1[6], phi2[6];
+};
+struct PairParams {
+    double kn, kt, mu, damping;  // kn, kt already scaled by _scale * contact_scale (.cpp:155-156)
+};
+
+// Per-contact results are handed to a Sink as soon as they are final, so that a
+// warp can reduce them across its 32 contacts block by block instead of keeping
+// 156-300 doubles live per thread:
+//   sink.emitF(fm12)                value-only path: the 12 force entries
+//   sink.emitK<B>(k36, fm3)         derivative path: 6x6 block B of Km (row-major)
+//                                   plus force entries fm[3B..3B+2]
+//   sink.emitD<B>(d36)              6x6 block B of Dm (only when damping/friction)
+// Block order: 0 = (A,A) topLeft, 1 = (A,B) topRight, 2 = (B,A) bottomLeft, 3 = (B,B).
+// Every lane of the warp must reach every emit (they contain warp shuffles).
+
+// [skew(xi) * M ; M] for a 3xC matrix M : Gamma(xi)^T applied after R^T (Utils.h:196-201)
+template <int C>
+__device__ __forceinline__ void gamma_t_apply(const double* xi, const double* M, double* O /* 6xC */) {
+    double S[9];
+    skew3(xi, S);
+    mm<3, 3, C>(S, M, O);
+#pragma unroll
+    for (int i = 0; i < 3 * C; ++i) O[3 * C + i] = M[i];
+}
+
+// One contact: BodySDFObj::collision + the per-contact body of
+// ForceGeneralSDFContact::computeForce[WithDerivative].
+//   FRIC: mu > eps (friction block .cpp:198-217 / 352-445 evaluated)
+//   DAMP: damping != 0 (ddot and every Dm term are live)
+// Returns 1 static friction, 0 dynamic, -1 friction off.
+template <bool F32, bool DERIV, bool FRIC, bool DAMP, class Sink>
+__device__ __forceinline__ int contact_eval(const GridDev& G, const PairPose& P, const PairParams& prm,
+                                            const double xi1[3], Sink& sink) {
+    constexpr bool DM = FRIC || DAMP;
+    double fm[12];
+    // With friction the blocks are revisited after the normal-force part, so all
+    // of them stay live (spills); otherwise one block at a time.
+    double Kst[(DERIV && FRIC) ? 4 : 1][36], Dst[(DERIV && FRIC) ? 4 : 1][36];
+#define SDFC_KB(b) Kst[FRIC ? (b) : 0]
+#define SDFC_DB(b) Dst[FRIC ? (b) : 0]
+    const double* R1 = P.R1; const double* R2 = P.R2;
+    const double* w1 = P.phi1; const double* v1 = P.phi1 + 3;
+    const double* w2 = P.phi2; const double* v2 = P.phi2 + 3;
+    const double kn = prm.kn, kt = prm.kt, mu = prm.mu, cd = prm.damping;
+    double R1T[9], R2T[9];
+    transpose3(R1, R1T); transpose3(R2, R2T);
+
+    // ---- kinematics of the point (.cpp:158-160 / 238-240)
+    double xw1[3], x[3];
+    to_world(R1, P.p1, xi1[0], xi1[1], xi1[2], xw1);
+    to_local(R2, P.p2, xw1, x);
+    double u[3], xw1_dot[3];
+    if (FRIC || DAMP) {
+        double S1T[9], S1[9], t3[3];
+        skew3(xi1, S1); transpose3(S1, S1T);
+        mm<3, 3, 1>(S1T, w1, t3);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) u[a] = t3[a] + v1[a];
+        mm<3, 3, 1>(R1, u, xw1_dot);
+    }
+
+    // ---- SDF samples; the cell of x is cached in registers
+    CellCache cc;
+    {
+        const double ci = (x[0] - G.mn[0]) / G.dx, cj = (x[1] - G.mn[1]) / G.dy, ck = (x[2] - G.mn[2]) / G.dz;
+        cc.i = (int)floor(ci); cc.j = (int)floor(cj); cc.k = (int)floor(ck);
+        load_cell<F32>(G, cc.i, cc.j, cc.k, cc.v);
+    }
+    const double s0 = query_sdf<F32>(G, x[0], x[1], x[2], true, &cc);  // x is inside for an active contact
+    const double d = query_sdf<F32>(G, x[0], x[1], x[2], false, &cc) + G.col_th;
+    // query_dSDF (BodySDFObj.cpp:176-187); axis samples are reused by query_ddSDF
+    double qp[3], qm[3], g[3];
+    {
+        qp[0] = query_sdf<F32>(G, x[0] + kFdEps, x[1], x[2], true, &cc);
+        qm[0] = query_sdf<F32>(G, x[0] - kFdEps, x[1], x[2], true, &cc);
+        qp[1] = query_sdf<F32>(G, x[0], x[1] + kFdEps, x[2], true, &cc);
+        qm[1] = query_sdf<F32>(G, x[0], x[1] - kFdEps, x[2], true, &cc);
+        qp[2] = query_sdf<F32>(G, x[0], x[1], x[2] + kFdEps, true, &cc);
+        qm[2] = query_sdf<F32>(G, x[0], x[1], x[2] - kFdEps, true, &cc);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) g[a] = (qp[a] - qm[a]) / (2 * kFdEps);
+    }
+    const double gn = sqrt(dot3(g, g));
+    double e[3], n[3], xi2[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) e[a] = g[a] / gn;
+    mm<3, 3, 1>(R2, e, n);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) xi2[a] = x[a] - d * e[a];
+
+    double xdot[3], ddot = 0, u3[3], tdot[3], vw[3], s3[3], Pn[9];
+    if (FRIC || DAMP) {
+        double W2T[9], W2[9], t3[3];
+        skew3(w2, W2); transpose3(W2, W2T);
+        mm<3, 3, 1>(W2T, x, t3);
+        mm<3, 3, 1>(R2T, xw1_dot, u3);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xdot[a] = t3[a] + u3[a] - v2[a];
+        ddot = dot3(g, xdot);
+    }
+    if (FRIC) {
+        double wx[3], xw2_dot[3];
+        cross3(w2, xi2, wx);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) s3[a] = wx[a] + v2[a];
+        mm<3, 3, 1>(R2, s3, xw2_dot);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) vw[a] = xw1_dot[a] - xw2_dot[a];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Pn[r * 3 + c] = (r == c ? 1.0 : 0.0) - n[r] * n[c];
+        mm<3, 3, 1>(Pn, vw, tdot);
+    }
+
+    // ---- contact force (.cpp:176-188 / 293-330)
+    double a1[3], a2[3], ni1[6], ni2[6];
+    mm<3, 3, 1>(R1T, n, a1);
+    mm<3, 3, 1>(R2T, n, a2);
+    gamma_t_apply<1>(xi1, a1, ni1);
+    gamma_t_apply<1>(xi2, a2, ni2);
+    const double s1 = DAMP ? (-kn * d + cd * ddot * d) : (-kn * d);
+    const double s2 = DAMP ? (kn * d - cd * ddot * d) : (kn * d);
+    double fc1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { fc1[i] = s1 * ni1[i]; fm[i] = fc1[i]; fm[6 + i] = s2 * ni2[i]; }
+
+    int is_static = -1;
+    double fc_norm = 0, tdot_norm = 0, b1[3], b2[3], G1t[6], G2t[6];
+    if (FRIC) {
+        double s = fc1[0] * fc1[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) s = s + fc1[i] * fc1[i];
+        fc_norm = sqrt(s);
+        tdot_norm = sqrt(dot3(tdot, tdot));
+        is_static = (mu * fc_norm >= kt * tdot_norm - kEps) ? 1 : 0;
+        mm<3, 3, 1>(R1T, tdot, b1);
+        mm<3, 3, 1>(R2T, tdot, b2);
+        gamma_t_apply<1>(xi1, b1, G1t);
+        gamma_t_apply<1>(xi2, b2, G2t);
+        if (is_static) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { fm[i] += -kt * G1t[i]; fm[6 + i] += kt * G2t[i]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                fm[i] += -mu * fc_norm / tdot_norm * G1t[i];
+                fm[6 + i] += mu * fc_norm / tdot_norm * G2t[i];
+            }
+        }
+    }
+    if constexpr (!DERIV) {
+        sink.emitF(fm);
+        return is_static;
+    } else {
+    // ================= derivatives =================
+    // query_ddSDF (BodySDFObj.cpp:189-205)
+    double H[9];
+    {
+        const double h = kFdEps / 2;
+        H[0] = qp[0] + qm[0] - 2 * s0;
+        H[4] = qp[1] + qm[1] - 2 * s0;
+        H[8] = qp[2] + qm[2] - 2 * s0;
+        const double xy = query_sdf<F32>(G, x[0] + h, x[1] + h, x[2], true, &cc) + query_sdf<F32>(G, x[0] - h, x[1] - h, x[2], true, &cc)
+                        - query_sdf<F32>(G, x[0] + h, x[1] - h, x[2], true, &cc) - query_sdf<F32>(G, x[0] - h, x[1] + h, x[2], true, &cc);
+        const double xz = query_sdf<F32>(G, x[0] + h, x[1], x[2] + h, true, &cc) + query_sdf<F32>(G, x[0] - h, x[1], x[2] - h, true, &cc)
+                        - query_sdf<F32>(G, x[0] + h, x[1], x[2] - h, true, &cc) - query_sdf<F32>(G, x[0] - h, x[1], x[2] + h, true, &cc);
+        const double yz = query_sdf<F32>(G, x[0], x[1] + h, x[2] + h, true, &cc) + query_sdf<F32>(G, x[0], x[1] - h, x[2] - h, true, &cc)
+                        - query_sdf<F32>(G, x[0], x[1] + h, x[2] - h, true, &cc) - query_sdf<F32>(G, x[0], x[1] - h, x[2] + h, true, &cc);
+        H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] = H[i] / (kFdEps * kFdEps);
+    }
+
+    // ---- BodySDFObj::collision derivatives (BodySDFObj.cpp:314-376)
+    double Sx[9];
+    skew3(x, Sx);
+    double dd_dxw[3], dd_dq2[6];
+    mm<1, 3, 3>(g, R2T, dd_dxw);
+    mm<1, 3, 3>(g, Sx, dd_dq2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dd_dq2[3 + a] = -g[a];
+
+    double de_dx[9], de_dxw[9], de_dw2[9];
+    {
+        double de_dg[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) de_dg[i * 3 + c] = (gn * (i == c ? 1.0 : 0.0) - g[i] * g[c] / gn) / (gn * gn);
+        mm<3, 3, 3>(de_dg, H, de_dx);
+    }
+    mm<3, 3, 3>(de_dx, R2T, de_dxw);
+    mm<3, 3, 3>(de_dx, Sx, de_dw2);
+    double dn_dxw[9], dn_dq2[18];
+    mm<3, 3, 3>(R2, de_dxw, dn_dxw);
+    {
+        double A3[9], B3[9], nde[9];
+        mm<3, 3, 3>(R2, de_dw2, A3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double ek[3] = {0, 0, 0}, c3[3], r3[3];
+            ek[k] = 1;
+            cross3(ek, e, c3);
+            mm<3, 3, 1>(R2, c3, r3);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) A3[r * 3 + k] += r3[r];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nde[i] = -de_dx[i];
+        mm<3, 3, 3>(R2, nde, B3);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { dn_dq2[r * 6 + c] = A3[r * 3 + c]; dn_dq2[r * 6 + 3 + c] = B3[r * 3 + c]; }
+    }
+    double dxi2_dxw[9], dxi2_dq2[18];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            dxi2_dxw[r * 3 + c] = R2T[r * 3 + c] - e[r] * dd_dxw[c] - d * de_dxw[r * 3 + c];
+            dxi2_dq2[r * 6 + c] = Sx[r * 3 + c] - e[r] * dd_dq2[c] - d * de_dw2[r * 3 + c];
+            dxi2_dq2[r * 6 + 3 + c] = -(r == c ? 1.0 : 0.0) - e[r] * dd_dq2[3 + c] - d * (-de_dx[r * 3 + c]);
+        }
+
+    double dddot_dxw[3], dddot_dxwdot[3], dddot_dq2[6], dddot_dphi2[6];
+    if (DAMP || FRIC) {
+        double W2[9], W2T[9], gW2T[3], xH[3], t1[3];
+        skew3(w2, W2); transpose3(W2, W2T);
+        mm<1, 3, 3>(g, W2T, gW2T);
+        mm<1, 3, 3>(xdot, H, xH);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t1[a] = gW2T[a] + xH[a];
+        mm<1, 3, 3>(t1, R2T, dddot_dxw);
+        mm<1, 3, 3>(g, R2T, dddot_dxwdot);
+        double WS[9], Su[9], M9[9], gM[3], xHS[3], gW2[3];
+        mm<3, 3, 3>(W2, Sx, WS);
+        skew3(u3, Su);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M9[i] = -WS[i] + Su[i];
+        mm<1, 3, 3>(g, M9, gM);
+        mm<1, 3, 3>(xH, Sx, xHS);
+        mm<1, 3, 3>(g, W2, gW2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { dddot_dq2[a] = gM[a] + xHS[a]; dddot_dq2[3 + a] = gW2[a] + (-xH[a]); }
+        mm<1, 3, 3>(g, Sx, dddot_dphi2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dddot_dphi2[3 + a] = -g[a];
+    }
+
+    double dtdot_dxw[9], dtdot_dq2[18], dtdot_dphi2[18];  // dtdot_dxwdot == Pn
+    if (FRIC) {
+        double W2[9], RW[9], dxw2dot_dxw[9], dxw2dot_dq2[18], dxw2dot_dphi2[18];
+        skew3(w2, W2);
+        mm<3, 3, 3>(R2, W2, RW);
+        mm<3, 3, 3>(RW, dxi2_dxw, dxw2dot_dxw);
+        {
+            double Ss[9], RS[9], L6[18];
+            skew3(s3, Ss);
+            mm<3, 3, 3>(R2, Ss, RS);
+            mm<3, 3, 6>(RW, dxi2_dq2, L6);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    dxw2dot_dq2[r * 6 + c] = -RS[r * 3 + c] + L6[r * 6 + c];
+                    dxw2dot_dq2[r * 6 + 3 + c] = L6[r * 6 + 3 + c];
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double ek[3] = {0, 0, 0}, c3[3], r3[3];
+            ek[k] = 1;
+            cross3(ek, xi2, c3);
+            mm<3, 3, 1>(R2, c3, r3);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { dxw2dot_dphi2[r * 6 + k] = r3[r]; dxw2dot_dphi2[r * 6 + 3 + k] = R2[r * 3 + k]; }
+        }
+        const double nvw = dot3(n, vw);
+        double vdn[3], ndx[3], vdq[6], ndq[6], neg[18];
+        mm<1, 3, 3>(vw, dn_dxw, vdn);
+        mm<1, 3, 3>(n, dxw2dot_dxw, ndx);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                dtdot_dxw[r * 3 + c] = -dxw2dot_dxw[r * 3 + c] - nvw * dn_dxw[r * 3 + c] - n[r] * vdn[c] + n[r] * ndx[c];
+        mm<1, 3, 6>(vw, dn_dq2, vdq);
+        mm<1, 3, 6>(n, dxw2dot_dq2, ndq);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                dtdot_dq2[r * 6 + c] = -dxw2dot_dq2[r * 6 + c] - nvw * dn_dq2[r * 6 + c] - n[r] * (vdq[c] - ndq[c]);
+#pragma unroll
+        for (int i = 0; i < 18; ++i) neg[i] = -dxw2dot_dphi2[i];
+        mm<3, 3, 6>(Pn, neg, dtdot_dphi2);
+    }
+
+    // ---- chain rule to q1 / phi1 (.cpp:242-252, 269, 305-310)
+    double dxw1_dq1[18];
+    {
+        double S1[9], RS[9];
+        skew3(xi1, S1);
+        mm<3, 3, 3>(R1, S1, RS);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { dxw1_dq1[r * 6 + k] = -RS[r * 3 + k]; dxw1_dq1[r * 6 + 3 + k] = R1[r * 3 + k]; }
+    }
+    double dxw1dot_dq1[18], dxw1dot_dphi1[18];
+    if (DAMP || FRIC) {
+        double Su[9], RSu[9], S1[9], S1T[9], RST[9];
+        skew3(u, Su);
+        mm<3, 3, 3>(R1, Su, RSu);
+        skew3(xi1, S1); transpose3(S1, S1T);
+        mm<3, 3, 3>(R1, S1T, RST);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dxw1dot_dq1[r * 6 + k] = -RSu[r * 3 + k];  dxw1dot_dq1[r * 6 + 3 + k] = 0;
+                dxw1dot_dphi1[r * 6 + k] = RST[r * 3 + k]; dxw1dot_dphi1[r * 6 + 3 + k] = R1[r * 3 + k];
+            }
+    }
+    double dxi2_dq1[18], dd_dq1[6], dn_dq1[18];
+    mm<3, 3, 6>(dxi2_dxw, dxw1_dq1, dxi2_dq1);
+    mm<1, 3, 6>(dd_dxw, dxw1_dq1, dd_dq1);
+    mm<3, 3, 6>(dn_dxw, dxw1_dq1, dn_dq1);
+    double dddot_dq1[6], dddot_dphi1[6];
+    if (DAMP || FRIC) {
+        double a6[6], b6[6];
+        mm<1, 3, 6>(dddot_dxw, dxw1_dq1, a6);
+        mm<1, 3, 6>(dddot_dxwdot, dxw1dot_dq1, b6);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dddot_dq1[i] = a6[i] + b6[i];
+        mm<1, 3, 6>(dddot_dxwdot, dxw1dot_dphi1, dddot_dphi1);
+    }
+    double dtdot_dq1[18], dtdot_dphi1[18];
+    if (FRIC) {
+        double m18a[18], m18b[18];
+        mm<3, 3, 6>(dtdot_dxw, dxw1_dq1, m18a);
+        mm<3, 3, 6>(Pn, dxw1dot_dq1, m18b);
+#pragma unroll
+        for (int i = 0; i < 18; ++i) dtdot_dq1[i] = m18a[i] + m18b[i];
+        mm<3, 3, 6>(Pn, dxw1dot_dphi1, dtdot_dphi1);
+    }
+
+    // ---- normal-force Jacobians (.cpp:312-349)
+    double rq1[6], rq2[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (DAMP) {
+            rq1[i] = kn * dd_dq1[i] - cd * dddot_dq1[i] * d - cd * ddot * dd_dq1[i];
+            rq2[i] = kn * dd_dq2[i] - cd * dddot_dq2[i] * d - cd * ddot * dd_dq2[i];
+        } else {
+            rq1[i] = kn * dd_dq1[i];
+            rq2[i] = kn * dd_dq2[i];
+        }
+    }
+    {
+        double N[18], GN[36], Sa[9], Gs[18];
+        // K11 = -ni1 rq1 - s2 G1 dn_dq1 ; leftCols(3) -= s2 Gamma1^T skew(R1^T n)
+        mm<3, 3, 6>(R1T, dn_dq1, N);
+        gamma_t_apply<6>(xi1, N, GN);
+        skew3(a1, Sa);
+        gamma_t_apply<3>(xi1, Sa, Gs);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double v = -ni1[r] * rq1[k] - s2 * GN[r * 6 + k];
+                if (k < 3) v -= s2 * Gs[r * 3 + k];
+                SDFC_KB(0)[r * 6 + k] = v;
+            }
+        if constexpr (!FRIC) sink.template emitK<0>(SDFC_KB(0), fm + 0);
+        // K12 = -ni1 rq2 - s2 G1 dn_dq2
+        mm<3, 3, 6>(R1T, dn_dq2, N);
+        gamma_t_apply<6>(xi1, N, GN);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) SDFC_KB(1)[r * 6 + k] = -ni1[r] * rq2[k] - s2 * GN[r * 6 + k];
+        if constexpr (!FRIC) sink.template emitK<1>(SDFC_KB(1), fm + 3);
+        // K21 = ni2 rq1 + s2 (tmp1 + G2 dn_dq1), tmp.col(j) = [dxi2_dq.col(j) x a2 ; 0]  (.cpp:275-291,333-338)
+        mm<3, 3, 6>(R2T, dn_dq1, N);
+        gamma_t_apply<6>(xi2, N, GN);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double c1[3] = {dxi2_dq1[k], dxi2_dq1[6 + k], dxi2_dq1[12 + k]}, r1[3];
+            cross3(c1, a2, r1);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const double t = (r < 3) ? r1[r % 3] : 0.0;
+                SDFC_KB(2)[r * 6 + k] = ni2[r] * rq1[k] + s2 * (t + GN[r * 6 + k]);
+            }
+        }
+        if constexpr (!FRIC) sink.template emitK<2>(SDFC_KB(2), fm + 6);
+        // K22 = ni2 rq2 + s2 (tmp2 + G2 dn_dq2); leftCols(3) += s2 Gamma2^T skew(R2^T n)
+        mm<3, 3, 6>(R2T, dn_dq2, N);
+        gamma_t_apply<6>(xi2, N, GN);
+        skew3(a2, Sa);
+        gamma_t_apply<3>(xi2, Sa, Gs);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double c2[3] = {dxi2_dq2[k], dxi2_dq2[6 + k], dxi2_dq2[12 + k]}, r2[3];
+            cross3(c2, a2, r2);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const double t = (r < 3) ? r2[r % 3] : 0.0;
+                double v = ni2[r] * rq2[k] + s2 * (t + GN[r * 6 + k]);
+                if (k < 3) v += s2 * Gs[r * 3 + k];
+                SDFC_KB(3)[r * 6 + k] = v;
+            }
+        }
+        if constexpr (!FRIC) sink.template emitK<3>(SDFC_KB(3), fm + 9);
+    }
+    if constexpr (DM) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double* nn = (b < 2) ? ni1 : ni2;
+            const double* dp = (b & 1) ? dddot_dphi2 : dddot_dphi1;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const double t = nn[r] * cd * dp[k] * d;
+                    SDFC_DB(b)[r * 6 + k] = (b < 2) ? t : -t;
+                }
+            if constexpr (!FRIC) {
+                if (b == 0) sink.template emitD<0>(SDFC_DB(0));
+                if (b == 1) sink.template emitD<1>(SDFC_DB(1));
+                if (b == 2) sink.template emitD<2>(SDFC_DB(2));
+                if (b == 3) sink.template emitD<3>(SDFC_DB(3));
+            }
+        }
+    }
+    // ---- friction Jacobians (.cpp:352-445)
+    if constexpr (FRIC) {
+        // d|fc1|/d*, d|tdot|/d* : (1/norm) * (vec^T * Jac)
+        double dfn[4][6], dtn[4][6];
+        {
+            double r6[6];
+            mm<1, 6, 6>(fc1, Kst[0], r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dfn[0][i] = (1. / fc_norm) * r6[i];
+            mm<1, 6, 6>(fc1, Kst[1], r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dfn[1][i] = (1. / fc_norm) * r6[i];
+            mm<1, 6, 6>(fc1, Dst[0], r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dfn[2][i] = (1. / fc_norm) * r6[i];
+            mm<1, 6, 6>(fc1, Dst[1], r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dfn[3][i] = (1. / fc_norm) * r6[i];
+            mm<1, 3, 6>(tdot, dtdot_dq1, r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dtn[0][i] = (1. / tdot_norm) * r6[i];
+            mm<1, 3, 6>(tdot, dtdot_dq2, r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dtn[1][i] = (1. / tdot_norm) * r6[i];
+            mm<1, 3, 6>(tdot, dtdot_dphi1, r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dtn[2][i] = (1. / tdot_norm) * r6[i];
+            mm<1, 3, 6>(tdot, dtdot_dphi2, r6);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dtn[3][i] = (1. / tdot_norm) * r6[i];
+        }
+        const double* J[4] = {dtdot_dq1, dtdot_dq2, dtdot_dphi1, dtdot_dphi2};
+        const double ratio = fc_norm / tdot_norm;
+        const double coefA = is_static ? kt : (mu / tdot_norm);         // multiplies G * inner
+        const double coefT = is_static ? kt : (mu * fc_norm / tdot_norm);  // multiplies tmp (dGamma2 terms)
+        const double coefS = is_static ? kt : mu;                       // multiplies Gamma^T skew(.)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {  // 0: dq1, 1: dq2, 2: dphi1, 3: dphi2
+            double inner[18], N[18], GN1[36], GN2[36];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (is_static) inner[r * 6 + k] = J[v][r * 6 + k];
+                    else inner[r * 6 + k] = tdot[r] * dfn[v][k] - ratio * tdot[r] * dtn[v][k] + fc_norm * J[v][r * 6 + k];
+                }
+            mm<3, 3, 6>(R1T, inner, N);
+            gamma_t_apply<6>(xi1, N, GN1);
+            mm<3, 3, 6>(R2T, inner, N);
+            gamma_t_apply<6>(xi2, N, GN2);
+            double* top = (v < 2) ? Kst[v] : Dst[v - 2];          // (A, .) blocks
+            double* bot = (v < 2) ? Kst[2 + v] : Dst[2 + (v - 2)];  // (B, .) blocks
+#pragma unroll
+            for (int i = 0; i < 36; ++i) { top[i] -= coefA * GN1[i]; bot[i] += coefA * GN2[i]; }
+        }
+        // dGamma2 terms on the SDF body's rows (.cpp:402-412, 422-436)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double c1[3] = {dxi2_dq1[k], dxi2_dq1[6 + k], dxi2_dq1[12 + k]}, c2[3] = {dxi2_dq2[k], dxi2_dq2[6 + k], dxi2_dq2[12 + k]};
+            double r1[3], r2[3];
+            cross3(c1, b2, r1); cross3(c2, b2, r2);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { Kst[2][r * 6 + k] += coefT * r1[r]; Kst[3][r * 6 + k] += coefT * r2[r]; }
+        }
+        // Gamma^T skew(R^T tdot [* ratio]) on leftCols(3) (.cpp:372,413 / 385-386,437-438)
+        double sb1[3], sb2[3], Sa[9], Gs[18];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { sb1[a] = is_static ? b1[a] : ratio * b1[a]; sb2[a] = is_static ? b2[a] : ratio * b2[a]; }
+        skew3(sb1, Sa);
+        gamma_t_apply<3>(xi1, Sa, Gs);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Kst[0][r * 6 + k] -= coefS * Gs[r * 3 + k];
+        skew3(sb2, Sa);
+        gamma_t_apply<3>(xi2, Sa, Gs);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Kst[3][r * 6 + k] += coefS * Gs[r * 3 + k];
+        sink.template emitK<0>(Kst[0], fm + 0);
+        sink.template emitK<1>(Kst[1], fm + 3);
+        sink.template emitK<2>(Kst[2], fm + 6);
+        sink.template emitK<3>(Kst[3], fm + 9);
+        sink.template emitD<0>(Dst[0]);
+        sink.template emitD<1>(Dst[1]);
+        sink.template emitD<2>(Dst[2]);
+        sink.template emitD<3>(Dst[3]);
+    }
+    return is_static;
+    }  // DERIV
+#undef SDFC_KB
+#undef SDFC_DB
+}
+
+}  // namespace sdfc

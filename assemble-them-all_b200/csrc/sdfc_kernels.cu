@@ -1,0 +1,535 @@
+// sdfc_kernels.cu — sm_100a kernels of the SDF-contact hot path.
+//
+//   k_detect_mask   LOOP C (collision_detection_general_SDF, CollisionDetection.cpp:124-147)
+//                   for E environments x P pairs: one 1-bit/pt active mask word per
+//                   warp-load of 32 points + an integer contact count per (env, pair).
+//   k_force         LOOP D (ForceGeneralSDFContact.cpp:147-447): compacts the mask in
+//                   shared memory, evaluates each active contact on one lane, reduces
+//                   the 12 / 156 / 300 outputs across the warp with a register
+//                   transpose-reduce, then across warps in a fixed order.
+//   k_reduce_splits / k_scatter_system   fixed-order sums -> per-pair blocks and the
+//                   per-environment system arrays (the += of .cpp:60-61,88-99).
+//   k_query_points  per-point d / cell / active in original order (parity + sweep entry).
+//   k_sdf_distance  raw trilinear sampling (SDFMesh::distance, Mesh.cpp:143-198).
+//
+// HBM-bound integer/fp64 work: no tensor cores. Points are read as coalesced SoA
+// fp64; grid corners are gathered through L1/L2 (fp32-lossless copy when legal).
+// Reductions are fixed-tree (no floating-point atomics): results are reproducible.
+// Compiled with -fmad=false (see sdfc_device.cuh).
+#include "sdfc_kernels.cuh"
+
+namespace sdfc {
+
+// --------------------------------------------------------------------------
+// register transpose-reduce across the 32 lanes of a warp
+// --------------------------------------------------------------------------
+// Every lane holds N values; afterwards lane L holds tr_out(N) values, each the
+// sum over all 32 lanes of one original entry (entry = tr_index<N>(L, j)). Each
+// step exchanges half of the remaining values with the lane at distance MASK, so
+// the cost is ~N shuffles instead of 5N for N independent butterfly sums.
+template <int N, int MASK>
+struct TransposeReduce {
+    static __device__ __forceinline__ void run(double* v, unsigned lane) {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & MASK) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const double lo = v[i];
+            const double hi = (H + i < N) ? v[H + i] : 0.0;
+            const double send = up ? lo : hi;
+            const double keep = up ? hi : lo;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+        }
+        TransposeReduce<H, MASK / 2>::run(v, lane);
+    }
+};
+template <int N>
+struct TransposeReduce<N, 0> {
+    static __device__ __forceinline__ void run(double*, unsigned) {}
+};
+
+// Original entry held by (lane, j) after TransposeReduce<N,16>, or -1 for padding.
+template <int N>
+__host__ __device__ inline int tr_index(int lane, int j) {
+    int sizes[6];
+    sizes[0] = N;
+    for (int s = 0; s < 5; ++s) sizes[s + 1] = (sizes[s] + 1) / 2;
+    int rel = j;
+    if (rel >= sizes[5]) return -1;
+    for (int s = 4; s >= 0; --s) {
+        if (lane & (16 >> s)) rel += sizes[s + 1];
+        if (rel >= sizes[s]) return -1;
+    }
+    return rel;
+}
+
+// Sink handed to contact_eval: reduces each emitted block across the warp at once.
+template <bool DERIV, bool DM>
+struct WarpSink {
+    double accK[DERIV ? 4 : 1][kOutK];
+    double accD[(DERIV && DM) ? 4 : 1][kOutD];
+    double accF[kOutF];
+    unsigned lane;
+    bool valid;  // false: this lane re-evaluates a valid contact but contributes zeros
+
+    __device__ __forceinline__ void init(unsigned l) {
+        lane = l;
+        valid = false;
+#pragma unroll
+        for (int b = 0; b < (DERIV ? 4 : 1); ++b)
+#pragma unroll
+            for (int j = 0; j < kOutK; ++j) accK[b][j] = 0.0;
+#pragma unroll
+        for (int b = 0; b < ((DERIV && DM) ? 4 : 1); ++b)
+#pragma unroll
+            for (int j = 0; j < kOutD; ++j) accD[b][j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < kOutF; ++j) accF[j] = 0.0;
+    }
+    __device__ __forceinline__ void emitF(const double* fm12) {
+        double v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = valid ? fm12[i] : 0.0;
+        TransposeReduce<12, 16>::run(v, lane);
+#pragma unroll
+        for (int j = 0; j < kOutF; ++j) accF[j] += v[j];
+    }
+    template <int B>
+    __device__ __forceinline__ void emitK(const double* k36, const double* fm3) {
+        double v[39];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) v[i] = valid ? k36[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[36 + i] = valid ? fm3[i] : 0.0;
+        TransposeReduce<39, 16>::run(v, lane);
+#pragma unroll
+        for (int j = 0; j < kOutK; ++j) accK[DERIV ? B : 0][j] += v[j];
+    }
+    template <int B>
+    __device__ __forceinline__ void emitD(const double* d36) {
+        double v[36];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) v[i] = valid ? d36[i] : 0.0;
+        TransposeReduce<36, 16>::run(v, lane);
+#pragma unroll
+        for (int j = 0; j < kOutD; ++j) accD[(DERIV && DM) ? B : 0][j] += v[j];
+    }
+};
+
+// Pose of (env, body) from column-major E[env][body][16] into row-major R, p.
+__device__ __forceinline__ void stage_pose(const double* E, int n_bodies, int env, int body, double* R, double* p,
+                                           int t) {
+    // t in [0, 12): element (r, c) of the top 3x4
+    const int r = t % 3, c = t / 3;
+    const double v = __ldg(E + ((size_t)env * n_bodies + body) * 16 + r + 4 * c);
+    if (c < 3) R[r * 3 + c] = v; else p[r] = v;
+}
+
+// --------------------------------------------------------------------------
+// detection
+// --------------------------------------------------------------------------
+template <bool F32>
+__device__ __forceinline__ double detect_point(const GridDev& G, const double* R1, const double* p1, const double* R2,
+                                               const double* p2, double x0, double x1, double x2) {
+    double xw[3], x[3];
+    to_world(R1, p1, x0, x1, x2, xw);
+    to_local(R2, p2, xw, x);
+    return query_sdf<F32>(G, x[0], x[1], x[2], false, nullptr) + G.col_th;  // BodySDFObj.cpp:212
+}
+
+template <bool F32>
+__device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
+                                            const double* p2, int word0, uint32_t* mask_row, int* s_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt = 0;
+    double px[kDetectWordsPerWarp], py[kDetectWordsPerWarp], pz[kDetectWordsPerWarp];
+    bool inr[kDetectWordsPerWarp];
+#pragma unroll
+    for (int u = 0; u < kDetectWordsPerWarp; ++u) {  // issue all point loads first
+        const int w = word0 + warp * kDetectWordsPerWarp + u;
+        const int idx = w * 32 + lane;
+        inr[u] = (w < pd.n_words) && (idx < pd.n);
+        px[u] = inr[u] ? __ldg(pd.sx + idx) : 0.0;
+        py[u] = inr[u] ? __ldg(pd.sy + idx) : 0.0;
+        pz[u] = inr[u] ? __ldg(pd.sz + idx) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kDetectWordsPerWarp; ++u) {
+        const int w = word0 + warp * kDetectWordsPerWarp + u;
+        bool act = false;
+        if (inr[u]) act = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]) < 0.;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (w < pd.n_words && lane == 0) { mask_row[pd.word_offset + w] = m; cnt += __popc(m); }
+    }
+    if (lane == 0 && cnt) atomicAdd(s_count, cnt);
+}
+
+__global__ void __launch_bounds__(kDetectThreads) k_detect_mask(BatchDev B, const double* __restrict__ E) {
+    __shared__ PairDev pd;
+    __shared__ double R1[9], p1[3], R2[9], p2[3];
+    __shared__ int s_count;
+    const int tile = blockIdx.x, env = blockIdx.y;
+    const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
+    {
+        const int* src = reinterpret_cast<const int*>(B.pairs + pair);
+        int* dst = reinterpret_cast<int*>(&pd);
+        for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) s_count = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) stage_pose(E, B.n_bodies, env, pd.body_a, R1, p1, threadIdx.x);
+    else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
+    __syncthreads();
+    uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
+    if (pd.grid.g32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
+    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+}
+
+void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream) {
+    cudaMemsetAsync(B.n_active, 0, sizeof(int32_t) * (size_t)B.n_envs * B.n_pairs, stream);
+    dim3 grid(B.n_tiles, B.n_envs);
+    k_detect_mask<<<grid, kDetectThreads, 0, stream>>>(B, E);
+}
+
+// --------------------------------------------------------------------------
+// force
+// --------------------------------------------------------------------------
+struct ForceShared {
+    PairDev pd;
+    PairPose pose;
+    int warp_tot[kNumWarps];
+    int ids[kForceThreads * 32];
+};
+
+template <bool F32, bool DERIV, bool FRIC, bool DAMP, class Sink>
+__device__ __forceinline__ void force_rounds(const ForceShared& S, int total, Sink& sink) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = warp * 32; base < total; base += kForceThreads) {
+        const int c = base + lane;
+        sink.valid = c < total;
+        const int id = S.ids[sink.valid ? c : base];
+        const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
+        contact_eval<F32, DERIV, FRIC, DAMP>(S.pd.grid, S.pose, S.pd.prm, xi1, sink);
+    }
+}
+
+template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
+__global__ void __launch_bounds__(kForceThreads) k_force(BatchDev B, const double* __restrict__ E,
+                                                         const double* __restrict__ phi) {
+    constexpr bool DM = ANYFRIC || ANYDAMP;
+    constexpr int NPART = DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ForceShared& S = *reinterpret_cast<ForceShared*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + sizeof(ForceShared));  // [kNumWarps][NPART]
+
+    const int env = blockIdx.y;
+    const int pair = blockIdx.x / B.splits, split = blockIdx.x % B.splits;
+    if (__ldg(B.n_active + (size_t)env * B.n_pairs + pair) == 0) return;  // CTA-uniform
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const int* src = reinterpret_cast<const int*>(B.pairs + pair);
+        int* dst = reinterpret_cast<int*>(&S.pd);
+        for (int i = tid; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (tid < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, tid);
+    else if (tid >= 32 && tid < 44) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, tid - 32);
+    else if (tid >= 64 && tid < 70) S.pose.phi1[tid - 64] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + tid - 64);
+    else if (tid >= 96 && tid < 102) S.pose.phi2[tid - 96] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + tid - 96);
+
+    WarpSink<DERIV, DM> sink;
+    sink.init(lane);
+
+    const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
+    const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
+    const uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
+    const bool f32 = S.pd.grid.g32 != nullptr;
+    const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
+    const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
+
+    for (int tw = w0; tw < w1; tw += kForceThreads) {
+        __syncthreads();  // poses staged / previous tile's ids consumed
+        uint32_t word = (tw + tid < w1) ? __ldg(mask_row + tw + tid) : 0u;
+        const int cnt = __popc(word);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) S.warp_tot[warp] = incl;
+        __syncthreads();
+        int off = incl - cnt, total = 0;
+#pragma unroll
+        for (int w = 0; w < kNumWarps; ++w) {
+            const int t = S.warp_tot[w];
+            if (w < warp) off += t;
+            total += t;
+        }
+        while (word) {
+            const int b = __ffs(word) - 1;
+            S.ids[off++] = (tw + tid) * 32 + b;
+            word &= word - 1;
+        }
+        __syncthreads();
+        if (total == 0) continue;
+        // CTA-uniform variant dispatch (template flags prune what cannot occur)
+        if (f32) {
+            if (fric) { if (damp) force_rounds<true, DERIV, ANYFRIC, ANYDAMP>(S, total, sink); else force_rounds<true, DERIV, ANYFRIC, false>(S, total, sink); }
+            else      { if (damp) force_rounds<true, DERIV, false, ANYDAMP>(S, total, sink);  else force_rounds<true, DERIV, false, false>(S, total, sink); }
+        } else {
+            if (fric) { if (damp) force_rounds<false, DERIV, ANYFRIC, ANYDAMP>(S, total, sink); else force_rounds<false, DERIV, ANYFRIC, false>(S, total, sink); }
+            else      { if (damp) force_rounds<false, DERIV, false, ANYDAMP>(S, total, sink);  else force_rounds<false, DERIV, false, false>(S, total, sink); }
+        }
+    }
+
+    // cross-warp combine in fixed order
+    double* mine = red + (size_t)warp * NPART;
+    if (DERIV) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int j = 0; j < kOutK; ++j) mine[(b * kOutK + j) * 32 + lane] = sink.accK[DERIV ? b : 0][j];
+        if (DM) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int j = 0; j < kOutD; ++j)
+                    mine[kPartialDeriv + (b * kOutD + j) * 32 + lane] = sink.accD[(DERIV && DM) ? b : 0][j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kOutF; ++j) mine[j * 32 + lane] = sink.accF[j];
+    }
+    __syncthreads();
+    double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * NPART;
+    for (int i = tid; i < NPART; i += kForceThreads) {
+        double s = red[i];
+#pragma unroll
+        for (int w = 1; w < kNumWarps; ++w) s += red[(size_t)w * NPART + i];
+        out[i] = s;
+    }
+}
+
+template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
+static void launch_force_t(const BatchDev& B, const double* E, const double* phi, cudaStream_t stream) {
+    constexpr bool DM = ANYFRIC || ANYDAMP;
+    constexpr int NPART = DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    const size_t smem = sizeof(ForceShared) + sizeof(double) * kNumWarps * NPART;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_force<DERIV, ANYFRIC, ANYDAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid(B.n_pairs * B.splits, B.n_envs);
+    k_force<DERIV, ANYFRIC, ANYDAMP><<<grid, kForceThreads, smem, stream>>>(B, E, phi);
+}
+
+void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
+                  cudaStream_t stream) {
+    if (deriv) {
+        if (any_fric) { if (any_damp) launch_force_t<true, true, true>(B, E, phi, stream); else launch_force_t<true, true, false>(B, E, phi, stream); }
+        else          { if (any_damp) launch_force_t<true, false, true>(B, E, phi, stream); else launch_force_t<true, false, false>(B, E, phi, stream); }
+    } else {
+        if (any_fric) { if (any_damp) launch_force_t<false, true, true>(B, E, phi, stream); else launch_force_t<false, true, false>(B, E, phi, stream); }
+        else          { if (any_damp) launch_force_t<false, false, true>(B, E, phi, stream); else launch_force_t<false, false, false>(B, E, phi, stream); }
+    }
+}
+
+// --------------------------------------------------------------------------
+// finalize: split partials -> per-pair blocks -> system arrays
+// --------------------------------------------------------------------------
+// Per-pair block layout (natural): fm_sub[12], Km_sub[144] col-major, Dm_sub[144] col-major.
+__global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restrict__ fm_sub, double* __restrict__ Km_sub,
+                                double* __restrict__ Dm_sub) {
+    const int pair = blockIdx.x, env = blockIdx.y;
+    const size_t ep = (size_t)env * B.n_pairs + pair;
+    const bool empty = B.n_active[ep] == 0;
+    const int npart = deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    const double* part = B.partial + ep * B.splits * npart;
+    for (int slot = threadIdx.x; slot < npart; slot += blockDim.x) {
+        double s = 0.0;
+        if (!empty)
+            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * npart + slot];
+        const int lane = slot & 31;
+        if (!deriv) {
+            const int e = tr_index<12>(lane, slot >> 5);
+            if (e >= 0) fm_sub[ep * 12 + e] = s;
+        } else if (slot < kPartialDeriv) {
+            const int b = (slot >> 5) / kOutK, j = (slot >> 5) % kOutK;
+            const int e = tr_index<39>(lane, j);
+            if (e >= 36) fm_sub[ep * 12 + 3 * b + (e - 36)] = s;
+            else if (e >= 0) {
+                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
+                Km_sub[ep * 144 + r + 12 * c] = s;
+            }
+        } else {
+            const int q = (slot - kPartialDeriv) >> 5;
+            const int b = q / kOutD, j = q % kOutD;
+            const int e = tr_index<36>(lane, j);
+            if (e >= 0) {
+                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
+                Dm_sub[ep * 144 + r + 12 * c] = s;
+            }
+        }
+    }
+    if (deriv && !dm && Dm_sub != nullptr)
+        for (int i = threadIdx.x; i < 144; i += blockDim.x) Dm_sub[ep * 144 + i] = 0.0;
+}
+
+// Gather form of the reference's scatter (.cpp:60-61,88-99): one thread per system
+// entry walks the pairs in force order, so the accumulation order is the reference's.
+__global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict__ fm_sub,
+                                 const double* __restrict__ Km_sub, const double* __restrict__ Dm_sub,
+                                 double* __restrict__ fm, double* __restrict__ Km, double* __restrict__ Dm) {
+    const int env = blockIdx.x;
+    const int nm = 6 * B.n_bodies;
+    const size_t e0 = (size_t)env * B.n_pairs;
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+        const int body = i / 6, r = i % 6;
+        double s = 0.0;
+        for (int p = 0; p < B.n_pairs; ++p) {
+            const int a = B.pairs[p].body_a, b = B.pairs[p].body_b;
+            if (a == body) s += fm_sub[(e0 + p) * 12 + r];
+            if (b == body) s += fm_sub[(e0 + p) * 12 + 6 + r];
+        }
+        fm[(size_t)env * nm + i] = s;
+    }
+    if (!deriv) return;
+    for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) {
+        const int R = i % nm, C = i / nm;  // column-major
+        const int bR = R / 6, r = R % 6, bC = C / 6, c = C % 6;
+        double sk = 0.0, sd = 0.0;
+        for (int p = 0; p < B.n_pairs; ++p) {
+            const int bodies[2] = {B.pairs[p].body_a, B.pairs[p].body_b};
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk) {  // topLeft, topRight, bottomLeft, bottomRight
+                if (bodies[blk >> 1] == bR && bodies[blk & 1] == bC) {
+                    const size_t src = (e0 + p) * 144 + (r + 6 * (blk >> 1)) + 12 * (c + 6 * (blk & 1));
+                    sk += Km_sub[src];
+                    if (Dm != nullptr) sd += Dm_sub[src];
+                }
+            }
+        }
+        Km[(size_t)env * nm * nm + i] = sk;
+        if (Dm != nullptr) Dm[(size_t)env * nm * nm + i] = sd;
+    }
+}
+
+void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
+                           cudaStream_t stream) {
+    dim3 grid(B.n_pairs, B.n_envs);
+    k_reduce_splits<<<grid, 128, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub);
+}
+
+void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,
+                           const double* Dm_sub, double* fm, double* Km, double* Dm, cudaStream_t stream) {
+    k_scatter_system<<<B.n_envs, 256, 0, stream>>>(B, deriv ? 1 : 0, fm_sub, Km_sub, Dm_sub, fm, Km, Dm);
+}
+
+// --------------------------------------------------------------------------
+// per-point query (original order) and raw sampling
+// --------------------------------------------------------------------------
+template <bool F32>
+__device__ __forceinline__ void query_points_body(const PairDev& pd, const double* R1, const double* p1,
+                                                  const double* R2, const double* p2, double* d_out, int32_t* cell_out,
+                                                  uint8_t* active_out, int* s_count) {
+    int cnt = 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < pd.n; idx += gridDim.x * blockDim.x) {
+        const double x0 = __ldg(pd.ox + idx), x1 = __ldg(pd.oy + idx), x2 = __ldg(pd.oz + idx);
+        double xw[3], x[3];
+        to_world(R1, p1, x0, x1, x2, xw);
+        to_local(R2, p2, xw, x);
+        const double d = query_sdf<F32>(pd.grid, x[0], x[1], x[2], false, nullptr) + pd.grid.col_th;
+        if (d_out) d_out[idx] = d;
+        if (cell_out) {  // BodySDFObj::query_grid_location, BodySDFObj.cpp:379-383
+            cell_out[3 * idx + 0] = (int)floor((x[0] - pd.grid.mn[0]) / pd.grid.dx);
+            cell_out[3 * idx + 1] = (int)floor((x[1] - pd.grid.mn[1]) / pd.grid.dy);
+            cell_out[3 * idx + 2] = (int)floor((x[2] - pd.grid.mn[2]) / pd.grid.dz);
+        }
+        const bool act = d < 0.;
+        if (active_out) active_out[idx] = act ? 1 : 0;
+        cnt += act ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_count, cnt);
+}
+
+__global__ void __launch_bounds__(256) k_query_points(PairDev pd, const double* __restrict__ E1,
+                                                      const double* __restrict__ E2, double* d_out, int32_t* cell_out,
+                                                      uint8_t* active_out, int32_t* n_active) {
+    __shared__ double R1[9], p1[3], R2[9], p2[3];
+    __shared__ int s_count;
+    if (threadIdx.x < 12) stage_pose(E1, 1, 0, 0, R1, p1, threadIdx.x);
+    else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E2, 1, 0, 0, R2, p2, threadIdx.x - 32);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    if (pd.grid.g32 != nullptr) query_points_body<true>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
+    else query_points_body<false>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) atomicAdd(n_active, s_count);
+}
+
+void launch_query_points(const PairDev& pd, const double* E1, const double* E2, double* d_out, int32_t* cell_out,
+                         uint8_t* active_out, int32_t* n_active, cudaStream_t stream) {
+    cudaMemsetAsync(n_active, 0, sizeof(int32_t), stream);
+    const int blocks = max(1, min((pd.n + 255) / 256, 148 * 8));
+    k_query_points<<<blocks, 256, 0, stream>>>(pd, E1, E2, d_out, cell_out, active_out, n_active);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256) k_sdf_distance(GridDev G, int64_t n, const double* __restrict__ x,
+                                                      const double* __restrict__ y, const double* __restrict__ z,
+                                                      double* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = query_sdf<F32>(G, __ldg(x + i), __ldg(y + i), __ldg(z + i), false, nullptr);  // Mesh.cpp:143-189
+}
+
+void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, double* out,
+                         cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)148 * 16));
+    if (G.g32 != nullptr) k_sdf_distance<true><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
+    else k_sdf_distance<false><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
+}
+
+__global__ void k_aos_to_soa(const double* __restrict__ aos, int64_t n, double* __restrict__ x, double* __restrict__ y,
+                             double* __restrict__ z) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] = aos[3 * i]; y[i] = aos[3 * i + 1]; z[i] = aos[3 * i + 2];
+    }
+}
+void launch_aos_to_soa(const double* aos, int64_t n, double* x, double* y, double* z, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)148 * 16));
+    k_aos_to_soa<<<blocks, 256, 0, stream>>>(aos, n, x, y, z);
+}
+
+// min over n values: per-block minima into scratch[gridDim], then one block.
+__global__ void k_min_stage(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    __shared__ double sm[32];
+    double m = DBL_MAX;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmin(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : DBL_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) out[blockIdx.x] = m;
+    }
+}
+void launch_min_reduce(const double* v, int64_t n, double* out_scalar, double* scratch, cudaStream_t stream) {
+    const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)1024));
+    k_min_stage<<<blocks, 256, 0, stream>>>(v, n, scratch);
+    k_min_stage<<<1, 256, 0, stream>>>(scratch, blocks, out_scalar);
+}
+
+}  // namespace sdfc

@@ -1,0 +1,81 @@
+// sdfc_kernels.cuh — kernel-side data layout and launch entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "sdfc_device.cuh"
+
+namespace sdfc {
+
+// Device descriptor of one contact pair (constant across environments).
+struct PairDev {
+    // contact points of the contact body, SoA. "s*" = spatially sorted copy used
+    // by the force path and batched detection; "o*" = original order, used
+    // whenever a per-point output is returned to the caller.
+    const double *sx, *sy, *sz;
+    const double *ox, *oy, *oz;
+    int n;            // number of contact points
+    int n_words;      // ceil(n / 32) mask words
+    int word_offset;  // first mask word of this pair inside an environment's mask row
+    int body_a, body_b;  // pose slots inside an environment
+    GridDev grid;
+    PairParams prm;   // effective kn, kt (scaled), mu, damping
+};
+
+// Output value layout of one (env, pair[, split]) partial, fp64:
+//   derivative: 4 K-blocks x kSlotK slots, then (if DM) 4 D-blocks x kSlotD slots
+//   value-only: kSlotF slots
+// Slot -> entry maps are produced by tr_index<N>() (see sdfc_kernels.cu).
+constexpr int kNumWarps = 4;           // force kernel: warps per CTA
+constexpr int kForceThreads = 32 * kNumWarps;
+constexpr int kDetectThreads = 256;
+constexpr int kDetectWordsPerWarp = 2; // 64 points per warp per tile
+constexpr int kDetectTileWords = (kDetectThreads / 32) * kDetectWordsPerWarp;
+
+constexpr int tr_out(int n) {  // values left per lane after the 5 halving steps
+    for (int s = 0; s < 5; ++s) n = (n + 1) / 2;
+    return n;
+}
+constexpr int kOutK = tr_out(39);  // 2
+constexpr int kOutD = tr_out(36);  // 2
+constexpr int kOutF = tr_out(12);  // 1
+constexpr int kPartialDeriv = 4 * kOutK * 32;         // 256 doubles
+constexpr int kPartialDerivDM = kPartialDeriv + 4 * kOutD * 32;  // 512 doubles
+constexpr int kPartialValue = kOutF * 32;             // 32 doubles
+
+struct BatchDev {
+    const PairDev* pairs;  // [n_pairs]
+    int n_pairs, n_bodies, n_envs;
+    int words_per_env;
+    // detection tiles: tile t covers kDetectTileWords words of pair tile_pair[t]
+    const int* tile_pair;
+    const int* tile_word0;
+    int n_tiles;
+    int splits;  // force CTAs per (env, pair)
+    uint32_t* mask;     // [n_envs][words_per_env]
+    int32_t* n_active;  // [n_envs][n_pairs]
+    double* partial;    // [n_envs][n_pairs][splits][kPartial*]
+};
+
+// launches (all asynchronous on `stream`)
+void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream);
+void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
+                  cudaStream_t stream);
+// Sums the split partials in fixed order into per-pair blocks (overwrite):
+// fm_sub [env][pair][12], Km_sub / Dm_sub [env][pair][144] column-major.
+void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
+                           cudaStream_t stream);
+// Gathers the pair blocks into per-environment system arrays in force order
+// (overwrite): fm [env][6*n_bodies], Km / Dm [env][(6*n_bodies)^2] column-major.
+// Dm may be nullptr.
+void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,
+                           const double* Dm_sub, double* fm, double* Km, double* Dm, cudaStream_t stream);
+// Per-point outputs in ORIGINAL order for one pair, one environment.
+void launch_query_points(const PairDev& pair_host_copy, const double* E1, const double* E2, double* d_out,
+                         int32_t* cell_out, uint8_t* active_out, int32_t* n_active, cudaStream_t stream);
+// Raw SDF sampling (SDFMesh::distance): SoA points in the grid's frame.
+void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, double* out,
+                         cudaStream_t stream);
+void launch_min_reduce(const double* v, int64_t n, double* out_scalar, double* scratch, cudaStream_t stream);
+void launch_aos_to_soa(const double* aos, int64_t n, double* x, double* y, double* z, cudaStream_t stream);
+
+}  // namespace sdfc

@@ -1,0 +1,174 @@
+/* sdfcontact_b200.h — C-ABI of the B200 (sm_100a) SDF-contact hot path.
+ *
+ * This is the drop-in boundary for ONE path of the RedMax simulator inside
+ * yunshengtian/Assemble-Them-All: point-vs-SDF contact detection and penalty
+ * contact force / Jacobian evaluation. Plain pointers and sizes,
+ * no C++/torch types. Every entry point cites the reference interface it
+ * replaces (paths relative to simulation/redmax/ of the reference).
+ *
+ * Conventions (Eigen-native, so a C++ host passes `.data()` directly):
+ *   - 4x4 poses E are COLUMN-MAJOR double[16]  (Body::_E_0i, Body/Body.h:52)
+ *   - spatial velocities phi are double[6] = (omega, v) in body frame (Body.h:58)
+ *   - fm_sub is double[12] = (contact body 6, SDF body 6); Km_sub/Dm_sub are
+ *     COLUMN-MAJOR double[144]                  (ForceGeneralSDFContact.cpp:84-99)
+ *   - SDF grids are linear, x fastest: a[i + ni*(j + nj*k)]
+ *                                               (externals/sdfgen/array3.h:70-80)
+ *   - contact points are AoS xyz in the contact body's frame
+ *                                               (Body::_contact_points, Body.h:36)
+ * All functions return SDFC_OK (0) or a negative sdfc_status; the message of
+ * the last failure on the calling thread is available from sdfc_last_error().
+ * There is NO CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef SDFCONTACT_B200_H
+#define SDFCONTACT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SDFC_API
+#else
+#define SDFC_API __attribute__((visibility("default")))
+#endif
+
+typedef int sdfc_status;
+#define SDFC_OK 0
+#define SDFC_ERR_INVALID (-1)  /* bad argument */
+#define SDFC_ERR_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define SDFC_ERR_NO_DEVICE (-3)
+
+typedef struct sdfc_context sdfc_context; /* one device + stream + scratch */
+typedef struct sdfc_sdf sdfc_sdf;         /* device copy of one body's voxel SDF */
+typedef struct sdfc_points sdfc_points;   /* device copy of one body's contact points */
+typedef struct sdfc_pair sdfc_pair;       /* one ForceGeneralSDFContact */
+typedef struct sdfc_batch sdfc_batch;     /* E environments x P pairs, device-resident */
+
+/* ---- library ---------------------------------------------------------- */
+SDFC_API int sdfc_version(void);
+/* Replaces throw_error()/`throw std::string` (Common.h:58-61): the host
+ * rethrows in the reference's convention using this message. */
+SDFC_API const char* sdfc_last_error(void);
+SDFC_API int sdfc_device_count(void);
+
+/* ---- context ---------------------------------------------------------- */
+SDFC_API sdfc_status sdfc_context_create(int device, sdfc_context** out);
+SDFC_API sdfc_status sdfc_context_destroy(sdfc_context* ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the
+ * context's own stream. */
+SDFC_API sdfc_status sdfc_context_set_stream(sdfc_context* ctx, void* cuda_stream);
+SDFC_API sdfc_status sdfc_context_synchronize(sdfc_context* ctx);
+/* Number of kernels this context has launched so far (bench bookkeeping). */
+SDFC_API int64_t sdfc_context_launch_count(const sdfc_context* ctx);
+
+/* ---- SDF grid: fields of BodySDFObj (Body/BodySDFObj.h:13-16) ---------- */
+/* grid_host: ni*nj*nk doubles. If every value is exactly representable in
+ * fp32 (true for freshly generated grids, BodySDFObj.cpp:81-83) an fp32 copy
+ * is stored as well and used for gathers (values are widened back exactly);
+ * grids reloaded from the text cache (BodySDFObj.cpp:86-103) stay fp64. */
+SDFC_API sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk,
+                                     const double min_box[3], const double max_box[3],
+                                     double dx, double dy, double dz, double col_th,
+                                     const double* grid_host, sdfc_sdf** out);
+SDFC_API sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th);
+/* 1 if the fp32-lossless copy is in use, else 0. */
+SDFC_API int sdfc_sdf_is_fp32(const sdfc_sdf* sdf);
+SDFC_API sdfc_status sdfc_sdf_destroy(sdfc_sdf* sdf);
+
+/* Batched raw sampling = SDFMesh::distance / min_distance (Mesh.cpp:143-198,
+ * python_interface.cpp:283-292): no col_th, FLT_MAX outside the box.
+ * X_host: n x 3 AoS in the SDF's own frame. Host buffers in and out. */
+SDFC_API sdfc_status sdfc_sdf_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_host);
+SDFC_API sdfc_status sdfc_sdf_min_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_min);
+/* Device-resident form: SoA inputs already in HBM, result left in HBM. */
+SDFC_API sdfc_status sdfc_sdf_distance_device(sdfc_sdf* sdf, int64_t n, const double* dx, const double* dy,
+                                              const double* dz, double* dout);
+
+/* ---- contact points: Body::_contact_points (Body/Body.h:36,129) -------- */
+/* morton_sort != 0 stores a spatially sorted SoA copy for the force path (the
+ * original order is kept for every per-point output). */
+SDFC_API sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host, int morton_sort,
+                                        sdfc_points** out);
+SDFC_API int sdfc_points_count(const sdfc_points* pts);
+SDFC_API sdfc_status sdfc_points_destroy(sdfc_points* pts);
+
+/* ---- pair: ForceGeneralSDFContact (Force/ForceGeneralSDFContact.h:13-31) */
+SDFC_API sdfc_status sdfc_pair_create(sdfc_context* ctx, sdfc_points* contact_points, sdfc_sdf* sdf,
+                                      double kn, double kt, double mu, double damping, sdfc_pair** out);
+SDFC_API sdfc_status sdfc_pair_set_stiffness(sdfc_pair* pair, double kn, double kt); /* .h:28 */
+SDFC_API sdfc_status sdfc_pair_set_friction(sdfc_pair* pair, double mu);             /* .h:29 */
+SDFC_API sdfc_status sdfc_pair_set_damping(sdfc_pair* pair, double damping);         /* .h:30 */
+SDFC_API sdfc_status sdfc_pair_set_scale(sdfc_pair* pair, double scale);             /* .h:31 */
+/* Body::_contact_scale of the contact body (Body/Body.h:47, Robot.cpp:462-472). */
+SDFC_API sdfc_status sdfc_pair_set_contact_scale(sdfc_pair* pair, double contact_scale);
+SDFC_API sdfc_status sdfc_pair_destroy(sdfc_pair* pair);
+
+/* collision_detection_general_SDF (CollisionDetection/CollisionDetection.cpp:124-147)
+ * for every point, in point order: d_out[n] = SDF_body->distance(xw),
+ * cell_out[3n] = query_grid_location, active_out[n] = (d < 0). Any of the three
+ * output pointers may be NULL. n_active receives the contact count. Host buffers. */
+SDFC_API sdfc_status sdfc_pair_query(sdfc_pair* pair, const double E1[16], const double E2[16],
+                                     double* d_out, int32_t* cell_out, uint8_t* active_out, int32_t* n_active);
+
+/* ForceGeneralSDFContact::computeForce (ForceGeneralSDFContact.cpp:46-67,147-219):
+ * detection + value-only force. fm_sub[12] is OVERWRITTEN with the pair's
+ * (contact body, SDF body) blocks; the caller scatters/accumulates (see
+ * sdfc_scatter_*). n_active > 0 means both bodies record contact history
+ * (CollisionDetection.cpp:143-146). */
+SDFC_API sdfc_status sdfc_pair_force(sdfc_pair* pair, const double E1[16], const double phi1[6],
+                                     const double E2[16], const double phi2[6],
+                                     double fm_sub[12], int32_t* n_active);
+
+/* ForceGeneralSDFContact::computeForceWithDerivative (.cpp:69-105,221-447). */
+SDFC_API sdfc_status sdfc_pair_force_deriv(sdfc_pair* pair, const double E1[16], const double phi1[6],
+                                           const double E2[16], const double phi2[6],
+                                           double fm_sub[12], double Km_sub[144], double Dm_sub[144],
+                                           int32_t* n_active);
+
+/* The accumulate (+=) half of the public wrappers (.cpp:60-61,88-99): host-side
+ * helper so a Force plug-in keeps the reference's semantics. System arrays are
+ * column-major ndof_m x ndof_m. */
+SDFC_API void sdfc_scatter_force(int idx_contact, int idx_sdf, const double fm_sub[12], double* fm_sys);
+SDFC_API void sdfc_scatter_deriv(int ndof_m, int idx_contact, int idx_sdf, const double Km_sub[144],
+                                 const double Dm_sub[144], double* Km_sys, double* Dm_sys);
+
+/* ---- batched: E independent environments, device-resident -------------- */
+/* An environment is one Simulation's worth of bodies: n_bodies poses, and
+ * n_pairs contact forces pair[p] = (body_a[p] -> contact points, body_b[p] ->
+ * SDF). All environments share geometry; only poses/velocities differ. This is
+ * Robot::computeForce[WithDerivative]'s loop over _forces (Robot.cpp:513-551)
+ * for E simulations at once. */
+SDFC_API sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n_pairs,
+                                       sdfc_pair* const* pairs, const int32_t* body_a, const int32_t* body_b,
+                                       sdfc_batch** out);
+SDFC_API sdfc_status sdfc_batch_destroy(sdfc_batch* batch);
+
+/* Host-buffer entry (the plug-in-facing call): E_host [n_envs][n_bodies][16],
+ * phi_host [n_envs][n_bodies][6]. Outputs, per environment, the caller-zeroed
+ * -then-accumulated system arrays exactly as Robot hands them to the forces:
+ * fm_out [n_envs][6*n_bodies]; Km_out, Dm_out [n_envs][(6*n_bodies)^2] column-
+ * major (NULL when deriv == 0); n_active_out [n_envs][n_pairs]. Arrays are
+ * overwritten (contact contribution only). Includes H2D and D2H copies. */
+SDFC_API sdfc_status sdfc_batch_eval(sdfc_batch* batch, const double* E_host, const double* phi_host, int deriv,
+                                     double* fm_out, double* Km_out, double* Dm_out, int32_t* n_active_out);
+
+/* Device-resident entry: same arrays, all in HBM; asynchronous on the context
+ * stream. Dm_dev may be NULL (skipped). */
+SDFC_API sdfc_status sdfc_batch_eval_device(sdfc_batch* batch, const double* E_dev, const double* phi_dev,
+                                            int deriv, double* fm_dev, double* Km_dev, double* Dm_dev,
+                                            int32_t* n_active_dev);
+
+/* Detection only over the whole batch (LOOP C): fills n_active_dev
+ * [n_envs][n_pairs]; per-point outputs are not materialised. */
+SDFC_API sdfc_status sdfc_batch_detect_device(sdfc_batch* batch, const double* E_dev, int32_t* n_active_dev);
+
+/* Total detection queries one batch evaluation performs = n_envs * sum_p n_p. */
+SDFC_API int64_t sdfc_batch_queries_per_eval(const sdfc_batch* batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFCONTACT_B200_H */

@@ -1,0 +1,180 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref).
+
+The reference ships no golden vectors or known-answer tests for this path
+(SURVEY.md §4, §8c), so the fixtures are outputs of the reference itself, run in
+the build container through oracle/_ref/ref_probe (which needs /root/reference
+only at BUILD time). Run from the repo root:
+
+    make -C oracle/ref_build -j8 && python oracle/make_golden.py
+
+Fixtures (all seeded, small):
+  contact_small.npz   peg/block pair (~600 vertices each, dx 0.1): body-frame
+                      contact points, fp32-lossless SDF grids, and for a set of
+                      seeded poses/velocities/parameters the reference's per-point
+                      d, cell index, active ids, and fm_sub/Km_sub/Dm_sub from both
+                      the derivative and value-only kernels, plus raw
+                      query_SDF/query_dSDF/query_ddSDF samples.
+  traj_small.npz      per-step q, qdot of the reference's BDF1 integration of the
+                      same pair under the planner's XML (translational and
+                      free3d-exp joints, external push), for the batched stepper.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+from assemble_them_all_b200 import synth  # noqa: E402
+
+import ref_probe  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# (mu, damping, kn, kt, scale, contact_scale); first rows = planner defaults
+PARAM_CASES = [
+    (0.0, 0.0, 1e6, 1e3, 1.0, 1.0),
+    (0.0, 0.0, 1e6, 1e3, 1.0, 1.0),
+    (0.0, 0.0, 1e5, 1e3, 0.5, 2.0),
+    (0.5, 0.0, 1e6, 1e3, 1.0, 1.0),
+    (0.0, 30.0, 1e6, 1e3, 1.0, 1.0),
+    (0.5, 30.0, 1e6, 1e3, 1.0, 1.0),
+    (0.9, 5.0, 1e5, 1e3, 1.0, 1.0),
+    (0.05, 100.0, 1e6, 2e3, 1.0, 0.7),
+]
+
+
+def pack_grid(out, prefix, g):
+    grid = np.asarray(g["grid"])
+    g32 = grid.astype(np.float32)
+    assert np.array_equal(g32.astype(np.float64), grid), "fresh grids must be fp32-lossless (BodySDFObj.cpp:81-83)"
+    out[prefix + "grid_f32"] = g32
+    out[prefix + "dims"] = np.array([g["ni"], g["nj"], g["nk"]], dtype=np.int32)
+    out[prefix + "min_box"] = np.asarray(g["min_box"])
+    out[prefix + "max_box"] = np.asarray(g["max_box"])
+    out[prefix + "spacing"] = np.array([g["dx"], g["dy"], g["dz"]])
+    out[prefix + "col_th"] = np.array(g["col_th"])
+
+
+def make_contact_small():
+    rng = np.random.default_rng(synth.MESH_SEED)
+    tmp = tempfile.mkdtemp(prefix="golden_asm_")
+    parts = synth.peg_in_hole(n_vertices=600)
+    synth.write_assembly(parts, tmp)
+    xml = synth.planner_xml(tmp, "0", ["1"], sdf_dx=0.1)
+    p = ref_probe.Probe(xml, tmp)
+    names = p.body_names()
+    out = {"names": np.array(names), "n_forces": np.array(p.num_forces()), "n_cases": np.array(len(PARAM_CASES)),
+           "ndof_m": np.array(p.ndof_m())}
+    E0 = {}
+    for n in names:
+        out[f"{n}_points"] = p.contact_points(n)
+        pack_grid(out, f"{n}_", p.sdf_grid(n))
+        E0[n] = p.body_info(n)["E_0i"]
+        out[f"{n}_E0"] = E0[n]
+        out[f"{n}_index"] = np.array(p.body_info(n)["index"])
+    for fi in range(p.num_forces()):
+        info = p.force_info(fi)
+        out[f"f{fi}_bodies"] = np.array([info["contact_body"], info["sdf_body"]])
+
+    # raw SDF samples (inside, near faces, outside)
+    for n in names:
+        g = p.sdf_grid(n)
+        lo, hi = np.asarray(g["min_box"]), np.asarray(g["max_box"])
+        X = rng.uniform(lo - 0.3, hi + 0.3, size=(3000, 3))
+        # exact lattice / box-face hits exercise floor() and the closed-interval test
+        ijk = rng.integers(0, [g["ni"], g["nj"], g["nk"]], size=(200, 3))
+        X[:200] = lo + ijk * np.array([g["dx"], g["dy"], g["dz"]])
+        X[200] = lo
+        X[201] = hi
+        out[f"{n}_qX"] = X
+        out[f"{n}_q_sdf"] = p.query_sdf(n, X, False)
+        out[f"{n}_q_sdf_acc"] = p.query_sdf(n, X, True)
+        out[f"{n}_q_dsdf"] = p.query_dsdf(n, X)
+        out[f"{n}_q_ddsdf"] = p.query_ddsdf(n, X[:1000])
+        out[f"{n}_q_cell"] = p.grid_location(n, X).astype(np.int32)
+
+    for c, (mu, damp, kn, kt, scale, cscale) in enumerate(PARAM_CASES):
+        out[f"c{c}_params"] = np.array([kn, kt, mu, damp, scale, cscale])
+        for n in names:
+            big = c in (1,)  # one deep-penetration case
+            E = synth.perturbed_pose(E0[n], rng, trans=0.2 if big else 0.08, rot=0.08 if big else 0.03)
+            phi = rng.normal(size=6) * (0.0 if c == 0 else 0.5)
+            p.set_body_pose(n, E, phi)
+            p.set_contact_scale(n, cscale)
+            out[f"c{c}_{n}_E"] = E
+            out[f"c{c}_{n}_phi"] = phi
+        p.clear_all_contact_bodies()
+        for fi in range(p.num_forces()):
+            p.set_force_params(fi, kn, kt, mu, damp, scale)
+            det = p.detect(fi)
+            out[f"c{c}_f{fi}_d"] = det["d"]
+            out[f"c{c}_f{fi}_cell"] = det["cell"].astype(np.int32)
+            out[f"c{c}_f{fi}_active"] = np.array(det["active_ids"], dtype=np.int32)
+            fm, Km, Dm = p.force_deriv_sub(fi)
+            out[f"c{c}_f{fi}_fm"] = fm
+            out[f"c{c}_f{fi}_Km"] = Km
+            out[f"c{c}_f{fi}_Dm"] = Dm
+            out[f"c{c}_f{fi}_fm_value"] = p.force_sub(fi)
+            fm_sys, Km_sys, Dm_sys = p.force_deriv_public(fi)
+            out[f"c{c}_f{fi}_fm_sys"] = fm_sys
+            out[f"c{c}_f{fi}_Km_sys"] = Km_sys
+            out[f"c{c}_f{fi}_Dm_sys"] = Dm_sys
+            if c in (1, 5):
+                ids, FM, KM, DM = p.force_deriv_per_contact(fi)
+                out[f"c{c}_f{fi}_pc_ids"] = np.array(ids, dtype=np.int32)
+                out[f"c{c}_f{fi}_pc_fm"] = FM
+                out[f"c{c}_f{fi}_pc_Km"] = KM
+                out[f"c{c}_f{fi}_pc_Dm"] = DM
+        for n in names:
+            out[f"c{c}_{n}_touched"] = np.array(p.get_contact_bodies(n))
+    path = os.path.join(GOLDEN, "contact_small.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
+def make_traj_small(steps=120):
+    tmp = tempfile.mkdtemp(prefix="golden_traj_")
+    parts = synth.peg_in_hole(n_vertices=600)
+    synth.write_assembly(parts, tmp)
+    out = {"steps": np.array(steps)}
+    for jt, force in (("translational", [0, 0, 0, 60.0, 80.0, 0.0]),
+                      ("free3d-exp", [30.0, -60.0, 15.0, 60.0, 80.0, 0.0])):
+        key = jt.replace("-", "_")
+        xml = synth.planner_xml(tmp, "0", ["1"], joint_type=jt, sdf_dx=0.1)
+        p = ref_probe.Probe(xml, tmp)
+        p.reset()
+        p.set_body_external_force("part0", np.array(force, dtype=np.float64))
+        Q, QD, CONV = [p.get_q()], [p.get_qdot()], []
+        for _ in range(steps):
+            p.forward(1)
+            Q.append(p.get_q())
+            QD.append(p.get_qdot())
+            CONV.append(p.is_converged())
+        out[f"{key}_force"] = np.array(force, dtype=np.float64)
+        out[f"{key}_q"] = np.array(Q)
+        out[f"{key}_qdot"] = np.array(QD)
+        out[f"{key}_converged"] = np.array(CONV)
+        out[f"{key}_touched"] = np.array(p.get_contact_bodies("part0"))
+        out[f"{key}_h"] = np.array(p.timestep())
+        for n in p.body_names():
+            bi = p.body_info(n)
+            out[f"{key}_{n}_mass"] = np.array(bi["mass"])
+            out[f"{key}_{n}_inertia"] = np.asarray(bi["inertia"])
+            out[f"{key}_{n}_E_ij"] = np.asarray(bi["E_ij"])
+            out[f"{key}_{n}_E_final"] = np.asarray(bi["E_0i"])
+    path = os.path.join(GOLDEN, "traj_small.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    for fn in (make_contact_small, make_traj_small):
+        path = fn()
+        print(path, "%.1f KB" % (os.path.getsize(path) / 1024))

@@ -172,6 +172,21 @@ struct Probe {
         b->_E_i0 = math::Einv(E);
         b->_phi = phi;
     }
+    // Overwrite the hot-path inputs of a body (public data members) so that the
+    // reference evaluates exactly the arrays the CUDA path is given.
+    void set_contact_points(const std::string& name, const RowMatX3& X) {
+        Body* b = body(name);
+        b->_contact_points.resize(X.rows());
+        for (int i = 0; i < X.rows(); ++i) b->_contact_points[i] = Vector3(X.row(i).transpose());
+    }
+    void set_sdf_grid(const std::string& name, int ni, int nj, int nk, const Vector3& mn, const Vector3& mx,
+                      double dx, double dy, double dz, py::array_t<double, py::array::c_style | py::array::forcecast> grid) {
+        BodySDFObj* b = sdf_body(name);
+        if ((size_t)grid.size() != (size_t)ni * nj * nk) throw std::runtime_error("grid size mismatch");
+        b->_SDF.resize(ni, nj, nk);
+        std::copy(grid.data(), grid.data() + grid.size(), b->_SDF.a.begin());
+        b->_min_box = mn; b->_max_box = mx; b->_dx = dx; b->_dy = dy; b->_dz = dz;
+    }
     void set_col_th(const std::string& name, double col_th) { sdf_body(name)->_col_th = col_th; }
     void set_force_params(int i, double kn, double kt, double mu, double damping, double scale) {
         auto* f = sdf_force(i);
@@ -416,6 +431,8 @@ PYBIND11_MODULE(ref_probe, m) {
         .def("contact_points", &Probe::contact_points)
         .def("sdf_grid", &Probe::sdf_grid)
         .def("set_body_pose", &Probe::set_body_pose)
+        .def("set_contact_points", &Probe::set_contact_points)
+        .def("set_sdf_grid", &Probe::set_sdf_grid)
         .def("set_col_th", &Probe::set_col_th)
         .def("set_force_params", &Probe::set_force_params)
         .def("set_contact_scale", &Probe::set_contact_scale)

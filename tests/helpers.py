@@ -1,0 +1,71 @@
+"""Shared test helpers: golden fixtures (outputs of the unmodified reference,
+see oracle/make_golden.py) and tolerance checks."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star: fp64 values agree to 1e-9 relative. Jacobian blocks contain
+# entries that cancel to ~0, so "relative" is taken against the largest
+# magnitude of the array being compared.
+RTOL = 1e-9
+
+
+def rel_err(ref, got):
+    ref, got = np.asarray(ref, dtype=np.float64), np.asarray(got, dtype=np.float64)
+    scale = np.max(np.abs(ref)) if ref.size else 0.0
+    if scale == 0.0:
+        return float(np.max(np.abs(got))) if got.size else 0.0
+    return float(np.max(np.abs(ref - got)) / scale)
+
+
+def assert_close(ref, got, what, rtol=RTOL):
+    e = rel_err(ref, got)
+    assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:.1e}"
+
+
+class GoldenContact:
+    def __init__(self, z):
+        self.z = z
+        self.names = [str(n) for n in z["names"]]
+        self.n_forces = int(z["n_forces"])
+        self.n_cases = int(z["n_cases"])
+        self.ndof_m = int(z["ndof_m"])
+
+    def grid_dict(self, name, col_th=None):
+        z = self.z
+        ni, nj, nk = (int(v) for v in z[f"{name}_dims"])
+        dx, dy, dz = (float(v) for v in z[f"{name}_spacing"])
+        return {"ni": ni, "nj": nj, "nk": nk, "min_box": z[f"{name}_min_box"], "max_box": z[f"{name}_max_box"],
+                "dx": dx, "dy": dy, "dz": dz, "col_th": float(z[f"{name}_col_th"]) if col_th is None else col_th,
+                "grid": z[f"{name}_grid_f32"].astype(np.float64)}
+
+    def points(self, name):
+        return self.z[f"{name}_points"]
+
+    def index(self, name):
+        return int(self.z[f"{name}_index"])
+
+    def force_bodies(self, fi):
+        a, b = self.z[f"f{fi}_bodies"]
+        return str(a), str(b)
+
+    def case_params(self, c):
+        kn, kt, mu, damp, scale, cscale = (float(v) for v in self.z[f"c{c}_params"])
+        return {"kn": kn, "kt": kt, "mu": mu, "damping": damp, "scale": scale, "contact_scale": cscale}
+
+    def case_pose(self, c, name):
+        return self.z[f"c{c}_{name}_E"], self.z[f"c{c}_{name}_phi"]
+
+    def out(self, c, fi, key):
+        return self.z[f"c{c}_f{fi}_{key}"]
+
+
+def load_contact_golden():
+    return GoldenContact(np.load(os.path.join(GOLDEN, "contact_small.npz")))
+
+
+def load_traj_golden():
+    return np.load(os.path.join(GOLDEN, "traj_small.npz"))
