@@ -26,6 +26,8 @@ SIGNATURES = {
     "sdfc_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sdfc_context_synchronize": (C.c_int, [C.c_void_p]),
     "sdfc_context_launch_count": (C.c_int64, [C.c_void_p]),
+    "sdfc_context_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "sdfc_context_read_timing": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int]),
     "sdfc_sdf_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double,
                                   C.c_double, C.c_double, c_double_p, c_void_pp]),
     "sdfc_sdf_set_col_th": (C.c_int, [C.c_void_p, C.c_double]),

@@ -18,7 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsdfcontact_b200.so")
 SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu"]
-HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_step.cuh", os.path.join("..", "..", "include", "sdfcontact_b200.h")]
+FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7
+HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_step.cuh", FORCE_INST,
+           os.path.join("..", "..", "include", "sdfcontact_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,9 +53,11 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    for s in srcs:
-        o = os.path.join(objdir, os.path.basename(s) + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+    jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), []) for s in srcs]
+    jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"), [f"-DSDFC_FORCE_VARIANT={v}"])
+             for v in range(8)]
+    for s, o, extra in jobs:
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

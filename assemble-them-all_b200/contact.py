@@ -57,6 +57,18 @@ class Context:
     def launch_count(self):
         return int(self._lib.sdfc_context_launch_count(self._h))
 
+    KERNEL_SLOTS = ("detect", "force", "reduce", "scatter")
+
+    def enable_timing(self, enable=True):
+        check(self._lib.sdfc_context_enable_timing(self._h, int(bool(enable))))
+
+    def read_timing(self, reset=True):
+        """-> {slot: (total_ms, launches)} accumulated since the last reset (synchronises)."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        check(self._lib.sdfc_context_read_timing(self._h, ms, cnt, int(bool(reset))))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_SLOTS)}
+
     def close(self):
         if self._h:
             self._lib.sdfc_context_destroy(self._h)

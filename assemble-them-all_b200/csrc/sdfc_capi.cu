@@ -44,6 +44,30 @@ struct sdfc_context {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // optional per-kernel timing: (slot, start, stop) triples pending resolution
+    bool timing = false;
+    struct Span { int slot; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double acc_ms[4] = {0, 0, 0, 0};
+    int64_t acc_n[4] = {0, 0, 0, 0};
+
+    cudaEvent_t get_event() {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int slot) {
+        if (!timing) return;
+        Span s{slot, get_event(), get_event()};
+        cudaEventRecord(s.a, stream);
+        spans.push_back(s);
+    }
+    void end() {
+        if (!timing) return;
+        cudaEventRecord(spans.back().b, stream);
+    }
 };
 
 struct sdfc_sdf {
@@ -143,13 +167,16 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     if (st != SDFC_OK) return st;
     cudaStream_t s = b->ctx->stream;
     const bool dm = b->any_fric || b->any_damp;
-    launch_detect_mask(b->dev, E_dev, s);
-    launch_force(b->dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s);
-    launch_finalize_pairs(b->dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s);
-    b->ctx->launches += 3;
+    sdfc_context* c = b->ctx;
+    c->begin(0); launch_detect_mask(b->dev, E_dev, s); c->end();
+    c->begin(1); launch_force(b->dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s); c->end();
+    c->begin(2); launch_finalize_pairs(b->dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
+    c->launches += 3;
     if (scatter) {
+        c->begin(3);
         launch_scatter_system(b->dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
-        b->ctx->launches += 1;
+        c->end();
+        c->launches += 1;
     }
     if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
@@ -202,6 +229,8 @@ sdfc_status sdfc_context_destroy(sdfc_context* ctx) {
     if (!ctx) return SDFC_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->free_events) cudaEventDestroy(e);
     delete ctx;
     return SDFC_OK;
 }
@@ -216,6 +245,26 @@ sdfc_status sdfc_context_synchronize(sdfc_context* ctx) {
     return SDFC_OK;
 }
 int64_t sdfc_context_launch_count(const sdfc_context* ctx) { return ctx ? ctx->launches : 0; }
+sdfc_status sdfc_context_enable_timing(sdfc_context* ctx, int enable) {
+    SDFC_REQUIRE(ctx != nullptr, "sdfc_context_enable_timing: ctx is NULL");
+    ctx->timing = enable != 0;
+    return SDFC_OK;
+}
+sdfc_status sdfc_context_read_timing(sdfc_context* ctx, double ms[4], int64_t counts[4], int reset) {
+    SDFC_REQUIRE(ctx && ms && counts, "sdfc_context_read_timing: NULL argument");
+    SDFC_CUDA(cudaSetDevice(ctx->device));
+    SDFC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ctx->acc_ms[sp.slot] += t; ctx->acc_n[sp.slot] += 1; }
+        ctx->free_events.push_back(sp.a);
+        ctx->free_events.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    for (int i = 0; i < 4; ++i) { ms[i] = ctx->acc_ms[i]; counts[i] = ctx->acc_n[i]; }
+    if (reset) for (int i = 0; i < 4; ++i) { ctx->acc_ms[i] = 0; ctx->acc_n[i] = 0; }
+    return SDFC_OK;
+}
 
 // -------------------------------------------------------------------- sdf
 sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const double min_box[3], const double max_box[3],
@@ -630,7 +679,7 @@ sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t
     SDFC_CUDA(cudaSetDevice(b->ctx->device));
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
-    launch_detect_mask(b->dev, E_dev, b->ctx->stream);
+    b->ctx->begin(0); launch_detect_mask(b->dev, E_dev, b->ctx->stream); b->ctx->end();
     b->ctx->launches += 1;
     if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,

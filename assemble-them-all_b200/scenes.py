@@ -1,0 +1,154 @@
+"""Benchmark / parity workloads expressed as hot-path inputs.
+
+A ContactScene holds exactly what the contact path consumes — per body: contact
+points in the body frame and a voxel SDF in the body frame; per pair: (contact
+body, SDF body, parameters); per environment: body poses and velocities — so the
+CUDA arm and the reference arm (which injects the same arrays into the
+unmodified reference through oracle/_ref/ref_probe) evaluate identical inputs.
+
+Datasets are not available offline: meshes come from synth.py and the SDF grids
+are ANALYTIC signed distances of the same shapes, sampled on a grid laid out by
+the reference's own rule (Body/BodySDFObj.cpp:59-70: spacing min(dx, bbox/res),
+one cell of padding, fp32 origin) and rounded to fp32 then widened
+(BodySDFObj.cpp:81-83). Body frames are the mesh frames shifted to the centroid
+of the bounding box (identity rotation).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import synth
+
+
+def _box_sdf(p, half):
+    q = np.abs(p) - half
+    outside = np.linalg.norm(np.maximum(q, 0.0), axis=-1)
+    inside = np.minimum(np.max(q, axis=-1), 0.0)
+    return outside + inside
+
+
+def _grid_layout(vmin, vmax, dx, res=20):
+    """Grid geometry as BodySDFObj::precompute_SDF lays it out (fp32 arithmetic where the reference uses it)."""
+    bbox = vmax - vmin
+    d = np.minimum(dx, bbox / res)                        # _dx, _dy, _dz (double)
+    unit = d.astype(np.float32)
+    mn = vmin.astype(np.float32) - np.float32(1) * unit   # padding = 1
+    mx = vmax.astype(np.float32) + np.float32(1) * unit
+    sizes = ((mx - mn + (0.5 * d).astype(np.float32)) / d.astype(np.float32)).astype(np.uint32) + 1
+    return d, mn.astype(np.float64), mx.astype(np.float64), sizes.astype(int)
+
+
+def analytic_grid(sdf_fn, vmin, vmax, dx, col_th, res=20):
+    d, mn, mx, n = _grid_layout(np.asarray(vmin, float), np.asarray(vmax, float), dx, res)
+    df = d.astype(np.float32).astype(np.float64)  # sdfgen steps in float
+    ax = [mn[a] + df[a] * np.arange(n[a]) for a in range(3)]
+    vals = np.empty((n[2], n[1], n[0]), dtype=np.float64)
+    for k in range(n[2]):  # slab by slab keeps memory small; layout index i + ni*(j + nj*k)
+        P = np.stack(np.meshgrid(ax[0], ax[1], [ax[2][k]], indexing="xy"), axis=-1).reshape(-1, 3)
+        vals[k] = sdf_fn(P).reshape(n[1], n[0])
+    vals = vals.astype(np.float32).astype(np.float64)
+    return synth.GridSpec(int(n[0]), int(n[1]), int(n[2]), mn, mx, float(d[0]), float(d[1]), float(d[2]), float(col_th),
+                          np.ascontiguousarray(vals.reshape(-1)))
+
+
+@dataclass
+class SceneBody:
+    name: str
+    points: np.ndarray       # (n,3) body frame
+    grid: synth.GridSpec     # body frame
+    rest_E: np.ndarray       # (4,4) pose in the assembled configuration
+
+
+@dataclass
+class ContactScene:
+    bodies: list
+    pairs: list              # (contact body index, SDF body index)
+    kn: float = 1e6
+    kt: float = 1e3
+    mu: float = 0.0
+    damping: float = 0.0
+    E: np.ndarray = field(default=None)    # (n_envs, n_bodies, 4, 4)
+    phi: np.ndarray = field(default=None)  # (n_envs, n_bodies, 6)
+    label: str = ""
+
+    @property
+    def n_envs(self):
+        return len(self.E)
+
+    @property
+    def queries_per_eval(self):
+        return self.n_envs * sum(len(self.bodies[a].points) for a, _ in self.pairs)
+
+    def upload(self, ctx, morton_sort=True):
+        """-> (ContactBatch, [pairs], [sdf], [points]) on the given context."""
+        from . import contact
+        sdf = [contact.SdfGrid.from_spec(ctx, b.grid) for b in self.bodies]
+        pts = [contact.ContactPoints(ctx, b.points, morton_sort=morton_sort) for b in self.bodies]
+        pairs = [contact.ForceGeneralSDFContact(ctx, pts[a], sdf[b], self.kn, self.kt, self.mu, self.damping,
+                                                index_contact=6 * a, index_sdf=6 * b) for a, b in self.pairs]
+        batch = contact.ContactBatch(ctx, self.n_envs, len(self.bodies), pairs, [a for a, _ in self.pairs],
+                                     [b for _, b in self.pairs])
+        return batch, pairs, sdf, pts
+
+
+def peg_hole_bodies(n_vertices=10000, sdf_dx=0.05, col_th=0.01):
+    """The C1/C2/C3 pair: peg 2x2x6 (body 0, moving) in a 6x6x4 block with a 2.1 square through-hole (body 1)."""
+    parts = synth.peg_in_hole(n_vertices=n_vertices)
+    col_th = float(np.float32(col_th))  # XML scalars pass through float (Simulation_Constructor.cpp:566-574)
+    sdf_dx = float(np.float32(sdf_dx))
+    out = []
+    half_peg = np.array([1.0, 1.0, 3.0])
+    half_blk = np.array([3.0, 3.0, 2.0])
+
+    def sd_peg(p):
+        return _box_sdf(p, half_peg)
+
+    def sd_block(p):
+        hole = _box_sdf(p[:, :2], np.array([1.05, 1.05]))
+        return np.maximum(_box_sdf(p, half_blk), -hole)
+
+    for pid, fn in (("0", sd_peg), ("1", sd_block)):
+        V, _ = parts[pid]
+        c = 0.5 * (V.min(0) + V.max(0))
+        Vb = V - c
+        grid = analytic_grid(fn, Vb.min(0), Vb.max(0), sdf_dx, col_th)
+        out.append(SceneBody(f"part{pid}", np.ascontiguousarray(Vb), grid, synth.make_E(np.eye(3), c)))
+    return out
+
+
+def c2_bfs_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sdf_dx=0.05, col_th=0.01):
+    """C2: states of 1024 translational BFS rollouts mid-push (run_joint_plan.py:511-570).
+
+    Environment e applies axis action e % 6 (+x, -x, +y, -y, +z, -z) to the peg
+    from a start offset along the hole axis uniform in [0, 3]; lateral pushes have
+    driven the peg 0.042-0.07 into the hole wall band (clearance 0.05, col_th
+    0.01), axial pushes slide freely. Planner parameters: kn 1e6, kt 1e3, mu 0,
+    damping 0 (run_joint_plan.py:153)."""
+    rng = np.random.default_rng(seed)
+    bodies = peg_hole_bodies(n_vertices, sdf_dx, col_th)
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64)
+    E = np.tile(np.eye(4), (n_envs, 2, 1, 1))
+    phi = np.zeros((n_envs, 2, 6))
+    for e in range(n_envs):
+        a = dirs[e % 6]
+        z0 = rng.uniform(0.0, 3.0)
+        push = rng.uniform(0.042, 0.07) if abs(a[2]) < 0.5 else rng.uniform(0.0, 0.5)
+        E[e, 0] = bodies[0].rest_E
+        E[e, 0, :3, 3] += a * push + np.array([0.0, 0.0, z0])
+        E[e, 1] = bodies[1].rest_E
+        phi[e, 0, 3:] = a * rng.uniform(0.05, 0.3)  # body frame == world axes (identity rotation)
+    return ContactScene(bodies, [(0, 1), (1, 0)], 1e6, 1e3, 0.0, 0.0, E, phi,
+                        label=f"C2 two-part BFS translational, {n_envs} rollouts, 2x~{n_vertices} contact pts, dx {sdf_dx}")
+
+
+def sweep_scene(n_points, grid_n, active_frac=0.05, seed=synth.SWEEP_SEED):
+    """C5: n_points uniform in an n^3 analytic sphere grid; col_th picked for the active fraction."""
+    rng = np.random.default_rng(seed)
+    spec = synth.sphere_grid(grid_n)
+    lo, hi = spec.min_box, spec.max_box
+    pts = rng.uniform(lo * 0.999, hi * 0.999, size=(n_points, 3))
+    r = np.linalg.norm(pts[: min(n_points, 200000)], axis=1) - 3.5
+    spec.col_th = float(-np.quantile(r, active_frac))
+    return spec, pts

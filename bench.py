@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py — the SDF-contact hot path on the C2 workload (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E]
+
+One "step" = one pass of the hot path over one batch: for every environment of a
+1024-rollout two-part BFS planning batch, detection of every contact point of
+both pairs against the other part's SDF (LOOP C), penalty force + Jacobian
+evaluation of every active contact (LOOP D) and the accumulation into the
+per-environment system arrays fm / Km / Dm — i.e. what Robot::computeForceWith
+Derivative's loop over the contact forces does (reference Robot.cpp:546-547),
+for all environments at once.
+
+metric  contact_point_sdf_queries_per_sec = detection queries processed by the
+        whole pass (E * sum_p N_p) / step time.  `value`: inputs resident in HBM,
+        CUDA events. `e2e`: the same pass through the host-buffer C-ABI call
+        (sdfc_batch_eval), H2D of poses and D2H of fm/Km/Dm inside the timing.
+--impl reference  times the reference's own CPU implementation (oracle/_ref, the
+        unmodified RedMax objects; falls back to the C oracle port) on all host
+        cores over a bounded sample of the same environments.
+Multi-GPU: environments are independent, so every rank takes its own E rollouts
+(weak scaling) with no data-path collective; one all_gather of the per-rank
+outcome record (contact counts) at the end, as the planner's final gather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "contact_point_sdf_queries_per_sec"
+UNIT = "queries/s"
+BYTES_PER_QUERY = 96  # 24 B point + 64 B eight-corner fp64 gather + 8 B result
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload(n_envs, seed_offset=0):
+    from assemble_them_all_b200 import scenes, synth
+    return scenes.c2_bfs_rollouts(n_envs=n_envs, n_vertices=10000, seed=synth.MESH_SEED + seed_offset)
+
+
+# ---------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref = unmodified reference objects; else the C port)
+# ---------------------------------------------------------------------------
+_W = {}
+
+
+def _ref_worker_init(scene_blob, use_ref):
+    """Per process: build the checker once and inject the scene's arrays."""
+    sc = scene_blob
+    _W["scene"] = sc
+    _W["kind"] = "port"
+    if use_ref:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+            import ref_probe
+            from assemble_them_all_b200 import synth
+            tmp = tempfile.mkdtemp(prefix="bench_ref_")
+            # placeholder meshes: geometry is overwritten below, so keep construction cheap
+            for pid in ("0", "1"):
+                V, F = synth.box_mesh((1.0, 1.0, 1.0), h=0.5)
+                synth.write_obj(os.path.join(tmp, f"{pid}.obj"), V, F)
+            xml = synth.planner_xml(tmp, "0", ["1"], sdf_dx=0.5, col_th=sc["col_th"])
+            p = ref_probe.Probe(xml, tmp)
+            for b, name in enumerate(("part0", "part1")):
+                g = sc["grids"][b]
+                p.set_contact_points(name, sc["points"][b])
+                p.set_sdf_grid(name, g["ni"], g["nj"], g["nk"], g["min_box"], g["max_box"], g["dx"], g["dy"], g["dz"], g["grid"])
+                p.set_col_th(name, g["col_th"])
+            for fi in range(p.num_forces()):
+                p.set_force_params(fi, sc["kn"], sc["kt"], sc["mu"], sc["damping"], 1.0)
+            _W["probe"] = p
+            _W["kind"] = "reference"
+            return
+        except Exception as exc:  # pragma: no cover - only when oracle/_ref is absent
+            _W["ref_error"] = repr(exc)
+    from oracle import sdfc_oracle as O
+    _W["O"] = O
+    _W["ogrids"] = [O.Grid.from_dict(g) for g in sc["grids"]]
+
+
+def _ref_eval_envs(args):
+    """Evaluate (with derivatives) the given environments once; -> (seconds, n_envs, kind, checksum)."""
+    env_ids, want_outputs = args
+    sc = _W["scene"]
+    outs = []
+    t_total = 0.0
+    if _W["kind"] == "reference":
+        p = _W["probe"]
+        for e in env_ids:
+            for b, name in enumerate(("part0", "part1")):
+                p.set_body_pose(name, sc["E"][e, b], sc["phi"][e, b])
+            t_total += p.time_force_evals(1, True)
+            if want_outputs:
+                acc = [p.force_deriv_public(fi) for fi in range(p.num_forces())]
+                outs.append((sum(a[0] for a in acc), sum(a[1] for a in acc), sum(a[2] for a in acc)))
+    else:
+        O = _W["O"]
+        for e in env_ids:
+            t0 = time.perf_counter()
+            fs, Ks, Ds = np.zeros(12), np.zeros((12, 12)), np.zeros((12, 12))
+            for (a, b) in sc["pairs"]:
+                fm, Km, Dm, _ = O.pair_force(_W["ogrids"][b], sc["E"][e, a], sc["phi"][e, a], sc["E"][e, b], sc["phi"][e, b],
+                                             sc["points"][a], sc["kn"], sc["kt"], sc["mu"], sc["damping"], True)
+                O.scatter(12, 6 * a, 6 * b, fm, Km, Dm, fs, Ks, Ds)
+            t_total += time.perf_counter() - t0
+            if want_outputs:
+                outs.append((fs, Ks, Ds))
+    return t_total, len(env_ids), _W["kind"], outs
+
+
+def scene_blob(scene):
+    def gd(g):
+        return {"ni": g.ni, "nj": g.nj, "nk": g.nk, "min_box": g.min_box, "max_box": g.max_box, "dx": g.dx, "dy": g.dy,
+                "dz": g.dz, "col_th": g.col_th, "grid": g.grid}
+    return {"points": [b.points for b in scene.bodies], "grids": [gd(b.grid) for b in scene.bodies],
+            "pairs": list(scene.pairs), "kn": scene.kn, "kt": scene.kt, "mu": scene.mu, "damping": scene.damping,
+            "E": scene.E, "phi": scene.phi, "col_th": scene.bodies[0].grid.col_th}
+
+
+def have_ref():
+    import glob
+    return bool(glob.glob(os.path.join(ROOT, "oracle", "_ref", "ref_probe*.so")))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    scene = workload(args.envs)
+    q_per_env = scene.queries_per_eval // scene.n_envs
+    sample = min(scene.n_envs, max(cores, args.ref_envs_per_core * cores))
+    blob = scene_blob(scene)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(blob, have_ref())) as pool:
+        shards = [list(range(i, sample, cores)) for i in range(cores)]
+        shards = [(s, False) for s in shards if s]
+        kind = "port"
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_eval_envs, shards)
+            dt = time.perf_counter() - t0
+            kind = res[0][2]
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample * q_per_env / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": scene.label, "envs_per_step": sample, "queries_per_env": q_per_env, "derivatives": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} of {scene.n_envs} environments per step, one process per core (fork), "
+                                   f"Robot-level loop over both contact forces with derivatives"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for i, n in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_leg(scene, gpu_out, budget_s=20.0):
+    """Rank 0, N=1: time the reference CPU path on one core over a bounded sample of
+    the same environments and gate parity of the GPU results on that sample."""
+    blob = scene_blob(scene)
+    _ref_worker_init(blob, have_ref())
+    q_per_env = scene.queries_per_eval // scene.n_envs
+    fm_g, Km_g, Dm_g = gpu_out
+    t_total, n_done, worst = 0.0, 0, 0.0
+    t_start = time.perf_counter()
+    order = list(range(0, scene.n_envs, max(1, scene.n_envs // 97))) + list(range(scene.n_envs))
+    seen = set()
+    for e in order:
+        if e in seen:
+            continue
+        seen.add(e)
+        check = n_done < 16
+        t, _, kind, outs = _ref_eval_envs(([e], check))
+        t_total += t
+        n_done += 1
+        if check:
+            fm, Km, Dm = outs[0]
+            for ref, got in ((fm, fm_g[e]), (Km, Km_g[e]), (Dm, Dm_g[e])):
+                ref = np.asarray(ref)
+                s = np.max(np.abs(ref))
+                err = float(np.max(np.abs(ref - got)) / s) if s > 0 else float(np.max(np.abs(got)))
+                worst = max(worst, err)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    if worst > 1e-9:
+        raise SystemExit(f"PARITY FAILURE: GPU vs CPU {_W['kind']} relative error {worst:.3e} > 1e-9")
+    return {"value": n_done * q_per_env / t_total, "unit": UNIT, "cores": 1, "kind": _W["kind"],
+            "sample": f"{n_done} of {scene.n_envs} environments, one evaluation with derivatives each, single core "
+                      f"({t_total:.1f} s CPU); GPU fm/Km/Dm checked on 16 of them: max rel err {worst:.1e}",
+            "env_evals_per_sec": n_done / t_total}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the contact path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from assemble_them_all_b200 import contact
+    scene = workload(args.envs, seed_offset=rank)
+    ctx = contact.Context(local)
+    # an explicit (non-legacy) stream: the library launches on it and the timing
+    # events below are recorded on the same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    batch, pairs, sdfs, pts = scene.upload(ctx)
+    nm = batch.ndof_m
+    E_col = np.ascontiguousarray(np.swapaxes(scene.E, -1, -2))
+    dE = torch.from_numpy(E_col).to(dev)
+    dphi = torch.from_numpy(np.ascontiguousarray(scene.phi)).to(dev)
+    dfm = torch.empty((scene.n_envs, nm), dtype=torch.float64, device=dev)
+    dKm = torch.empty((scene.n_envs, nm * nm), dtype=torch.float64, device=dev)
+    dDm = torch.empty((scene.n_envs, nm * nm), dtype=torch.float64, device=dev)
+    dna = torch.empty((scene.n_envs, batch.n_pairs), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        batch.eval_device(dE.data_ptr(), dphi.data_ptr(), True, dfm.data_ptr(), dKm.data_ptr(), dDm.data_ptr(), dna.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    # keep the device under this load for >= 1.5 s so that nvidia-smi (100 ms period)
+    # samples the clocks the timed steps will run at
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 1.5:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    barrier()
+
+    ctx.enable_timing(True)
+    ctx.read_timing(reset=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    l0 = ctx.launch_count
+    for a, b in evs:
+        flush.fill_(1)          # L2 flush between timed iterations (outside the event pair)
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    gpu_launches = ctx.launch_count - l0
+    for _ in range(40):  # tail load so the sampler also brackets the timed region
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    ms_step = float(np.mean(per_step))
+    kt = ctx.read_timing(reset=True)
+    ctx.enable_timing(False)
+
+    t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    q_rank = scene.queries_per_eval
+    value = world * q_rank / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI entry (pinned staging inside the library)
+    E_host, phi_host = scene.E, scene.phi
+    for _ in range(2):
+        out = batch.eval(E_host, phi_host, deriv=True)
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = batch.eval(E_host, phi_host, deriv=True)
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    t = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * q_rank / float(t.item())
+    h2d = scene.n_envs * batch.n_bodies * (16 + 6) * 8
+    d2h = scene.n_envs * (nm + 2 * nm * nm) * 8 + scene.n_envs * batch.n_pairs * 4
+
+    # ---- final gather of outcome records (the planner's only exchange)
+    n_active = dna.sum(dim=0).to(torch.int64)
+    if world > 1:
+        gathered = [torch.zeros_like(n_active) for _ in range(world)]
+        dist.all_gather(gathered, n_active)
+        n_active = torch.stack(gathered).sum(dim=0)
+    contacts_per_step = int(n_active.sum().item())
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        det_ms = kt["detect"][0] / max(1, kt["detect"][1])
+        frc_ms = kt["force"][0] / max(1, kt["force"][1])
+        red_ms = (kt["reduce"][0] + kt["scatter"][0]) / max(1, kt["reduce"][1])
+        achieved = q_rank * BYTES_PER_QUERY / (det_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": scene.label, "envs_per_gpu": scene.n_envs, "pairs": batch.n_pairs,
+                       "queries_per_step_per_gpu": q_rank, "active_contacts_per_step": contacts_per_step,
+                       "derivatives": True, "sdf_storage": "fp32-lossless" if all(s.is_fp32 for s in sdfs) else "fp64",
+                       "l2": "flushed between timed iterations (256 MiB write)", "parity_mode": "-fmad=false"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(np.mean(e2e_times))},
+            "gpu_launches": gpu_launches,
+            "roofline": {"kernel": "k_detect_mask", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": q_rank * BYTES_PER_QUERY, "avg_launch_ms": det_ms,
+                         "share_of_step": det_ms / ms_step},
+            "kernels_ms": {"k_detect_mask": det_ms, "k_force": frc_ms, "k_reduce_splits+k_scatter_system": red_ms,
+                           "step": ms_step},
+            "env_evals_per_sec": world * scene.n_envs / (ms_max * 1e-3),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            fm_h, Km_h, Dm_h, _ = out
+            line["cpu_baseline"] = cpu_baseline_leg(scene, (fm_h, Km_h, Dm_h))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
+    ap.add_argument("--ref-envs-per-core", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,6 +63,13 @@ SDFC_API sdfc_status sdfc_context_set_stream(sdfc_context* ctx, void* cuda_strea
 SDFC_API sdfc_status sdfc_context_synchronize(sdfc_context* ctx);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
 SDFC_API int64_t sdfc_context_launch_count(const sdfc_context* ctx);
+/* Per-kernel device timing with CUDA events recorded on the launching stream
+ * around each kernel of the batched path. Slots: 0 = detection (LOOP C),
+ * 1 = force / Jacobian (LOOP D), 2 = split reduction, 3 = system scatter.
+ * read_timing synchronises the stream, adds the elapsed times of every launch
+ * since the previous read into ms[4] / counts[4], and optionally resets. */
+SDFC_API sdfc_status sdfc_context_enable_timing(sdfc_context* ctx, int enable);
+SDFC_API sdfc_status sdfc_context_read_timing(sdfc_context* ctx, double ms[4], int64_t counts[4], int reset);
 
 /* ---- SDF grid: fields of BodySDFObj (Body/BodySDFObj.h:13-16) ---------- */
 /* grid_host: ni*nj*nk doubles. If every value is exactly representable in
