@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdfcontact_b200.so")
+LIB_PATH = os.environ.get("SDFC_LIB_PATH") or os.path.join(HERE, "libsdfcontact_b200.so")  # override: tuning builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -28,6 +28,7 @@ SIGNATURES = {
     "sdfc_context_launch_count": (C.c_int64, [C.c_void_p]),
     "sdfc_context_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "sdfc_context_read_timing": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int]),
+    "sdfc_selftest_exact_div": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_double, C.POINTER(C.c_int64)]),
     "sdfc_sdf_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double,
                                   C.c_double, C.c_double, c_double_p, c_void_pp]),
     "sdfc_sdf_set_col_th": (C.c_int, [C.c_void_p, C.c_double]),

@@ -4,8 +4,9 @@
 
 Output: assemble-them-all_b200/libsdfcontact_b200.so (git-ignored; it travels to
 the GPU box with the gpurun snapshot). nvcc cross-compiles without a GPU.
--fmad=false: the bit-critical part of the path must not contract a*b+c into an
-FMA (the reference's x86-64 build has none); see csrc/sdfc_device.cuh.
+The bit-critical part of the path is written with round-to-nearest intrinsics
+that nvcc never contracts into FMAs (the reference's x86-64 build has none); the
+remaining algebra may use FMAs. See csrc/sdfc_device.cuh.
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libsdfcontact_b200.so")
+OUT = os.environ.get("SDFC_OUT") or os.path.join(HERE, "libsdfcontact_b200.so")
 SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu"]
 FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7
 HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_step.cuh", FORCE_INST,
@@ -24,7 +25,7 @@ HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_step.c
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--compiler-bindir", "/usr/bin/g++",
 ]
@@ -49,13 +50,15 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not _stale():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.basename(OUT))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), []) for s in srcs]
-    jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"), [f"-DSDFC_FORCE_VARIANT={v}"])
-             for v in range(8)]
+    min_blocks = os.environ.get("SDFC_FORCE_MIN_BLOCKS")  # tuning knob: __launch_bounds__(128, n) of k_force
+    extra_all = [f"-DSDFC_FORCE_MIN_BLOCKS={int(min_blocks)}"] if min_blocks else []
+    jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"),
+              [f"-DSDFC_FORCE_VARIANT={v}", *extra_all]) for v in range(8)]
     for s, o, extra in jobs:
         cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o]
         if verbose:

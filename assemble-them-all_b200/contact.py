@@ -69,6 +69,12 @@ class Context:
         check(self._lib.sdfc_context_read_timing(self._h, ms, cnt, int(bool(reset))))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_SLOTS)}
 
+    def selftest_exact_div(self, n, seed, b):
+        """Mismatches between the library's reciprocal-based division and IEEE `/` (must be 0)."""
+        bad = C.c_int64(-1)
+        check(self._lib.sdfc_selftest_exact_div(self._h, int(n), int(seed), float(b), C.byref(bad)))
+        return int(bad.value)
+
     def close(self):
         if self._h:
             self._lib.sdfc_context_destroy(self._h)

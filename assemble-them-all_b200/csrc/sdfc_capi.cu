@@ -74,7 +74,7 @@ struct sdfc_sdf {
     sdfc_context* ctx = nullptr;
     GridDev dev{};
     double* d_g64 = nullptr;
-    float* d_g32 = nullptr;
+    float4* d_c32 = nullptr;  // fp32 cell records (2 float4 per cell) when the grid is fp32-lossless
     size_t count = 0;
     uint64_t version = 1;
     // grow-only scratch for the host-buffer sampling entry
@@ -87,6 +87,7 @@ struct sdfc_points {
     int n = 0;
     double* d_o = nullptr;  // original order SoA: x[n] y[n] z[n]
     double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
+    double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
     bool sorted = false;
 };
 
@@ -128,6 +129,7 @@ void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, 
     const sdfc_points* pts = p->pts;
     out->sx = pts->d_s; out->sy = pts->d_s + pts->n; out->sz = pts->d_s + 2 * (size_t)pts->n;
     out->ox = pts->d_o; out->oy = pts->d_o + pts->n; out->oz = pts->d_o + 2 * (size_t)pts->n;
+    out->wsphere = pts->d_wsphere;
     out->n = pts->n;
     out->n_words = (pts->n + 31) / 32;
     out->word_offset = word_offset;
@@ -266,6 +268,24 @@ sdfc_status sdfc_context_read_timing(sdfc_context* ctx, double ms[4], int64_t co
     return SDFC_OK;
 }
 
+sdfc_status sdfc_selftest_exact_div(sdfc_context* ctx, int64_t n, uint64_t seed, double b, int64_t* mismatches) {
+    SDFC_REQUIRE(ctx && mismatches, "sdfc_selftest_exact_div: NULL argument");
+    SDFC_REQUIRE(n > 0 && b > 0, "sdfc_selftest_exact_div: n and b must be positive");
+    SDFC_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    SDFC_CUDA(cudaMalloc((void**)&d, sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream);
+    launch_selftest_exact_div(n, seed, b, d, ctx->stream);
+    ctx->launches += 1;
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SDFC_ERR_CUDA, std::string("sdfc_selftest_exact_div: ") + cudaGetErrorString(e));
+    *mismatches = (int64_t)h;
+    return SDFC_OK;
+}
+
 // -------------------------------------------------------------------- sdf
 sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const double min_box[3], const double max_box[3],
                             double dx, double dy, double dz, double col_th, const double* grid_host, sdfc_sdf** out) {
@@ -287,17 +307,31 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
     if (st != SDFC_OK) { delete s; return st; }
     cudaError_t e = cudaMemcpy(s->d_g64, grid_host, s->count * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && lossless) {
-        st = dev_alloc(&s->d_g32, s->count);
-        if (st == SDFC_OK) e = cudaMemcpy(s->d_g32, g32.data(), s->count * sizeof(float), cudaMemcpyHostToDevice);
+        float* d_g32 = nullptr;
+        // cell records need 8x the plain fp32 grid; if that does not fit, stay on the fp64 path
+        if (cudaMalloc((void**)&d_g32, s->count * sizeof(float)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_c32, s->count * 2 * sizeof(float4)) == cudaSuccess) {
+            e = cudaMemcpy(d_g32, g32.data(), s->count * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                launch_build_cells(d_g32, ni, nj, nk, s->d_c32, ctx->stream);
+                ctx->launches += 1;
+                e = cudaStreamSynchronize(ctx->stream);
+            }
+        } else {
+            cudaGetLastError();
+            cudaFree(s->d_c32); s->d_c32 = nullptr;
+        }
+        cudaFree(d_g32);
     }
     if (e != cudaSuccess || st != SDFC_OK) {
-        cudaFree(s->d_g64); cudaFree(s->d_g32); delete s;
+        cudaFree(s->d_g64); cudaFree(s->d_c32); delete s;
         return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_create: upload failed: ") + cudaGetErrorString(e));
     }
-    s->dev.g64 = s->d_g64; s->dev.g32 = s->d_g32;
+    s->dev.g64 = s->d_g64; s->dev.c32 = s->d_c32;
     s->dev.ni = ni; s->dev.nj = nj; s->dev.nk = nk;
     for (int a = 0; a < 3; ++a) { s->dev.mn[a] = min_box[a]; s->dev.mx[a] = max_box[a]; }
     s->dev.dx = dx; s->dev.dy = dy; s->dev.dz = dz; s->dev.col_th = col_th;
+    s->dev.rdx = 1.0 / dx; s->dev.rdy = 1.0 / dy; s->dev.rdz = 1.0 / dz;  // IEEE division: correctly rounded
     *out = s;
     return SDFC_OK;
 }
@@ -307,11 +341,11 @@ sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th) {
     sdf->version++;
     return SDFC_OK;
 }
-int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && sdf->d_g32) ? 1 : 0; }
+int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && sdf->d_c32) ? 1 : 0; }
 sdfc_status sdfc_sdf_destroy(sdfc_sdf* s) {
     if (!s) return SDFC_OK;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_g64); cudaFree(s->d_g32); cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
+    cudaFree(s->d_g64); cudaFree(s->d_c32); cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
     delete s;
     return SDFC_OK;
 }
@@ -390,6 +424,7 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
     if (st != SDFC_OK) { delete p; return st; }
     cudaError_t e = cudaMemcpy(p->d_o, soa.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice);
     p->d_s = p->d_o;
+    std::vector<double> soa_sorted;
     if (e == cudaSuccess && morton_sort) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (int i = 0; i < n; ++i)
@@ -413,10 +448,34 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
         st = dev_alloc(&p->d_s, (size_t)3 * n);
         if (st == SDFC_OK) e = cudaMemcpy(p->d_s, srt.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice);
         p->sorted = true;
+        soa_sorted.swap(srt);
+    }
+    if (e == cudaSuccess && st == SDFC_OK) {
+        // per-word bounding spheres of the (sorted) order used by batched detection
+        const std::vector<double>& src = soa_sorted.empty() ? soa : soa_sorted;
+        const int nw = (n + 31) / 32;
+        std::vector<double> sph((size_t)4 * nw);
+        for (int w = 0; w < nw; ++w) {
+            const int i0 = w * 32, i1 = std::min(n, i0 + 32);
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int i = i0; i < i1; ++i)
+                for (int a = 0; a < 3; ++a) { const double v = src[(size_t)a * n + i]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+            double c[3], r2 = 0;
+            for (int a = 0; a < 3; ++a) c[a] = 0.5 * (lo[a] + hi[a]);
+            for (int i = i0; i < i1; ++i) {
+                double d2 = 0;
+                for (int a = 0; a < 3; ++a) { const double t = src[(size_t)a * n + i] - c[a]; d2 += t * t; }
+                r2 = std::max(r2, d2);
+            }
+            sph[4 * (size_t)w] = c[0]; sph[4 * (size_t)w + 1] = c[1]; sph[4 * (size_t)w + 2] = c[2];
+            sph[4 * (size_t)w + 3] = std::sqrt(r2) * (1.0 + 1e-12);
+        }
+        st = dev_alloc(&p->d_wsphere, sph.size());
+        if (st == SDFC_OK) e = cudaMemcpy(p->d_wsphere, sph.data(), sizeof(double) * sph.size(), cudaMemcpyHostToDevice);
     }
     if (e != cudaSuccess || st != SDFC_OK) {
         if (p->d_s != p->d_o) cudaFree(p->d_s);
-        cudaFree(p->d_o); delete p;
+        cudaFree(p->d_o); cudaFree(p->d_wsphere); delete p;
         return fail(SDFC_ERR_CUDA, std::string("sdfc_points_create: upload failed: ") + cudaGetErrorString(e));
     }
     *out = p;
@@ -427,7 +486,7 @@ sdfc_status sdfc_points_destroy(sdfc_points* p) {
     if (!p) return SDFC_OK;
     cudaSetDevice(p->ctx->device);
     if (p->d_s != p->d_o) cudaFree(p->d_s);
-    cudaFree(p->d_o);
+    cudaFree(p->d_o); cudaFree(p->d_wsphere);
     delete p;
     return SDFC_OK;
 }

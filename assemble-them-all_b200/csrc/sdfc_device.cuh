@@ -2,11 +2,15 @@
 //
 // Two groups of functions:
 //   * bit-critical: pose transforms, cell index, trilinear sample and the
-//     finite-difference stencils. They use only IEEE + - * / sqrt floor in the
-//     evaluation order the reference's x86-64 build executes (no FMA; the whole
-//     library is compiled with -fmad=false), so cell indices, active masks and
-//     per-point distances are bit-identical to the reference:
+//     finite-difference stencil differences. They are written with the
+//     round-to-nearest intrinsics (__dadd_rn / __dmul_rn / ..., which nvcc never
+//     contracts into FMAs) in the evaluation order the reference's x86-64 build
+//     executes, so cell indices, active masks, per-point distances and every
+//     SDF sample are bit-identical to the reference:
 //       Body/BodySDFObj.cpp:123-213,379-383, CollisionDetection.cpp:136-138.
+//     The quotients (x - min) / dx use exact_div(): a correctly rounded division
+//     from a precomputed correctly rounded reciprocal (5 FP64 instructions
+//     instead of the ~20 of a generic IEEE division; same bits).
 //   * contact algebra: BodySDFObj::collision (Body/BodySDFObj.cpp:239-377) and
 //     the per-contact terms of ForceGeneralSDFContact::computeForce
 //     [WithDerivative] (Force/ForceGeneralSDFContact.cpp:147-447), restated on
@@ -26,17 +30,36 @@ constexpr double kFdEps = 1e-5;   // BodySDFObj.cpp:178,191
 // Fields of BodySDFObj (Body/BodySDFObj.h:13-16) as the kernels see them.
 struct GridDev {
     const double* g64;
-    const float* g32;  // fp32-lossless copy or nullptr
+    // fp32-lossless CELL RECORDS or nullptr: for every cell (i,j,k) the 8 corner
+    // values the trilinear sample needs, contiguous and 32-byte aligned
+    // (2 x float4: {000,100,010,110}, {001,101,011,111}, upper neighbours already
+    // clamped as BodySDFObj.cpp:137-140 does). One query = one 32-byte sector
+    // instead of four scattered row segments; 8x the footprint of the plain fp32
+    // grid, which HBM capacity (180 GB) makes a non-issue.
+    const float4* c32;
     int ni, nj, nk;
     double mn[3], mx[3];
     double dx, dy, dz;
+    double rdx, rdy, rdz;  // RN(1/dx), RN(1/dy), RN(1/dz), computed on the host with an IEEE division
     double col_th;
 };
 
-template <bool F32>
-__device__ __forceinline__ double grid_at(const GridDev& G, int i, int j, int k) {
+// a / b, correctly rounded, given rb = RN(1/b). Markstein's sequence: a first
+// quotient, two FMA residual corrections; the last one yields RN(a/b) because rb
+// is the correctly rounded reciprocal and the corrected quotient is faithful
+// (Muller et al., Handbook of Floating-Point Arithmetic, thm. on division with
+// FMA). Valid without over/underflow: here a is 0 or >= 2^-60 and b is a grid
+// spacing. Verified against `/` on the GPU by sdfc_selftest_exact_div().
+__device__ __forceinline__ double exact_div(double a, double b, double rb) {
+    const double q0 = __dmul_rn(a, rb);
+    const double r0 = __fma_rn(-b, q0, a);
+    const double q1 = __fma_rn(r0, rb, q0);
+    const double r1 = __fma_rn(-b, q1, a);
+    return __fma_rn(r1, rb, q1);
+}
+
+__device__ __forceinline__ double grid_at64(const GridDev& G, int i, int j, int k) {
     const size_t idx = (size_t)i + (size_t)G.ni * ((size_t)j + (size_t)G.nj * (size_t)k);
-    if (F32) return (double)__ldg(G.g32 + idx);
     return __ldg(G.g64 + idx);
 }
 
@@ -45,24 +68,34 @@ __device__ __forceinline__ double grid_at(const GridDev& G, int i, int j, int k)
 template <bool F32>
 __device__ __forceinline__ void load_cell(const GridDev& G, int i, int j, int k, double v[8]) {
     i = max(0, min(i, G.ni - 1)); j = max(0, min(j, G.nj - 1)); k = max(0, min(k, G.nk - 1));
+    if (F32) {
+        const size_t idx = (size_t)i + (size_t)G.ni * ((size_t)j + (size_t)G.nj * (size_t)k);
+        const float4 a = __ldg(G.c32 + 2 * idx), b = __ldg(G.c32 + 2 * idx + 1);
+        v[0] = (double)a.x; v[1] = (double)a.y; v[2] = (double)a.z; v[3] = (double)a.w;
+        v[4] = (double)b.x; v[5] = (double)b.y; v[6] = (double)b.z; v[7] = (double)b.w;
+        return;
+    }
     const int ip = (i == G.ni - 1) ? i : i + 1;
     const int jp = (j == G.nj - 1) ? j : j + 1;
     const int kp = (k == G.nk - 1) ? k : k + 1;
-    v[0] = grid_at<F32>(G, i, j, k);   v[1] = grid_at<F32>(G, ip, j, k);
-    v[2] = grid_at<F32>(G, i, jp, k);  v[3] = grid_at<F32>(G, ip, jp, k);
-    v[4] = grid_at<F32>(G, i, j, kp);  v[5] = grid_at<F32>(G, ip, j, kp);
-    v[6] = grid_at<F32>(G, i, jp, kp); v[7] = grid_at<F32>(G, ip, jp, kp);
+    v[0] = grid_at64(G, i, j, k);   v[1] = grid_at64(G, ip, j, k);
+    v[2] = grid_at64(G, i, jp, k);  v[3] = grid_at64(G, ip, jp, k);
+    v[4] = grid_at64(G, i, j, kp);  v[5] = grid_at64(G, ip, j, kp);
+    v[6] = grid_at64(G, i, jp, kp); v[7] = grid_at64(G, ip, jp, kp);
 }
 
 // Lerp order i, then j, then k; form (1-c)*a + c*b   (BodySDFObj.cpp:143-153)
+__device__ __forceinline__ double lerp1(double c, double a, double b) {
+    return __dadd_rn(__dmul_rn(__dsub_rn(1.0, c), a), __dmul_rn(c, b));
+}
 __device__ __forceinline__ double lerp8(const double v[8], double ci, double cj, double ck) {
-    const double v00 = (1 - ci) * v[0] + ci * v[1];
-    const double v10 = (1 - ci) * v[2] + ci * v[3];
-    const double v01 = (1 - ci) * v[4] + ci * v[5];
-    const double v11 = (1 - ci) * v[6] + ci * v[7];
-    const double w0 = (1 - cj) * v00 + cj * v10;
-    const double w1 = (1 - cj) * v01 + cj * v11;
-    return (1 - ck) * w0 + ck * w1;
+    const double v00 = lerp1(ci, v[0], v[1]);
+    const double v10 = lerp1(ci, v[2], v[3]);
+    const double v01 = lerp1(ci, v[4], v[5]);
+    const double v11 = lerp1(ci, v[6], v[7]);
+    const double w0 = lerp1(cj, v00, v10);
+    const double w1 = lerp1(cj, v01, v11);
+    return lerp1(ck, w0, w1);
 }
 
 __device__ __forceinline__ bool in_box(const GridDev& G, double x, double y, double z) {
@@ -80,9 +113,11 @@ struct CellCache {
 template <bool F32>
 __device__ __forceinline__ double sample_inside(const GridDev& G, double x, double y, double z,
                                                 const CellCache* cache) {
-    double ci = (x - G.mn[0]) / G.dx, cj = (y - G.mn[1]) / G.dy, ck = (z - G.mn[2]) / G.dz;
+    double ci = exact_div(__dsub_rn(x, G.mn[0]), G.dx, G.rdx);
+    double cj = exact_div(__dsub_rn(y, G.mn[1]), G.dy, G.rdy);
+    double ck = exact_div(__dsub_rn(z, G.mn[2]), G.dz, G.rdz);
     const int i = (int)floor(ci), j = (int)floor(cj), k = (int)floor(ck);
-    ci = ci - i; cj = cj - j; ck = ck - k;
+    ci = __dsub_rn(ci, (double)i); cj = __dsub_rn(cj, (double)j); ck = __dsub_rn(ck, (double)k);
     if (cache != nullptr && i == cache->i && j == cache->j && k == cache->k) return lerp8(cache->v, ci, cj, ck);
     double v[8];
     load_cell<F32>(G, i, j, k, v);
@@ -99,8 +134,9 @@ __device__ __forceinline__ double query_sdf(const GridDev& G, double x, double y
     double bx = (x < G.mn[0]) ? G.mn[0] : x; bx = (G.mx[0] < bx) ? G.mx[0] : bx;
     double by = (y < G.mn[1]) ? G.mn[1] : y; by = (G.mx[1] < by) ? G.mx[1] : by;
     double bz = (z < G.mn[2]) ? G.mn[2] : z; bz = (G.mx[2] < bz) ? G.mx[2] : bz;
-    const double ex = x - bx, ey = y - by, ez = z - bz;
-    return sqrt((ex * ex + ey * ey) + ez * ez) + sample_inside<F32>(G, bx, by, bz, cache);
+    const double ex = __dsub_rn(x, bx), ey = __dsub_rn(y, by), ez = __dsub_rn(z, bz);
+    const double n2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+    return __dadd_rn(__dsqrt_rn(n2), sample_inside<F32>(G, bx, by, bz, cache));
 }
 
 // xw = R*xi + p, rows evaluated left to right   (CollisionDetection.cpp:136)
@@ -108,13 +144,16 @@ __device__ __forceinline__ double query_sdf(const GridDev& G, double x, double y
 __device__ __forceinline__ void to_world(const double* R, const double* p, double x0, double x1, double x2,
                                          double xw[3]) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) xw[r] = ((R[r * 3] * x0 + R[r * 3 + 1] * x1) + R[r * 3 + 2] * x2) + p[r];
+    for (int r = 0; r < 3; ++r)
+        xw[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[r * 3], x0), __dmul_rn(R[r * 3 + 1], x1)),
+                                    __dmul_rn(R[r * 3 + 2], x2)), p[r]);
 }
 // x = R^T (xw - p)   (BodySDFObj.cpp:209-211)
 __device__ __forceinline__ void to_local(const double* R, const double* p, const double xw[3], double x[3]) {
-    const double d0 = xw[0] - p[0], d1 = xw[1] - p[1], d2 = xw[2] - p[2];
+    const double d0 = __dsub_rn(xw[0], p[0]), d1 = __dsub_rn(xw[1], p[1]), d2 = __dsub_rn(xw[2], p[2]);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) x[r] = (R[r] * d0 + R[3 + r] * d1) + R[6 + r] * d2;
+    for (int r = 0; r < 3; ++r)
+        x[r] = __dadd_rn(__dadd_rn(__dmul_rn(R[r], d0), __dmul_rn(R[3 + r], d1)), __dmul_rn(R[6 + r], d2));
 }
 
 // ------------------------------------------------------------ small algebra
@@ -216,28 +255,31 @@ __device__ __forceinline__ int contact_eval(const GridDev& G, const PairPose& P,
     // ---- SDF samples; the cell of x is cached in registers
     CellCache cc;
     {
-        const double ci = (x[0] - G.mn[0]) / G.dx, cj = (x[1] - G.mn[1]) / G.dy, ck = (x[2] - G.mn[2]) / G.dz;
+        const double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
+        const double cj = exact_div(__dsub_rn(x[1], G.mn[1]), G.dy, G.rdy);
+        const double ck = exact_div(__dsub_rn(x[2], G.mn[2]), G.dz, G.rdz);
         cc.i = (int)floor(ci); cc.j = (int)floor(cj); cc.k = (int)floor(ck);
         load_cell<F32>(G, cc.i, cc.j, cc.k, cc.v);
     }
     const double s0 = query_sdf<F32>(G, x[0], x[1], x[2], true, &cc);  // x is inside for an active contact
-    const double d = query_sdf<F32>(G, x[0], x[1], x[2], false, &cc) + G.col_th;
+    const double d = __dadd_rn(query_sdf<F32>(G, x[0], x[1], x[2], false, &cc), G.col_th);
     // query_dSDF (BodySDFObj.cpp:176-187); axis samples are reused by query_ddSDF
     double qp[3], qm[3], g[3];
     {
-        qp[0] = query_sdf<F32>(G, x[0] + kFdEps, x[1], x[2], true, &cc);
-        qm[0] = query_sdf<F32>(G, x[0] - kFdEps, x[1], x[2], true, &cc);
-        qp[1] = query_sdf<F32>(G, x[0], x[1] + kFdEps, x[2], true, &cc);
-        qm[1] = query_sdf<F32>(G, x[0], x[1] - kFdEps, x[2], true, &cc);
-        qp[2] = query_sdf<F32>(G, x[0], x[1], x[2] + kFdEps, true, &cc);
-        qm[2] = query_sdf<F32>(G, x[0], x[1], x[2] - kFdEps, true, &cc);
+        qp[0] = query_sdf<F32>(G, __dadd_rn(x[0], kFdEps), x[1], x[2], true, &cc);
+        qm[0] = query_sdf<F32>(G, __dsub_rn(x[0], kFdEps), x[1], x[2], true, &cc);
+        qp[1] = query_sdf<F32>(G, x[0], __dadd_rn(x[1], kFdEps), x[2], true, &cc);
+        qm[1] = query_sdf<F32>(G, x[0], __dsub_rn(x[1], kFdEps), x[2], true, &cc);
+        qp[2] = query_sdf<F32>(G, x[0], x[1], __dadd_rn(x[2], kFdEps), true, &cc);
+        qm[2] = query_sdf<F32>(G, x[0], x[1], __dsub_rn(x[2], kFdEps), true, &cc);
+        constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) g[a] = (qp[a] - qm[a]) / (2 * kFdEps);
+        for (int a = 0; a < 3; ++a) g[a] = exact_div(__dsub_rn(qp[a], qm[a]), kTwoEps, kRTwoEps);
     }
     const double gn = sqrt(dot3(g, g));
     double e[3], n[3], xi2[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) e[a] = g[a] / gn;
+    for (int a = 0; a < 3; ++a) e[a] = g[a] / gn;  // 3 IEEE divisions; feeds n, xi2 (kept exact: cheap)
     mm<3, 3, 1>(R2, e, n);
 #pragma unroll
     for (int a = 0; a < 3; ++a) xi2[a] = x[a] - d * e[a];
@@ -312,18 +354,24 @@ __device__ __forceinline__ int contact_eval(const GridDev& G, const PairPose& P,
     double H[9];
     {
         const double h = kFdEps / 2;
-        H[0] = qp[0] + qm[0] - 2 * s0;
-        H[4] = qp[1] + qm[1] - 2 * s0;
-        H[8] = qp[2] + qm[2] - 2 * s0;
-        const double xy = query_sdf<F32>(G, x[0] + h, x[1] + h, x[2], true, &cc) + query_sdf<F32>(G, x[0] - h, x[1] - h, x[2], true, &cc)
-                        - query_sdf<F32>(G, x[0] + h, x[1] - h, x[2], true, &cc) - query_sdf<F32>(G, x[0] - h, x[1] + h, x[2], true, &cc);
-        const double xz = query_sdf<F32>(G, x[0] + h, x[1], x[2] + h, true, &cc) + query_sdf<F32>(G, x[0] - h, x[1], x[2] - h, true, &cc)
-                        - query_sdf<F32>(G, x[0] + h, x[1], x[2] - h, true, &cc) - query_sdf<F32>(G, x[0] - h, x[1], x[2] + h, true, &cc);
-        const double yz = query_sdf<F32>(G, x[0], x[1] + h, x[2] + h, true, &cc) + query_sdf<F32>(G, x[0], x[1] - h, x[2] - h, true, &cc)
-                        - query_sdf<F32>(G, x[0], x[1] + h, x[2] - h, true, &cc) - query_sdf<F32>(G, x[0], x[1] - h, x[2] + h, true, &cc);
+        const double two_s0 = __dmul_rn(2.0, s0);
+        H[0] = __dsub_rn(__dadd_rn(qp[0], qm[0]), two_s0);
+        H[4] = __dsub_rn(__dadd_rn(qp[1], qm[1]), two_s0);
+        H[8] = __dsub_rn(__dadd_rn(qp[2], qm[2]), two_s0);
+        const double xp = __dadd_rn(x[0], h), xm = __dsub_rn(x[0], h);
+        const double yp = __dadd_rn(x[1], h), ym = __dsub_rn(x[1], h);
+        const double zp = __dadd_rn(x[2], h), zm = __dsub_rn(x[2], h);
+        // v = q(++) + q(--) - q(+-) - q(-+), left to right
+        const double xy = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, yp, x[2], true, &cc), query_sdf<F32>(G, xm, ym, x[2], true, &cc)),
+                                              query_sdf<F32>(G, xp, ym, x[2], true, &cc)), query_sdf<F32>(G, xm, yp, x[2], true, &cc));
+        const double xz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, x[1], zp, true, &cc), query_sdf<F32>(G, xm, x[1], zm, true, &cc)),
+                                              query_sdf<F32>(G, xp, x[1], zm, true, &cc)), query_sdf<F32>(G, xm, x[1], zp, true, &cc));
+        const double yz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, x[0], yp, zp, true, &cc), query_sdf<F32>(G, x[0], ym, zm, true, &cc)),
+                                              query_sdf<F32>(G, x[0], yp, zm, true, &cc)), query_sdf<F32>(G, x[0], ym, zp, true, &cc));
         H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
+        constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) H[i] = H[i] / (kFdEps * kFdEps);
+        for (int i = 0; i < 9; ++i) H[i] = exact_div(H[i], kEps2, kREps2);
     }
 
     // ---- BodySDFObj::collision derivatives (BodySDFObj.cpp:314-376)

@@ -133,8 +133,11 @@ __device__ __forceinline__ void force_rounds(const ForceShared& S, int total, Si
     }
 }
 
+#ifndef SDFC_FORCE_MIN_BLOCKS
+#define SDFC_FORCE_MIN_BLOCKS 2
+#endif
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
-__global__ void __launch_bounds__(kForceThreads) k_force(BatchDev B, const double* __restrict__ E,
+__global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(BatchDev B, const double* __restrict__ E,
                                                          const double* __restrict__ phi) {
     constexpr bool DM = ANYFRIC || ANYDAMP;
     constexpr int NPART = DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kForceThreads) k_force(BatchDev B, const doubl
     const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
     const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
     const uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
-    const bool f32 = S.pd.grid.g32 != nullptr;
+    const bool f32 = S.pd.grid.c32 != nullptr;
     const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
     const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
 

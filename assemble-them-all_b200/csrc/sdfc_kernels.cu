@@ -15,7 +15,8 @@
 // HBM-bound integer/fp64 work: no tensor cores. Points are read as coalesced SoA
 // fp64; grid corners are gathered through L1/L2 (fp32-lossless copy when legal).
 // Reductions are fixed-tree (no floating-point atomics): results are reproducible.
-// Compiled with -fmad=false (see sdfc_device.cuh).
+// Bit-critical arithmetic uses non-contractable intrinsics (see sdfc_device.cuh);
+// the rest of the algebra is free to use FMAs.
 #include "sdfc_kernels.cuh"
 
 #include "sdfc_force.cuh"
@@ -43,32 +44,62 @@ __device__ __forceinline__ double detect_point(const GridDev& G, const double* R
     double xw[3], x[3];
     to_world(R1, p1, x0, x1, x2, xw);
     to_local(R2, p2, xw, x);
-    return query_sdf<F32>(G, x[0], x[1], x[2], false, nullptr) + G.col_th;  // BodySDFObj.cpp:212
+    return __dadd_rn(query_sdf<F32>(G, x[0], x[1], x[2], false, nullptr), G.col_th);  // BodySDFObj.cpp:212
 }
 
 template <bool F32>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int U = 2;  // words in flight per warp: all point loads of a group are issued before any use
     int cnt = 0;
-    double px[kDetectWordsPerWarp], py[kDetectWordsPerWarp], pz[kDetectWordsPerWarp];
-    bool inr[kDetectWordsPerWarp];
-#pragma unroll
-    for (int u = 0; u < kDetectWordsPerWarp; ++u) {  // issue all point loads first
-        const int w = word0 + warp * kDetectWordsPerWarp + u;
-        const int idx = w * 32 + lane;
-        inr[u] = (w < pd.n_words) && (idx < pd.n);
-        px[u] = inr[u] ? __ldg(pd.sx + idx) : 0.0;
-        py[u] = inr[u] ? __ldg(pd.sy + idx) : 0.0;
-        pz[u] = inr[u] ? __ldg(pd.sz + idx) : 0.0;
+    const int wbase = word0 + warp * kDetectWordsPerWarp;
+    // Broad phase, one lane per word: transform the word's bounding sphere centre
+    // into the SDF frame and test it against the grid box grown by the radius.
+    // Rigid motions preserve distances, so a culled word has no point inside the
+    // box (1e-7 absolute slack covers the rounding of the rotation); every such
+    // point would evaluate to FLT_MAX + col_th > 0, i.e. inactive.
+    unsigned live;
+    {
+        bool keep = false;
+        const int w = wbase + lane;
+        if (lane < kDetectWordsPerWarp && w < pd.n_words) {
+            const double* sp = pd.wsphere + 4 * (size_t)w;
+            double cw[3], cl[3];
+            to_world(R1, p1, __ldg(sp), __ldg(sp + 1), __ldg(sp + 2), cw);
+            to_local(R2, p2, cw, cl);
+            const double r = __ldg(sp + 3) + 1e-7;
+            keep = cl[0] >= pd.grid.mn[0] - r && cl[0] <= pd.grid.mx[0] + r &&
+                   cl[1] >= pd.grid.mn[1] - r && cl[1] <= pd.grid.mx[1] + r &&
+                   cl[2] >= pd.grid.mn[2] - r && cl[2] <= pd.grid.mx[2] + r;
+        }
+        live = __ballot_sync(0xffffffffu, keep);
     }
+    if (lane < kDetectWordsPerWarp && wbase + lane < pd.n_words && !((live >> lane) & 1u))
+        mask_row[pd.word_offset + wbase + lane] = 0u;  // culled words: empty mask
+    // surviving words, U at a time
+    while (live) {
+        int ws[U];
+        double px[U], py[U], pz[U];
+        bool inr[U];
 #pragma unroll
-    for (int u = 0; u < kDetectWordsPerWarp; ++u) {
-        const int w = word0 + warp * kDetectWordsPerWarp + u;
-        bool act = false;
-        if (inr[u]) act = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]) < 0.;
-        const unsigned m = __ballot_sync(0xffffffffu, act);
-        if (w < pd.n_words && lane == 0) { mask_row[pd.word_offset + w] = m; cnt += __popc(m); }
+        for (int u = 0; u < U; ++u) {
+            ws[u] = -1;
+            if (live) { ws[u] = wbase + (__ffs(live) - 1); live &= live - 1; }
+            const int idx = ws[u] * 32 + lane;
+            inr[u] = (ws[u] >= 0) && (idx < pd.n);
+            px[u] = inr[u] ? __ldg(pd.sx + idx) : 0.0;
+            py[u] = inr[u] ? __ldg(pd.sy + idx) : 0.0;
+            pz[u] = inr[u] ? __ldg(pd.sz + idx) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ws[u] < 0) continue;  // warp-uniform
+            bool act = false;
+            if (inr[u]) act = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]) < 0.;
+            const unsigned m = __ballot_sync(0xffffffffu, act);
+            if (lane == 0) { mask_row[pd.word_offset + ws[u]] = m; cnt += __popc(m); }
+        }
     }
     if (lane == 0 && cnt) atomicAdd(s_count, cnt);
 }
@@ -90,7 +121,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect_mask(BatchDev B, cons
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
     __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
-    if (pd.grid.g32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
+    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
     else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
@@ -217,7 +248,7 @@ __device__ __forceinline__ void query_points_body(const PairDev& pd, const doubl
         double xw[3], x[3];
         to_world(R1, p1, x0, x1, x2, xw);
         to_local(R2, p2, xw, x);
-        const double d = query_sdf<F32>(pd.grid, x[0], x[1], x[2], false, nullptr) + pd.grid.col_th;
+        const double d = __dadd_rn(query_sdf<F32>(pd.grid, x[0], x[1], x[2], false, nullptr), pd.grid.col_th);
         if (d_out) d_out[idx] = d;
         if (cell_out) {  // BodySDFObj::query_grid_location, BodySDFObj.cpp:379-383
             cell_out[3 * idx + 0] = (int)floor((x[0] - pd.grid.mn[0]) / pd.grid.dx);
@@ -241,7 +272,7 @@ __global__ void __launch_bounds__(256) k_query_points(PairDev pd, const double* 
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E2, 1, 0, 0, R2, p2, threadIdx.x - 32);
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    if (pd.grid.g32 != nullptr) query_points_body<true>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
+    if (pd.grid.c32 != nullptr) query_points_body<true>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
     else query_points_body<false>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(n_active, s_count);
@@ -267,7 +298,7 @@ void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const dou
                          cudaStream_t stream) {
     if (n <= 0) return;
     const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)148 * 16));
-    if (G.g32 != nullptr) k_sdf_distance<true><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
+    if (G.c32 != nullptr) k_sdf_distance<true><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
     else k_sdf_distance<false><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
 }
 
@@ -282,6 +313,46 @@ void launch_aos_to_soa(const double* aos, int64_t n, double* x, double* y, doubl
     if (n <= 0) return;
     const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)148 * 16));
     k_aos_to_soa<<<blocks, 256, 0, stream>>>(aos, n, x, y, z);
+}
+
+// Builds the fp32 cell records (see GridDev::c32) from the plain fp32 grid.
+__global__ void k_build_cells(const float* __restrict__ g, int ni, int nj, int nk, float4* __restrict__ out) {
+    const size_t n = (size_t)ni * nj * nk;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % ni), j = (int)((idx / ni) % nj), k = (int)(idx / ((size_t)ni * nj));
+        const int ip = (i == ni - 1) ? i : i + 1, jp = (j == nj - 1) ? j : j + 1, kp = (k == nk - 1) ? k : k + 1;
+        auto at = [&](int a, int b, int c) { return g[(size_t)a + (size_t)ni * ((size_t)b + (size_t)nj * (size_t)c)]; };
+        out[2 * idx] = make_float4(at(i, j, k), at(ip, j, k), at(i, jp, k), at(ip, jp, k));
+        out[2 * idx + 1] = make_float4(at(i, j, kp), at(ip, j, kp), at(i, jp, kp), at(ip, jp, kp));
+    }
+}
+void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, cudaStream_t stream) {
+    const size_t n = (size_t)ni * nj * nk;
+    const int blocks = (int)max((size_t)1, min((n + 255) / 256, (size_t)148 * 16));
+    k_build_cells<<<blocks, 256, 0, stream>>>(g32, ni, nj, nk, out);
+}
+
+// Self-test of exact_div(): n pseudo-random numerators (full 52-bit mantissas,
+// magnitudes 2^-40 .. 2^12) divided by b, compared bit for bit with the IEEE `/`.
+__global__ void k_selftest_exact_div(int64_t n, uint64_t seed, double b, double rb, unsigned long long* mismatches) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);  // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const uint64_t mant = z & 0x000FFFFFFFFFFFFFull;
+        const int e = (int)((z >> 52) % 53) - 40;  // exponent in [-40, 12]
+        const double a = __longlong_as_double((long long)(((uint64_t)(1023 + e) << 52) | mant));
+        const double q_ref = a / b;
+        const double q = exact_div(a, b, rb);
+        if (__double_as_longlong(q) != __double_as_longlong(q_ref)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+void launch_selftest_exact_div(int64_t n, uint64_t seed, double b, unsigned long long* mismatches, cudaStream_t stream) {
+    k_selftest_exact_div<<<148 * 8, 256, 0, stream>>>(n, seed, b, 1.0 / b, mismatches);
 }
 
 // min over n values: per-block minima into scratch[gridDim], then one block.

@@ -13,6 +13,10 @@ struct PairDev {
     // whenever a per-point output is returned to the caller.
     const double *sx, *sy, *sz;
     const double *ox, *oy, *oz;
+    // bounding sphere (cx, cy, cz, r) of every 32-point word of the sorted copy,
+    // in the contact body's frame: lets detection skip whole words that cannot
+    // reach the SDF's box (they would all return FLT_MAX, BodySDFObj.cpp:170)
+    const double* wsphere;
     int n;            // number of contact points
     int n_words;      // ceil(n / 32) mask words
     int word_offset;  // first mask word of this pair inside an environment's mask row
@@ -28,7 +32,7 @@ struct PairDev {
 constexpr int kNumWarps = 4;           // force kernel: warps per CTA
 constexpr int kForceThreads = 32 * kNumWarps;
 constexpr int kDetectThreads = 256;
-constexpr int kDetectWordsPerWarp = 2; // 64 points per warp per tile
+constexpr int kDetectWordsPerWarp = 8; // 256 points per warp per tile (2048 per CTA)
 constexpr int kDetectTileWords = (kDetectThreads / 32) * kDetectWordsPerWarp;
 
 constexpr int tr_out(int n) {  // values left per lane after the 5 halving steps
@@ -76,6 +80,8 @@ void launch_query_points(const PairDev& pair_host_copy, const double* E1, const 
 void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, double* out,
                          cudaStream_t stream);
 void launch_min_reduce(const double* v, int64_t n, double* out_scalar, double* scratch, cudaStream_t stream);
+void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, cudaStream_t stream);
+void launch_selftest_exact_div(int64_t n, uint64_t seed, double b, unsigned long long* mismatches, cudaStream_t stream);
 void launch_aos_to_soa(const double* aos, int64_t n, double* x, double* y, double* z, cudaStream_t stream);
 
 }  // namespace sdfc

@@ -71,6 +71,12 @@ SDFC_API int64_t sdfc_context_launch_count(const sdfc_context* ctx);
 SDFC_API sdfc_status sdfc_context_enable_timing(sdfc_context* ctx, int enable);
 SDFC_API sdfc_status sdfc_context_read_timing(sdfc_context* ctx, double ms[4], int64_t counts[4], int reset);
 
+/* Device self-test: n pseudo-random numerators divided by b with the library's
+ * reciprocal-based exact division, compared bit for bit with the IEEE division.
+ * mismatches must come back 0 (the cell index and the interpolation weights of
+ * query_SDF, BodySDFObj.cpp:132-134, depend on it). */
+SDFC_API sdfc_status sdfc_selftest_exact_div(sdfc_context* ctx, int64_t n, uint64_t seed, double b, int64_t* mismatches);
+
 /* ---- SDF grid: fields of BodySDFObj (Body/BodySDFObj.h:13-16) ---------- */
 /* grid_host: ni*nj*nk doubles. If every value is exactly representable in
  * fp32 (true for freshly generated grids, BodySDFObj.cpp:81-83) an fp32 copy

@@ -31,6 +31,13 @@ def make_pair(ctx, scene, G, fi, prm, sorted_pts=True):
     return p
 
 
+@pytest.mark.parametrize("b", [0.05000000074505806, 0.1, float(np.float32(10.0 / 511)), 0.0333333333333, 1.0, 0.7853981633974483])
+def test_exact_division_matches_ieee(cuda_ctx, b):
+    """(x - min) / dx is evaluated from a precomputed reciprocal; it must equal the
+    IEEE quotient for every numerator (cell index and lerp weights depend on it)."""
+    assert cuda_ctx.selftest_exact_div(200_000_000, 12345, b) == 0
+
+
 def test_grids_use_fp32_lossless_storage(scene):
     assert all(s.is_fp32 for s in scene["sdf"].values())
 
