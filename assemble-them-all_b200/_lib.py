@@ -62,7 +62,24 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "sdfc_batch_detect_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdfc_batch_queries_per_eval": (C.c_int64, [C.c_void_p]),
+    "sdfc_sim_create": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, c_void_pp]),
+    "sdfc_sim_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_sim_ndof_r": (C.c_int, [C.c_void_p]),
+    "sdfc_sim_set_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "sdfc_sim_get_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "sdfc_sim_set_external_force": (C.c_int, [C.c_void_p, c_double_p]),
+    "sdfc_sim_clear_contact_history": (C.c_int, [C.c_void_p]),
+    "sdfc_sim_forward": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
+    "sdfc_sim_get_status": (C.c_int, [C.c_void_p, c_uint8_p, c_uint8_p]),
+    "sdfc_sim_get_poses": (C.c_int, [C.c_void_p, c_double_p]),
+    "sdfc_sim_get_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
+
+
+class BodyDesc(C.Structure):
+    """struct sdfc_body_desc (include/sdfcontact_b200.h)."""
+    _fields_ = [("joint_type", C.c_int32), ("reserved", C.c_int32), ("E_pj_0", C.c_double * 16),
+                ("E_ji", C.c_double * 16), ("inertia", C.c_double * 6), ("mass", C.c_double)]
 
 _lib = None
 

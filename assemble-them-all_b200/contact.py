@@ -295,3 +295,110 @@ class ContactBatch:
         if self._h:
             self._lib.sdfc_batch_destroy(self._h)
             self._h = C.c_void_p()
+
+
+JOINT_FIXED, JOINT_TRANSLATIONAL, JOINT_FREE3D_EXP = 0, 1, 2
+JOINT_TYPES = {"fixed": JOINT_FIXED, "translational": JOINT_TRANSLATIONAL, "free3d-exp": JOINT_FREE3D_EXP}
+JOINT_NDOF = {JOINT_FIXED: 0, JOINT_TRANSLATIONAL: 3, JOINT_FREE3D_EXP: 6}
+
+
+class BatchedSimulation:
+    """Simulation::reset / set_state / forward / get_q ... (Simulation.cpp:73-122,894-993)
+    for E environments at once, device-resident, on top of a ContactBatch.
+
+    bodies: one dict per link in robot order with keys joint_type ("fixed" |
+    "translational" | "free3d-exp"), E_pj_0 (4,4), E_ji (4,4), inertia (6,), mass.
+    Reduced coordinates are ordered body by body (Robot.cpp:48-101)."""
+
+    def __init__(self, batch, bodies, gravity, h):
+        self.batch, self.ctx, self._lib = batch, batch.ctx, batch._lib
+        if len(bodies) != batch.n_bodies:
+            raise SdfContactError("[Error] BatchedSimulation: body count does not match the batch")
+        arr = (_lib.BodyDesc * len(bodies))()
+        self.joint_types = []
+        for i, b in enumerate(bodies):
+            jt = b["joint_type"]
+            jt = JOINT_TYPES[jt] if isinstance(jt, str) else int(jt)
+            self.joint_types.append(jt)
+            arr[i].joint_type = jt
+            arr[i].E_pj_0[:] = _colmajor44(b["E_pj_0"]).reshape(-1)
+            arr[i].E_ji[:] = _colmajor44(b["E_ji"]).reshape(-1)
+            arr[i].inertia[:] = _f64(b["inertia"]).reshape(6)
+            arr[i].mass = float(b["mass"])
+        g = _f64(gravity)
+        self.h = float(h)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_sim_create(batch._h, arr, _dp(g), self.h, C.byref(self._h)))
+        self.n_envs, self.n_bodies, self.n_pairs = batch.n_envs, batch.n_bodies, batch.n_pairs
+        self.ndof_r = int(self._lib.sdfc_sim_ndof_r(self._h))
+        self.dof_offset = np.cumsum([0] + [JOINT_NDOF[t] for t in self.joint_types])
+        self._fext = np.zeros((self.n_envs, self.n_bodies, 6))
+
+    # ---- state
+    def set_state(self, q, qdot):
+        q = _f64(np.broadcast_to(q, (self.n_envs, self.ndof_r)))
+        qd = _f64(np.broadcast_to(qdot, (self.n_envs, self.ndof_r)))
+        check(self._lib.sdfc_sim_set_state(self._h, _dp(q), _dp(qd)))
+
+    def get_state(self):
+        q = np.empty((self.n_envs, self.ndof_r))
+        qd = np.empty((self.n_envs, self.ndof_r))
+        check(self._lib.sdfc_sim_get_state(self._h, _dp(q), _dp(qd)))
+        return q, qd
+
+    def get_q(self):
+        return self.get_state()[0]
+
+    def get_qdot(self):
+        return self.get_state()[1]
+
+    def set_body_external_force(self, body, force):
+        """force: (6,) for every environment or (n_envs, 6)."""
+        self._fext[:, body, :] = np.broadcast_to(_f64(force), (self.n_envs, 6))
+        check(self._lib.sdfc_sim_set_external_force(self._h, _dp(self._fext)))
+
+    def reset(self, q=None, qdot=None):
+        """Simulation::reset: initial state, cleared contact history and external forces."""
+        self.set_state(np.zeros(self.ndof_r) if q is None else q, np.zeros(self.ndof_r) if qdot is None else qdot)
+        check(self._lib.sdfc_sim_clear_contact_history(self._h))
+        self._fext[:] = 0.0
+        check(self._lib.sdfc_sim_set_external_force(self._h, _dp(self._fext)))
+
+    # ---- stepping
+    def forward(self, n_steps, trajectory=False):
+        """n BDF1 steps of every environment. trajectory=True -> (q, qdot) of shape
+        (n_steps, n_envs, ndof_r) copied back once at the end."""
+        if not trajectory:
+            check(self._lib.sdfc_sim_forward(self._h, int(n_steps), None, None))
+            return None
+        Q = np.empty((n_steps, self.n_envs, self.ndof_r))
+        QD = np.empty((n_steps, self.n_envs, self.ndof_r))
+        check(self._lib.sdfc_sim_forward(self._h, int(n_steps), _dp(Q), _dp(QD)))
+        return Q, QD
+
+    def is_converged(self):
+        c = np.empty(self.n_envs, dtype=np.uint8)
+        check(self._lib.sdfc_sim_get_status(self._h, c.ctypes.data_as(_lib.c_uint8_p), None))
+        return c.astype(bool)
+
+    def get_contact_history(self):
+        """(n_envs, n_pairs) bool: the pair recorded a contact since the last reset."""
+        t = np.empty((self.n_envs, self.n_pairs), dtype=np.uint8)
+        check(self._lib.sdfc_sim_get_status(self._h, None, t.ctypes.data_as(_lib.c_uint8_p)))
+        return t.astype(bool)
+
+    def get_body_E0i(self):
+        """(n_envs, n_bodies, 4, 4) body poses at the current state."""
+        E = np.empty((self.n_envs, self.n_bodies, 4, 4))
+        check(self._lib.sdfc_sim_get_poses(self._h, _dp(E)))
+        return np.ascontiguousarray(np.swapaxes(E, -1, -2))
+
+    def stats(self):
+        s = (C.c_int64 * 4)()
+        check(self._lib.sdfc_sim_get_stats(self._h, s))
+        return {"rounds": int(s[0]), "deriv_env_evals": int(s[1]), "value_env_evals": int(s[2]), "env_steps": int(s[3])}
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_sim_destroy(self._h)
+            self._h = C.c_void_p()

@@ -1,8 +1,7 @@
 // sdfc_capi.cu — host side of the C-ABI declared in include/sdfcontact_b200.h.
 // Owns device buffers, uploads geometry once, stages poses, launches the kernels
 // of sdfc_kernels.cu. No CPU compute path: every entry needs a CUDA device.
-#include "../../include/sdfcontact_b200.h"
-#include "sdfc_kernels.cuh"
+#include "sdfc_host.h"
 
 #include <algorithm>
 #include <cmath>
@@ -14,114 +13,15 @@ using namespace sdfc;
 
 namespace {
 thread_local std::string g_last_error;
-
+}  // namespace
+namespace sdfc_host {
 sdfc_status fail(sdfc_status code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
-#define SDFC_CUDA(expr)                                                                         \
-    do {                                                                                        \
-        cudaError_t _e = (expr);                                                                \
-        if (_e != cudaSuccess)                                                                  \
-            return fail(SDFC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
-    } while (0)
-#define SDFC_REQUIRE(cond, msg) \
-    do {                        \
-        if (!(cond)) return fail(SDFC_ERR_INVALID, msg); \
-    } while (0)
-
-template <class T>
-sdfc_status dev_alloc(T** p, size_t count) {
-    *p = nullptr;
-    if (count == 0) return SDFC_OK;
-    SDFC_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
-    return SDFC_OK;
-}
-}  // namespace
-
-struct sdfc_context {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    int64_t launches = 0;
-    // optional per-kernel timing: (slot, start, stop) triples pending resolution
-    bool timing = false;
-    struct Span { int slot; cudaEvent_t a, b; };
-    std::vector<Span> spans;
-    std::vector<cudaEvent_t> free_events;
-    double acc_ms[4] = {0, 0, 0, 0};
-    int64_t acc_n[4] = {0, 0, 0, 0};
-
-    cudaEvent_t get_event() {
-        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
-        cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        return e;
-    }
-    void begin(int slot) {
-        if (!timing) return;
-        Span s{slot, get_event(), get_event()};
-        cudaEventRecord(s.a, stream);
-        spans.push_back(s);
-    }
-    void end() {
-        if (!timing) return;
-        cudaEventRecord(spans.back().b, stream);
-    }
-};
-
-struct sdfc_sdf {
-    sdfc_context* ctx = nullptr;
-    GridDev dev{};
-    double* d_g64 = nullptr;
-    float4* d_c32 = nullptr;  // fp32 cell records (2 float4 per cell) when the grid is fp32-lossless
-    size_t count = 0;
-    uint64_t version = 1;
-    // grow-only scratch for the host-buffer sampling entry
-    double* d_aos = nullptr; double* d_soa = nullptr; double* d_out = nullptr; double* d_red = nullptr;
-    int64_t scratch_n = 0;
-};
-
-struct sdfc_points {
-    sdfc_context* ctx = nullptr;
-    int n = 0;
-    double* d_o = nullptr;  // original order SoA: x[n] y[n] z[n]
-    double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
-    double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
-    bool sorted = false;
-};
-
-struct sdfc_pair {
-    sdfc_context* ctx = nullptr;
-    sdfc_points* pts = nullptr;
-    sdfc_sdf* sdf = nullptr;
-    double kn = 1, kt = 0, mu = 0, damping = 0, scale = 1, contact_scale = 1;
-    uint64_t version = 1;
-    sdfc_batch* single = nullptr;  // lazily created 1-env batch behind the per-pair entries
-    // per-point query scratch
-    double* d_d = nullptr; int32_t* d_cell = nullptr; uint8_t* d_active = nullptr; int32_t* d_count = nullptr;
-    double* d_E = nullptr;  // 32 doubles
-};
-
-struct sdfc_batch {
-    sdfc_context* ctx = nullptr;
-    int n_envs = 0, n_bodies = 0, n_pairs = 0;
-    std::vector<sdfc_pair*> pairs;
-    std::vector<int32_t> body_a, body_b;
-    std::vector<uint64_t> seen_pair_version, seen_sdf_version;
-    BatchDev dev{};
-    PairDev* d_pairs = nullptr;
-    int* d_tile_pair = nullptr; int* d_tile_word0 = nullptr;
-    uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; double* d_partial = nullptr;
-    double* d_fm_sub = nullptr; double* d_Km_sub = nullptr; double* d_Dm_sub = nullptr;
-    bool any_fric = false, any_damp = false;
-    int64_t queries = 0;
-    // staging for the host-buffer entry
-    double* d_E = nullptr; double* d_phi = nullptr; double* d_fm = nullptr; double* d_Km = nullptr; double* d_Dm = nullptr;
-    double* h_in = nullptr;   // pinned: E then phi
-    double* h_out = nullptr;  // pinned: fm, Km, Dm
-    int32_t* h_nact = nullptr;
-};
+}  // namespace sdfc_host
+using sdfc_host::dev_alloc;
+using sdfc_host::fail;
 
 namespace {
 
@@ -163,20 +63,33 @@ sdfc_status batch_refresh(sdfc_batch* b) {
     return SDFC_OK;
 }
 
-sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, bool scatter, double* fm_dev,
-                      double* Km_dev, double* Dm_dev, int32_t* n_active_dev) {
+}  // namespace
+
+namespace sdfc_host {
+sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
+                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev) {
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
     cudaStream_t s = b->ctx->stream;
     const bool dm = b->any_fric || b->any_damp;
     sdfc_context* c = b->ctx;
-    c->begin(0); launch_detect_mask(b->dev, E_dev, s); c->end();
-    c->begin(1); launch_force(b->dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s); c->end();
-    c->begin(2); launch_finalize_pairs(b->dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
+    BatchDev dev = b->dev;
+    dev.env_mode = env_mode_dev;
+    c->begin(0); launch_detect_mask(dev, E_dev, s); c->end();
+    c->begin(1);
+    if (env_mode_dev != nullptr) {
+        launch_force(dev, E_dev, phi_dev, false, b->any_fric, b->any_damp, s);
+        launch_force(dev, E_dev, phi_dev, true, b->any_fric, b->any_damp, s);
+        c->launches += 1;
+    } else {
+        launch_force(dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s);
+    }
+    c->end();
+    c->begin(2); launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
     c->launches += 3;
     if (scatter) {
         c->begin(3);
-        launch_scatter_system(b->dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
+        launch_scatter_system(dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
         c->end();
         c->launches += 1;
     }
@@ -186,7 +99,10 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     SDFC_CUDA(cudaGetLastError());
     return SDFC_OK;
 }
+}  // namespace sdfc_host
+using sdfc_host::batch_run;
 
+namespace {
 // 30-bit Morton code of a point quantised to 10 bits per axis inside [lo, hi].
 uint32_t expand10(uint32_t v) {
     v &= 0x3ffu;
@@ -591,7 +507,7 @@ static sdfc_status pair_eval(sdfc_pair* p, const double* E1, const double* phi1,
     std::memcpy(b->h_in + 38, phi2, 6 * sizeof(double));
     SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, 32 * sizeof(double), cudaMemcpyHostToDevice, s));
     SDFC_CUDA(cudaMemcpyAsync(b->d_phi, b->h_in + 32, 12 * sizeof(double), cudaMemcpyHostToDevice, s));
-    st = batch_run(b, b->d_E, b->d_phi, deriv, /*scatter=*/false, nullptr, nullptr, nullptr, nullptr);
+    st = batch_run(b, b->d_E, b->d_phi, deriv, nullptr, /*scatter=*/false, nullptr, nullptr, nullptr, nullptr);
     if (st != SDFC_OK) return st;
     SDFC_CUDA(cudaMemcpyAsync(b->h_out, b->d_fm_sub, 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (deriv) {
@@ -730,7 +646,7 @@ sdfc_status sdfc_batch_eval_device(sdfc_batch* b, const double* E_dev, const dou
     SDFC_REQUIRE(b && E_dev && phi_dev && fm_dev, "sdfc_batch_eval_device: NULL argument");
     SDFC_REQUIRE(!deriv || Km_dev, "sdfc_batch_eval_device: Km_dev is NULL with deriv != 0");
     SDFC_CUDA(cudaSetDevice(b->ctx->device));
-    return batch_run(b, E_dev, phi_dev, deriv, /*scatter=*/true, fm_dev, Km_dev, deriv ? Dm_dev : nullptr, n_active_dev);
+    return batch_run(b, E_dev, phi_dev, deriv, nullptr, /*scatter=*/true, fm_dev, Km_dev, deriv ? Dm_dev : nullptr, n_active_dev);
 }
 
 sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t* n_active_dev) {
@@ -759,7 +675,7 @@ sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* p
     std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double));
     SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, nE * sizeof(double), cudaMemcpyHostToDevice, s));
     SDFC_CUDA(cudaMemcpyAsync(b->d_phi, b->h_in + nE, nP * sizeof(double), cudaMemcpyHostToDevice, s));
-    sdfc_status st = batch_run(b, b->d_E, b->d_phi, deriv, /*scatter=*/true, b->d_fm, b->d_Km, deriv ? b->d_Dm : nullptr, nullptr);
+    sdfc_status st = batch_run(b, b->d_E, b->d_phi, deriv, nullptr, /*scatter=*/true, b->d_fm, b->d_Km, deriv ? b->d_Dm : nullptr, nullptr);
     if (st != SDFC_OK) return st;
     SDFC_CUDA(cudaMemcpyAsync(b->h_out, b->d_fm, nF * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (deriv) {

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(
     double* red = reinterpret_cast<double*>(smem_raw + sizeof(ForceShared));  // [kNumWarps][NPART]
 
     const int env = blockIdx.y;
+    if (B.env_mode != nullptr && __ldg(B.env_mode + env) != (DERIV ? 2 : 1)) return;  // CTA-uniform
     const int pair = blockIdx.x / B.splits, split = blockIdx.x % B.splits;
     if (__ldg(B.n_active + (size_t)env * B.n_pairs + pair) == 0) return;  // CTA-uniform
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

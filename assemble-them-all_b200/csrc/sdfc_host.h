@@ -1,0 +1,126 @@
+// sdfc_host.h — host-side object definitions shared by the C-ABI translation units
+// (sdfc_capi.cu: contact objects; sdfc_step.cu: batched BDF1 stepper). Internal.
+#pragma once
+#include "../../include/sdfcontact_b200.h"
+#include "sdfc_kernels.cuh"
+
+#include <string>
+#include <vector>
+
+namespace sdfc_host {
+sdfc_status fail(sdfc_status code, const std::string& msg);
+}
+#define SDFC_CUDA(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return sdfc_host::fail(SDFC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+#define SDFC_REQUIRE(cond, msg)                                        \
+    do {                                                               \
+        if (!(cond)) return sdfc_host::fail(SDFC_ERR_INVALID, msg);    \
+    } while (0)
+
+namespace sdfc_host {
+template <class T>
+sdfc_status dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return SDFC_OK;
+    SDFC_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return SDFC_OK;
+}
+}  // namespace sdfc_host
+
+struct sdfc_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // optional per-kernel timing: (slot, start, stop) triples pending resolution
+    bool timing = false;
+    struct Span { int slot; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double acc_ms[4] = {0, 0, 0, 0};
+    int64_t acc_n[4] = {0, 0, 0, 0};
+
+    cudaEvent_t get_event() {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int slot) {
+        if (!timing) return;
+        Span s{slot, get_event(), get_event()};
+        cudaEventRecord(s.a, stream);
+        spans.push_back(s);
+    }
+    void end() {
+        if (!timing) return;
+        cudaEventRecord(spans.back().b, stream);
+    }
+};
+
+struct sdfc_sdf {
+    sdfc_context* ctx = nullptr;
+    sdfc::GridDev dev{};
+    double* d_g64 = nullptr;
+    float4* d_c32 = nullptr;  // fp32 cell records (2 float4 per cell) when the grid is fp32-lossless
+    size_t count = 0;
+    uint64_t version = 1;
+    // grow-only scratch for the host-buffer sampling entry
+    double* d_aos = nullptr; double* d_soa = nullptr; double* d_out = nullptr; double* d_red = nullptr;
+    int64_t scratch_n = 0;
+};
+
+struct sdfc_points {
+    sdfc_context* ctx = nullptr;
+    int n = 0;
+    double* d_o = nullptr;  // original order SoA: x[n] y[n] z[n]
+    double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
+    double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
+    bool sorted = false;
+};
+
+struct sdfc_pair {
+    sdfc_context* ctx = nullptr;
+    sdfc_points* pts = nullptr;
+    sdfc_sdf* sdf = nullptr;
+    double kn = 1, kt = 0, mu = 0, damping = 0, scale = 1, contact_scale = 1;
+    uint64_t version = 1;
+    sdfc_batch* single = nullptr;  // lazily created 1-env batch behind the per-pair entries
+    // per-point query scratch
+    double* d_d = nullptr; int32_t* d_cell = nullptr; uint8_t* d_active = nullptr; int32_t* d_count = nullptr;
+    double* d_E = nullptr;  // 32 doubles
+};
+
+struct sdfc_batch {
+    sdfc_context* ctx = nullptr;
+    int n_envs = 0, n_bodies = 0, n_pairs = 0;
+    std::vector<sdfc_pair*> pairs;
+    std::vector<int32_t> body_a, body_b;
+    std::vector<uint64_t> seen_pair_version, seen_sdf_version;
+    sdfc::BatchDev dev{};
+    sdfc::PairDev* d_pairs = nullptr;
+    int* d_tile_pair = nullptr; int* d_tile_word0 = nullptr;
+    uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; double* d_partial = nullptr;
+    double* d_fm_sub = nullptr; double* d_Km_sub = nullptr; double* d_Dm_sub = nullptr;
+    bool any_fric = false, any_damp = false;
+    int64_t queries = 0;
+    // staging for the host-buffer entry
+    double* d_E = nullptr; double* d_phi = nullptr; double* d_fm = nullptr; double* d_Km = nullptr; double* d_Dm = nullptr;
+    double* h_in = nullptr;   // pinned: E then phi
+    double* h_out = nullptr;  // pinned: fm, Km, Dm
+    int32_t* h_nact = nullptr;
+};
+
+
+namespace sdfc_host {
+// Runs detection + force + per-pair finalisation (+ optional system scatter) of one batch.
+// env_mode_dev == nullptr: every environment is evaluated, with derivatives iff deriv != 0.
+// env_mode_dev != nullptr: per-environment 0 = skip, 1 = value only, 2 = with derivatives
+// (both force variants are launched; CTAs of non-matching environments exit at once).
+sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
+                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev);
+}  // namespace sdfc_host

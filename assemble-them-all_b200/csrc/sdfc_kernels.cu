@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect_mask(BatchDev B, cons
     __shared__ double R1[9], p1[3], R2[9], p2[3];
     __shared__ int s_count;
     const int tile = blockIdx.x, env = blockIdx.y;
+    if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;  // CTA-uniform
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
     {
         const int* src = reinterpret_cast<const int*>(B.pairs + pair);
@@ -151,6 +152,11 @@ void launch_force(const BatchDev& B, const double* E, const double* phi, bool de
 __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restrict__ fm_sub, double* __restrict__ Km_sub,
                                 double* __restrict__ Dm_sub) {
     const int pair = blockIdx.x, env = blockIdx.y;
+    if (B.env_mode != nullptr) {
+        const int m = __ldg(B.env_mode + env);
+        if (m == 0) return;
+        deriv = (m == 2) ? 1 : 0;
+    }
     const size_t ep = (size_t)env * B.n_pairs + pair;
     const bool empty = B.n_active[ep] == 0;
     const int npart = deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue;

@@ -58,6 +58,10 @@ struct BatchDev {
     uint32_t* mask;     // [n_envs][words_per_env]
     int32_t* n_active;  // [n_envs][n_pairs]
     double* partial;    // [n_envs][n_pairs][splits][kPartial*]
+    // optional per-environment evaluation mode (batched stepper): nullptr = every
+    // environment, derivative flag taken from the launch; else 0 = skip,
+    // 1 = value only, 2 = with derivatives
+    const int* env_mode;
 };
 
 // launches (all asynchronous on `stream`)

@@ -181,6 +181,61 @@ SDFC_API sdfc_status sdfc_batch_detect_device(sdfc_batch* batch, const double* E
 /* Total detection queries one batch evaluation performs = n_envs * sum_p n_p. */
 SDFC_API int64_t sdfc_batch_queries_per_eval(const sdfc_batch* batch);
 
+/* ---- batched BDF1 stepper: Simulation::forward for E environments -------- */
+/* The caller side of the contact path, device-resident:
+ * joint + body kinematics (Joint/Joint.cpp:95-141, JointFixed / JointTranslational /
+ * JointFree3DExp + JointSphericalExp, Body/Body.cpp:138-181), body forces
+ * (Body/Body.cpp:250-330), reduced assembly M, f, K, D (Simulation.cpp:379-503),
+ * BDF1 residual and Jacobian (Simulation.cpp:1081-1112), Newton with the
+ * reference's halving line search and strike rules, partial-pivot LU
+ * (Simulation.cpp:999-1079), reparam (JointSphericalExp.cpp:237-264).
+ * Robots are "flat": every link is a root link with its own joint, which is what
+ * examples/run_joint_plan.py:140-178 and test_joint_sim.py:24-63 emit. Reduced
+ * coordinates are ordered body by body (the reference's DFS joint order,
+ * Robot.cpp:48-101); at most 2 non-fixed bodies / 12 reduced dofs. */
+typedef struct sdfc_sim sdfc_sim;
+#define SDFC_JOINT_FIXED 0         /* Joint/JointFixed.cpp */
+#define SDFC_JOINT_TRANSLATIONAL 1 /* Joint/JointTranslational.cpp, q = p */
+#define SDFC_JOINT_FREE3D_EXP 2    /* Joint/JointFree3DExp.cpp, q = (p, r) */
+
+typedef struct sdfc_body_desc {
+    int32_t joint_type;
+    int32_t reserved;
+    double E_pj_0[16]; /* Joint::_E_pj_0 (Joint/Joint.cpp:23-31), column-major */
+    double E_ji[16];   /* Body::_E_ji (Body/Body.h), column-major */
+    double inertia[6]; /* Body::_Inertia: principal moments (3), mass (3) */
+    double mass;       /* Body::_mass */
+} sdfc_body_desc;
+
+/* `batch` supplies n_envs, n_bodies and the contact forces in force order
+ * (Robot::_forces); bodies[n_bodies]; gravity = Options::_gravity; h = _h. */
+SDFC_API sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, const double gravity[3],
+                                     double h, sdfc_sim** out);
+SDFC_API sdfc_status sdfc_sim_destroy(sdfc_sim* sim);
+SDFC_API int sdfc_sim_ndof_r(const sdfc_sim* sim);
+/* Simulation::set_state (Simulation.cpp:73): q, qdot [n_envs][ndof_r], host. */
+SDFC_API sdfc_status sdfc_sim_set_state(sdfc_sim* sim, const double* q_host, const double* qdot_host);
+SDFC_API sdfc_status sdfc_sim_get_state(sdfc_sim* sim, double* q_host, double* qdot_host);
+/* Simulation::set_body_external_force (Simulation.cpp:272): [n_envs][n_bodies][6]. */
+SDFC_API sdfc_status sdfc_sim_set_external_force(sdfc_sim* sim, const double* f_host);
+/* Simulation::reset's clear_all_contact_bodies (Simulation.cpp:896). */
+SDFC_API sdfc_status sdfc_sim_clear_contact_history(sdfc_sim* sim);
+/* Simulation::forward(n_steps) (Simulation.cpp:914) for every environment.
+ * q_traj_host / qdot_traj_host: [n_steps][n_envs][ndof_r] or NULL; with NULL the
+ * call moves no per-step data to the host (state stays in HBM). */
+SDFC_API sdfc_status sdfc_sim_forward(sdfc_sim* sim, int n_steps, double* q_traj_host, double* qdot_traj_host);
+/* converged[n_envs]: Simulation::is_converged of the last step (Simulation.cpp:995);
+ * touched[n_envs][n_pairs]: contact history since the last clear
+ * (CollisionDetection.cpp:143-146). Either may be NULL. */
+SDFC_API sdfc_status sdfc_sim_get_status(sdfc_sim* sim, uint8_t* converged, uint8_t* touched);
+/* Simulation::get_body_E0i (Simulation.cpp:248) at the current state:
+ * [n_envs][n_bodies][16] column-major. */
+SDFC_API sdfc_status sdfc_sim_get_poses(sdfc_sim* sim, double* E_host);
+/* Counters since creation: [0] evaluation rounds launched, [1] environment
+ * evaluations with derivatives, [2] value-only environment evaluations,
+ * [3] environment steps completed. */
+SDFC_API sdfc_status sdfc_sim_get_stats(sdfc_sim* sim, int64_t stats[4]);
+
 #ifdef __cplusplus
 }
 #endif

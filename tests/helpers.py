@@ -69,3 +69,36 @@ def load_contact_golden():
 
 def load_traj_golden():
     return np.load(os.path.join(GOLDEN, "traj_small.npz"))
+
+
+# ---------------------------------------------------------------- stepper fixtures
+JOINT_KEYS = {"translational": "translational", "free3d-exp": "free3d_exp"}
+
+
+def traj_bodies(T, joint_type):
+    """Body descriptors of the traj_small scene (part0 moving, part1 fixed): the
+    reference's own mass properties / frames, dumped by oracle/make_golden.py."""
+    key = JOINT_KEYS[joint_type]
+    out = []
+    for name, jt in (("part0", joint_type), ("part1", "fixed")):
+        E_ij = T[f"{key}_{name}_E_ij"]
+        E_ji = np.eye(4)
+        E_ji[:3, :3] = E_ij[:3, :3].T
+        E_ji[:3, 3] = -E_ij[:3, :3].T @ E_ij[:3, 3]
+        out.append({"joint_type": jt, "E_pj_0": np.eye(4), "E_ji": E_ji, "inertia": T[f"{key}_{name}_inertia"],
+                    "mass": float(T[f"{key}_{name}_mass"])})
+    return out
+
+
+def oracle_sim(G, T, joint_type, kn=1e6, kt=1e3, mu=0.0, damping=0.0):
+    """oracle.sim_oracle.Sim of the traj_small scene."""
+    from oracle import sdfc_oracle as O, sim_oracle as S
+    O.build()
+    jt = {"fixed": S.FIXED, "translational": S.TRANSLATIONAL, "free3d-exp": S.FREE3D_EXP}
+    bodies = [S.BodyDesc(jt[b["joint_type"]], b["E_pj_0"], b["E_ji"], np.asarray(b["inertia"], dtype=np.float64), b["mass"])
+              for b in traj_bodies(T, joint_type)]
+    grids = {n: O.Grid.from_dict(G.grid_dict(n)) for n in G.names}
+    pairs = [S.PairDesc(0, 1, grids["part1"], G.points("part0"), kn, kt, mu, damping),
+             S.PairDesc(1, 0, grids["part0"], G.points("part1"), kn, kt, mu, damping)]
+    key = JOINT_KEYS[joint_type]
+    return S.Sim(bodies, pairs, float(T[f"{key}_h"]), np.array([0.0, 0.0, 1e-12]))

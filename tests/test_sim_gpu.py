@@ -1,0 +1,142 @@
+"""GPU parity of the batched BDF1 stepper (sdfc_sim_*, through the C-ABI) against
+the reference's own trajectories (tests/golden/traj_small.npz) and the CPU oracle.
+Bars as in tests/test_sim_oracle.py: q 1e-9 relative, qdot 1e-6 relative,
+convergence flags / contact history exact."""
+import numpy as np
+import pytest
+
+from tests.helpers import load_traj_golden, oracle_sim, rel_err, traj_bodies
+
+pytestmark = pytest.mark.gpu
+Q_RTOL, QDOT_RTOL = 1e-9, 1e-6
+
+
+def build(ctx, G, T, joint_type, n_envs, kn=1e6, kt=1e3, mu=0.0, damping=0.0):
+    from assemble_them_all_b200 import contact
+    sdf = {n: contact.SdfGrid.from_dict(ctx, G.grid_dict(n)) for n in G.names}
+    pts = {n: contact.ContactPoints(ctx, G.points(n)) for n in G.names}
+    pairs = [contact.ForceGeneralSDFContact(ctx, pts["part0"], sdf["part1"], kn, kt, mu, damping, 0, 6),
+             contact.ForceGeneralSDFContact(ctx, pts["part1"], sdf["part0"], kn, kt, mu, damping, 6, 0)]
+    batch = contact.ContactBatch(ctx, n_envs, 2, pairs, [0, 1], [1, 0])
+    key = joint_type.replace("-", "_")
+    sim = contact.BatchedSimulation(batch, traj_bodies(T, joint_type), [0.0, 0.0, 1e-12], float(T[f"{key}_h"]))
+    return sim
+
+
+@pytest.mark.parametrize("joint_type", ["translational", "free3d-exp"])
+def test_trajectory_matches_reference_golden(cuda_ctx, golden_contact, joint_type):
+    T = load_traj_golden()
+    key = joint_type.replace("-", "_")
+    steps = int(T["steps"])
+    sim = build(cuda_ctx, golden_contact, T, joint_type, n_envs=3)
+    assert sim.ndof_r == (3 if joint_type == "translational" else 6)
+    sim.reset()
+    sim.set_body_external_force(0, T[f"{key}_force"])
+    Q, QD = sim.forward(steps, trajectory=True)
+    Qr, QDr, CV = T[f"{key}_q"], T[f"{key}_qdot"], T[f"{key}_converged"]
+    for s in range(steps):
+        for e in range(3):
+            assert rel_err(Qr[s + 1], Q[s, e]) <= Q_RTOL, f"step {s} env {e}: q"
+            assert rel_err(QDr[s + 1], QD[s, e]) <= QDOT_RTOL, f"step {s} env {e}: qdot"
+    # identical environments are bit-identical (fixed-order reductions)
+    assert np.array_equal(Q[:, 0], Q[:, 1]) and np.array_equal(QD[:, 0], QD[:, 2])
+    q, qd = sim.get_state()
+    assert np.array_equal(q, Q[-1]) and np.array_equal(qd, QD[-1])
+    assert np.array_equal(sim.is_converged(), np.full(3, bool(CV[-1])))
+    hist = sim.get_contact_history()
+    assert hist[:, 0].all()
+    E = sim.get_body_E0i()
+    assert rel_err(T[f"{key}_part0_E_final"], E[0, 0]) <= 1e-9
+    assert rel_err(T[f"{key}_part1_E_final"], E[0, 1]) <= 1e-9
+    st = sim.stats()
+    assert st["env_steps"] == 3 * steps and st["deriv_env_evals"] >= 3 * steps
+    sim.close()
+
+
+def test_forward_in_chunks_equals_one_call(cuda_ctx, golden_contact):
+    """forward(100) == 10 x forward(10): the planner's frame_skip loop (run_joint_plan.py:551-554)."""
+    T = load_traj_golden()
+    sim = build(cuda_ctx, golden_contact, T, "translational", n_envs=2)
+    sim.reset()
+    sim.set_body_external_force(0, T["translational_force"])
+    Q1, _ = sim.forward(60, trajectory=True)
+    sim.reset()
+    sim.set_body_external_force(0, T["translational_force"])
+    chunks = [sim.forward(10, trajectory=True)[0] for _ in range(6)]
+    assert np.array_equal(Q1, np.concatenate(chunks))
+    sim.close()
+
+
+@pytest.mark.parametrize("joint_type,mu,damping", [("translational", 0.0, 0.0), ("free3d-exp", 0.0, 0.0),
+                                                  ("free3d-exp", 0.3, 10.0)])
+def test_heterogeneous_envs_match_oracle(cuda_ctx, golden_contact, joint_type, mu, damping):
+    """Every environment gets its own push and start state, so Newton iteration and
+    line-search counts differ across the batch; each must follow the CPU oracle."""
+    T = load_traj_golden()
+    rng = np.random.default_rng(7)
+    n_envs, steps = 6, 40
+    sim = build(cuda_ctx, golden_contact, T, joint_type, n_envs, mu=mu, damping=damping)
+    nr = sim.ndof_r
+    q0 = rng.uniform(-0.02, 0.02, size=(n_envs, nr))
+    qd0 = rng.uniform(-0.3, 0.3, size=(n_envs, nr))
+    if nr == 6:
+        q0[:, 3:] *= 0.5
+        q0[0, 3:] = 0.0  # small-angle branch of JointSphericalExp::update
+    force = np.zeros((n_envs, 6))
+    force[:, 3:] = rng.uniform(-120, 120, size=(n_envs, 3))
+    if nr == 6:
+        force[:, :3] = rng.uniform(-60, 60, size=(n_envs, 3))
+    sim.reset(q0, qd0)
+    sim.set_body_external_force(0, force)
+    Q, QD = sim.forward(steps, trajectory=True)
+    conv = sim.is_converged()
+    hist = sim.get_contact_history()
+    for e in range(n_envs):
+        ref = oracle_sim(golden_contact, T, joint_type, mu=mu, damping=damping)
+        ref.q, ref.qdot = q0[e].copy(), qd0[e].copy()
+        ref.f_ext[0] = force[e]
+        for s in range(steps):
+            ref.step()
+            assert rel_err(ref.q, Q[s, e]) <= Q_RTOL, f"env {e} step {s}: q"
+            assert rel_err(ref.qdot, QD[s, e]) <= QDOT_RTOL, f"env {e} step {s}: qdot"
+        assert bool(conv[e]) == ref.converged
+        assert np.array_equal(hist[e], ref.touched)
+    sim.close()
+
+
+def test_large_rotation_reparam(cuda_ctx, golden_contact):
+    """|r| beyond 1.5 pi is wrapped at the end of the step (JointSphericalExp.cpp:237-264)."""
+    T = load_traj_golden()
+    sim = build(cuda_ctx, golden_contact, T, "free3d-exp", n_envs=2)
+    q0 = np.zeros((2, 6)); qd0 = np.zeros((2, 6))
+    q0[:, 2] = 30.0                      # far away from part1: free flight
+    q0[0, 3:] = [0.0, 0.0, 4.70]         # just below 1.5 pi = 4.712
+    q0[1, 3:] = [0.3, 0.0, 1.0]
+    qd0[:, 3:] = [0.0, 0.0, 40.0]        # crosses the threshold within a few steps
+    sim.reset(q0, qd0)
+    Q, QD = sim.forward(5, trajectory=True)
+    ref = oracle_sim(golden_contact, T, "free3d-exp")
+    ref.q, ref.qdot = q0[0].copy(), qd0[0].copy()
+    wrapped = False
+    for s in range(5):
+        ref.step()
+        wrapped |= np.linalg.norm(ref.q[3:]) < 4.0
+        assert rel_err(ref.q, Q[s, 0]) <= Q_RTOL and rel_err(ref.qdot, QD[s, 0]) <= QDOT_RTOL
+    assert wrapped
+    sim.close()
+
+
+def test_rejects_unsupported_models(cuda_ctx, golden_contact):
+    from assemble_them_all_b200 import contact
+    T = load_traj_golden()
+    bodies = traj_bodies(T, "translational")
+    bodies[1]["joint_type"] = 7
+    sim = None
+    with pytest.raises(contact.SdfContactError):
+        G = golden_contact
+        sdf = contact.SdfGrid.from_dict(cuda_ctx, G.grid_dict("part1"))
+        pts = contact.ContactPoints(cuda_ctx, G.points("part0"))
+        pair = contact.ForceGeneralSDFContact(cuda_ctx, pts, sdf, 1e6, 1e3)
+        batch = contact.ContactBatch(cuda_ctx, 1, 2, [pair], [0], [1])
+        sim = contact.BatchedSimulation(batch, bodies, [0, 0, 0], 1e-3)
+    assert sim is None
