@@ -59,6 +59,21 @@ class SceneBody:
     points: np.ndarray       # (n,3) body frame
     grid: synth.GridSpec     # body frame
     rest_E: np.ndarray       # (4,4) pose in the assembled configuration
+    mass: float = 1.0        # Body::_mass (density 1, run_joint_plan.py:162)
+    inertia: np.ndarray = None   # Body::_Inertia: principal moments about the body frame (3), mass (3)
+    joint_type: str = "fixed"
+
+    def desc(self):
+        """Stepper descriptor: the joint sits at the world origin (pos 0, frame WORLD,
+        run_joint_plan.py:161), so E_pj_0 = I and E_ji = rest pose of the body frame."""
+        return {"joint_type": self.joint_type, "E_pj_0": np.eye(4), "E_ji": self.rest_E, "inertia": self.inertia,
+                "mass": self.mass}
+
+
+def _box_inertia(size, density=1.0):
+    a, b, c = size
+    m = density * a * b * c
+    return m, m / 12.0 * np.array([b * b + c * c, a * a + c * c, a * a + b * b])
 
 
 @dataclass
@@ -109,12 +124,18 @@ def peg_hole_bodies(n_vertices=10000, sdf_dx=0.05, col_th=0.01):
         hole = _box_sdf(p[:, :2], np.array([1.05, 1.05]))
         return np.maximum(_box_sdf(p, half_blk), -hole)
 
+    m_peg, I_peg = _box_inertia(2 * half_peg)
+    m_blk, I_blk = _box_inertia(2 * half_blk)
+    m_hole, I_hole = _box_inertia((2.1, 2.1, 4.0))  # concentric with the block: moments subtract
+    props = {"0": (m_peg, I_peg), "1": (m_blk - m_hole, I_blk - I_hole)}
     for pid, fn in (("0", sd_peg), ("1", sd_block)):
         V, _ = parts[pid]
-        c = 0.5 * (V.min(0) + V.max(0))
+        c = 0.5 * (V.min(0) + V.max(0))  # == centre of mass for both shapes
         Vb = V - c
         grid = analytic_grid(fn, Vb.min(0), Vb.max(0), sdf_dx, col_th)
-        out.append(SceneBody(f"part{pid}", np.ascontiguousarray(Vb), grid, synth.make_E(np.eye(3), c)))
+        m, I3 = props[pid]
+        out.append(SceneBody(f"part{pid}", np.ascontiguousarray(Vb), grid, synth.make_E(np.eye(3), c), float(m),
+                             np.concatenate([I3, [m, m, m]])))
     return out
 
 
@@ -141,6 +162,69 @@ def c2_bfs_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sdf_dx=
         phi[e, 0, 3:] = a * rng.uniform(0.05, 0.3)  # body frame == world axes (identity rotation)
     return ContactScene(bodies, [(0, 1), (1, 0)], 1e6, 1e3, 0.0, 0.0, E, phi,
                         label=f"C2 two-part BFS translational, {n_envs} rollouts, 2x~{n_vertices} contact pts, dx {sdf_dx}")
+
+
+@dataclass
+class RolloutScene:
+    """Start states of batched planner rollouts for the stepper (sdfc_sim_* / Simulation::forward)."""
+    bodies: list
+    pairs: list
+    q0: np.ndarray        # (n_envs, ndof_r)
+    qdot0: np.ndarray
+    f_ext: np.ndarray     # (n_envs, n_bodies, 6): set_body_external_force (run_joint_plan.py:270-278)
+    h: float
+    gravity: np.ndarray
+    kn: float = 1e6
+    kt: float = 1e3
+    mu: float = 0.0
+    damping: float = 0.0
+    frame_skip: int = 100
+    label: str = ""
+
+    @property
+    def n_envs(self):
+        return len(self.q0)
+
+    @property
+    def queries_per_eval(self):
+        return self.n_envs * sum(len(self.bodies[a].points) for a, _ in self.pairs)
+
+    def upload(self, ctx):
+        from . import contact
+        sdf = [contact.SdfGrid.from_spec(ctx, b.grid) for b in self.bodies]
+        pts = [contact.ContactPoints(ctx, b.points) for b in self.bodies]
+        pairs = [contact.ForceGeneralSDFContact(ctx, pts[a], sdf[b], self.kn, self.kt, self.mu, self.damping,
+                                                index_contact=6 * a, index_sdf=6 * b) for a, b in self.pairs]
+        batch = contact.ContactBatch(ctx, self.n_envs, len(self.bodies), pairs, [a for a, _ in self.pairs],
+                                     [b for _, b in self.pairs])
+        sim = contact.BatchedSimulation(batch, [b.desc() for b in self.bodies], self.gravity, self.h)
+        return sim, batch, pairs, sdf, pts
+
+
+def c2_planner_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sdf_dx=0.05, col_th=0.01,
+                        joint_type="translational", force_mag=100.0):
+    """C2 as the BFS planner drives it (run_joint_plan.py:511-570): environment e starts
+    at rest with the peg offset z0 in [0, 3] along the hole axis (a BFS node), applies
+    axis action e % 6 (e % 12 with rotation) with force_mag 100 and integrates frame_skip = 100 BDF1
+    steps of h = float(1e-3), gravity (0, 0, 1e-12) (run_joint_plan.py:149)."""
+    rng = np.random.default_rng(seed)
+    bodies = peg_hole_bodies(n_vertices, sdf_dx, col_th)
+    bodies[0].joint_type = joint_type
+    nr = 3 if joint_type == "translational" else 6
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64)
+    q0 = np.zeros((n_envs, nr))
+    f = np.zeros((n_envs, 2, 6))
+    n_act = 6 if nr == 3 else 12
+    for e in range(n_envs):
+        q0[e, 2] = rng.uniform(0.0, 3.0)
+        a = e % n_act
+        if a < 6:
+            f[e, 0, 3:] = dirs[a] * force_mag          # translation action
+        else:
+            f[e, 0, :3] = 3.0 * dirs[a - 6] * force_mag  # rotation action (run_joint_plan.py:275)
+    return RolloutScene(bodies, [(0, 1), (1, 0)], q0, np.zeros((n_envs, nr)), f, float(np.float32(1e-3)),
+                        np.array([0.0, 0.0, 1e-12]),
+                        label=f"C2 two-part BFS {joint_type}, {n_envs} rollouts x frame_skip 100, 2x~{n_vertices} contact pts, dx {sdf_dx}")
 
 
 def sweep_scene(n_points, grid_n, active_frac=0.05, seed=synth.SWEEP_SEED):

@@ -63,24 +63,10 @@ def _ref_worker_init(scene_blob, use_ref):
     _W["kind"] = "port"
     if use_ref:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
-            import ref_probe
-            from assemble_them_all_b200 import synth
-            tmp = tempfile.mkdtemp(prefix="bench_ref_")
-            # placeholder meshes: geometry is overwritten below, so keep construction cheap
-            for pid in ("0", "1"):
-                V, F = synth.box_mesh((1.0, 1.0, 1.0), h=0.5)
-                synth.write_obj(os.path.join(tmp, f"{pid}.obj"), V, F)
-            xml = synth.planner_xml(tmp, "0", ["1"], sdf_dx=0.5, col_th=sc["col_th"])
-            p = ref_probe.Probe(xml, tmp)
-            for b, name in enumerate(("part0", "part1")):
-                g = sc["grids"][b]
-                p.set_contact_points(name, sc["points"][b])
-                p.set_sdf_grid(name, g["ni"], g["nj"], g["nk"], g["min_box"], g["max_box"], g["dx"], g["dy"], g["dz"], g["grid"])
-                p.set_col_th(name, g["col_th"])
-            for fi in range(p.num_forces()):
-                p.set_force_params(fi, sc["kn"], sc["kt"], sc["mu"], sc["damping"], 1.0)
-            _W["probe"] = p
+            from oracle import ref_scene
+            _W["probe"] = ref_scene.make_probe(sc["bodies"], sc["kn"], sc["kt"], sc["mu"], sc["damping"],
+                                               joint_type=sc.get("joint_type", "translational"),
+                                               inject_frames=sc.get("inject_frames", False))
             _W["kind"] = "reference"
             return
         except Exception as exc:  # pragma: no cover - only when oracle/_ref is absent
@@ -88,6 +74,34 @@ def _ref_worker_init(scene_blob, use_ref):
     from oracle import sdfc_oracle as O
     _W["O"] = O
     _W["ogrids"] = [O.Grid.from_dict(g) for g in sc["grids"]]
+
+
+def _ref_rollout_envs(env_ids):
+    """Simulation::forward(frame_skip) of the given rollouts on this core; -> (seconds, env-steps, kind, finals)."""
+    sc = _W["scene"]
+    n = sc["frame_skip"]
+    t_total, finals = 0.0, []
+    if _W["kind"] == "reference":
+        from oracle import ref_scene
+        for e in env_ids:
+            t, q, qd = ref_scene.rollout(_W["probe"], sc["q0"][e], sc["qdot0"][e], sc["f_ext"][e, 0], n)
+            t_total += t
+            finals.append((e, q, qd))
+    else:
+        from oracle import sim_oracle as S
+        jt = {"fixed": S.FIXED, "translational": S.TRANSLATIONAL, "free3d-exp": S.FREE3D_EXP}
+        for e in env_ids:
+            bodies = [S.BodyDesc(jt[b.joint_type], np.eye(4), b.rest_E, b.inertia, b.mass) for b in sc["bodies"]]
+            pairs = [S.PairDesc(a, b, _W["ogrids"][b], sc["points"][a], sc["kn"], sc["kt"], sc["mu"], sc["damping"])
+                     for a, b in sc["pairs"]]
+            sim = S.Sim(bodies, pairs, sc["h"], sc["gravity"])
+            sim.q, sim.qdot, sim.f_ext = sc["q0"][e].copy(), sc["qdot0"][e].copy(), sc["f_ext"][e].copy()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                sim.step()
+            t_total += time.perf_counter() - t0
+            finals.append((e, sim.q, sim.qdot))
+    return t_total, len(env_ids) * n, _W["kind"], finals
 
 
 def _ref_eval_envs(args):
@@ -124,14 +138,25 @@ def scene_blob(scene):
     def gd(g):
         return {"ni": g.ni, "nj": g.nj, "nk": g.nk, "min_box": g.min_box, "max_box": g.max_box, "dx": g.dx, "dy": g.dy,
                 "dz": g.dz, "col_th": g.col_th, "grid": g.grid}
-    return {"points": [b.points for b in scene.bodies], "grids": [gd(b.grid) for b in scene.bodies],
-            "pairs": list(scene.pairs), "kn": scene.kn, "kt": scene.kt, "mu": scene.mu, "damping": scene.damping,
-            "E": scene.E, "phi": scene.phi, "col_th": scene.bodies[0].grid.col_th}
+    blob = {"points": [b.points for b in scene.bodies], "grids": [gd(b.grid) for b in scene.bodies],
+            "bodies": scene.bodies, "pairs": list(scene.pairs), "kn": scene.kn, "kt": scene.kt, "mu": scene.mu,
+            "damping": scene.damping, "col_th": scene.bodies[0].grid.col_th}
+    if hasattr(scene, "q0"):   # RolloutScene (stepper)
+        blob.update({"q0": scene.q0, "qdot0": scene.qdot0, "f_ext": scene.f_ext, "h": scene.h, "gravity": scene.gravity,
+                     "frame_skip": scene.frame_skip, "joint_type": scene.bodies[0].joint_type, "inject_frames": True})
+    else:
+        blob.update({"E": scene.E, "phi": scene.phi})
+    return blob
 
 
 def have_ref():
-    import glob
-    return bool(glob.glob(os.path.join(ROOT, "oracle", "_ref", "ref_probe*.so")))
+    from oracle import ref_scene
+    return ref_scene.available()
+
+
+def rollout_workload(n_envs, seed_offset=0):
+    from assemble_them_all_b200 import scenes, synth
+    return scenes.c2_planner_rollouts(n_envs=n_envs, n_vertices=10000, seed=synth.MESH_SEED + seed_offset)
 
 
 def run_reference_arm(args):
@@ -158,6 +183,16 @@ def run_reference_arm(args):
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample * q_per_env / (ms * 1e-3)
+    # env-steps/s of the reference's own Simulation::forward on the planner rollouts: one rollout
+    # (frame_skip BDF1 steps) per core, measured once
+    rs = rollout_workload(max(cores, 16))
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(scene_blob(rs), have_ref())) as pool:
+        rres = pool.map(_ref_rollout_envs, [[e] for e in range(cores)])
+        dt_roll = max(r[0] for r in rres)  # all cores run concurrently: time of the slowest rollout (setup excluded)
+    env_steps = {"value": sum(r[1] for r in rres) / dt_roll, "unit": "env-steps/s", "cores": cores, "kind": rres[0][2],
+                 "sample": f"{cores} rollouts x {rs.frame_skip} BDF1 steps, one process per core concurrently, "
+                           f"slowest rollout {dt_roll:.2f} s in Simulation::forward",
+                 "workload": rs.label}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -167,6 +202,7 @@ def run_reference_arm(args):
                          "sample": f"{sample} of {scene.n_envs} environments per step, one process per core (fork), "
                                    f"Robot-level loop over both contact forces with derivatives"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "env_steps": env_steps,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -262,6 +298,85 @@ def cpu_baseline_leg(scene, gpu_out, budget_s=20.0):
             "sample": f"{n_done} of {scene.n_envs} environments, one evaluation with derivatives each, single core "
                       f"({t_total:.1f} s CPU); GPU fm/Km/Dm checked on 16 of them: max rel err {worst:.1e}",
             "env_evals_per_sec": n_done / t_total}
+
+
+def env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream):
+    """env-steps/s of the batched stepper on the planner rollouts (sdfc_sim_forward = Simulation::forward(frame_skip)
+    for every rollout). `value`: state resident in HBM, nothing returned per step. `e2e`: reset + external force
+    from host buffers, forward(frame_skip) and the per-substep q / qdot trajectory (what run_joint_plan.py:553
+    reads) copied back to the host, all inside the timed region."""
+    rs = rollout_workload(args.envs, seed_offset=rank)
+    sim, batch, pairs, sdfs, pts = rs.upload(ctx)
+    n = rs.frame_skip
+
+    def prepare():
+        sim.reset(rs.q0, rs.qdot0)
+        for b in range(len(rs.bodies)):
+            sim.set_body_external_force(b, rs.f_ext[:, b])
+
+    prepare()
+    sim.forward(n)   # warm-up
+    reps = max(2, min(args.steps, 5))
+    dev_ms, e2e_s = [], []
+    st0 = sim.stats()
+    l0 = ctx.launch_count
+    for _ in range(reps):
+        prepare()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        sim.forward(n)
+        b.record(stream)
+        torch.cuda.synchronize()
+        dev_ms.append(a.elapsed_time(b))
+    st1 = sim.stats()
+    launches = ctx.launch_count - l0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        prepare()
+        Q, QD = sim.forward(n, trajectory=True)
+        e2e_s.append(time.perf_counter() - t0)
+    t = torch.tensor([float(np.mean(dev_ms)) * 1e-3, float(np.mean(e2e_s))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(t[0].item()), float(t[1].item())
+    steps_total = world * rs.n_envs * n
+    d = {k: (st1[k] - st0[k]) / reps for k in st0}
+    evals = (d["deriv_env_evals"] + d["value_env_evals"]) / (rs.n_envs * n)
+    out = {
+        "value": steps_total / t_dev, "unit": "env-steps/s", "workload": rs.label, "rollouts_per_gpu": rs.n_envs,
+        "steps_per_rollout": n, "ms_per_forward": 1e3 * t_dev,
+        "e2e": {"value": steps_total / t_e2e, "unit": "env-steps/s", "ms_per_forward": 1e3 * t_e2e,
+                "h2d_bytes_per_forward": int(rs.q0.nbytes * 2 + rs.f_ext.nbytes * len(rs.bodies)),
+                "d2h_bytes_per_forward": int(Q.nbytes + QD.nbytes)},
+        "rounds_per_forward": d["rounds"], "contact_evals_per_env_step": evals,
+        "queries_per_sec_while_stepping": world * (d["deriv_env_evals"] + d["value_env_evals"]) *
+        (rs.queries_per_eval // rs.n_envs) / t_dev,
+        "gpu_launches_per_forward": launches / reps,
+        "converged_fraction": float(sim.is_converged().mean()),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # reference Simulation::forward on one core over a bounded sample of the same rollouts + parity of final states
+        _ref_worker_init(scene_blob(rs), have_ref())
+        t_cpu, n_cpu, worst_q, done = 0.0, 0, 0.0, 0
+        t_start = time.perf_counter()
+        for e in range(0, rs.n_envs, max(1, rs.n_envs // 61)):
+            tt, ns, kind, finals = _ref_rollout_envs([e])
+            t_cpu += tt
+            n_cpu += ns
+            done += 1
+            _, q_ref, _ = finals[0]
+            scale = float(np.max(np.abs(q_ref)))
+            worst_q = max(worst_q, float(np.max(np.abs(q_ref - Q[-1, e])) / scale) if scale > 0 else 0.0)
+            if time.perf_counter() - t_start > 15.0:
+                break
+        if worst_q > 1e-9:
+            raise SystemExit(f"PARITY FAILURE: stepper final q vs CPU {_W['kind']} relative error {worst_q:.3e} > 1e-9")
+        out["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "env-steps/s", "cores": 1, "kind": _W["kind"],
+                               "sample": f"{done} of {rs.n_envs} rollouts x {n} steps on one core ({t_cpu:.1f} s CPU); "
+                                         f"GPU final q after {n} steps checked on all of them: max rel err {worst_q:.1e}"}
+    sim.close()
+    return out
 
 
 def run_ours(args):
@@ -374,6 +489,8 @@ def run_ours(args):
         n_active = torch.stack(gathered).sum(dim=0)
     contacts_per_step = int(n_active.sum().item())
 
+    env_steps = env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream)
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         det_ms = kt["detect"][0] / max(1, kt["detect"][1])
@@ -387,7 +504,10 @@ def run_ours(args):
             "config": {"workload": scene.label, "envs_per_gpu": scene.n_envs, "pairs": batch.n_pairs,
                        "queries_per_step_per_gpu": q_rank, "active_contacts_per_step": contacts_per_step,
                        "derivatives": True, "sdf_storage": "fp32-lossless" if all(s.is_fp32 for s in sdfs) else "fp64",
-                       "l2": "flushed between timed iterations (256 MiB write)", "parity_mode": "-fmad=false"},
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "parity_mode": "bit-critical arithmetic in non-contracted IEEE intrinsics",
+                       "roofline_note": "C2 shares 2 point sets + 2 grids (~65 MB) across all rollouts, so the kernel "
+                                        "is L1/L2-served: frac > 1 against the HBM peak is cache reuse"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(np.mean(e2e_times))},
@@ -399,6 +519,7 @@ def run_ours(args):
             "kernels_ms": {"k_detect_mask": det_ms, "k_force": frc_ms, "k_reduce_splits+k_scatter_system": red_ms,
                            "step": ms_step},
             "env_evals_per_sec": world * scene.n_envs / (ms_max * 1e-3),
+            "env_steps": env_steps,
         }
         if world == 1 and not args.no_cpu_baseline:
             fm_h, Km_h, Dm_h, _ = out

@@ -188,6 +188,33 @@ struct Probe {
         b->_min_box = mn; b->_max_box = mx; b->_dx = dx; b->_dy = dy; b->_dz = dz;
     }
     void set_col_th(const std::string& name, double col_th) { sdf_body(name)->_col_th = col_th; }
+    // Overwrite the mass properties / body frame the reference derived from the mesh
+    // (BodyMeshObj.cpp:70-177 -> Body.cpp:63-66,88-91) so that both arms integrate
+    // exactly the same rigid bodies.
+    void set_body_frame(const std::string& name, const Matrix4& E_ji, const Vector6& inertia, double mass) {
+        Body* b = body(name);
+        b->_E_ji = E_ji;
+        b->_E_ij = math::Einv(E_ji);
+        b->_A_ji = math::Ad(b->_E_ji);
+        b->_A_ij = math::Ad(b->_E_ij);
+        b->_Inertia = inertia;
+        b->_mass = mass;
+    }
+    py::dict joint_info(const std::string& body_name) {
+        Joint* j = body(body_name)->_joint;
+        py::dict d;
+        d["ndof"] = j->_ndof;
+        d["E_pj_0"] = Matrix4(j->_E_pj_0);
+        d["index"] = j->_ndof > 0 ? j->_index[0] : -1;
+        return d;
+    }
+    // Wall time of Simulation::forward(n) (the stepping loop the planners drive).
+    double time_forward(int n) {
+        auto t0 = std::chrono::steady_clock::now();
+        sim->forward(n, false, false);
+        auto t1 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double>(t1 - t0).count();
+    }
     void set_force_params(int i, double kn, double kt, double mu, double damping, double scale) {
         auto* f = sdf_force(i);
         f->_kn = kn; f->_kt = kt; f->_mu = mu; f->_damping = damping; f->_scale = scale;
@@ -434,6 +461,9 @@ PYBIND11_MODULE(ref_probe, m) {
         .def("set_contact_points", &Probe::set_contact_points)
         .def("set_sdf_grid", &Probe::set_sdf_grid)
         .def("set_col_th", &Probe::set_col_th)
+        .def("set_body_frame", &Probe::set_body_frame)
+        .def("joint_info", &Probe::joint_info)
+        .def("time_forward", &Probe::time_forward, py::call_guard<py::gil_scoped_release>())
         .def("set_force_params", &Probe::set_force_params)
         .def("set_contact_scale", &Probe::set_contact_scale)
         .def("query_sdf", &Probe::query_sdf, py::arg("name"), py::arg("X"), py::arg("outside_accurate") = false)

@@ -26,6 +26,22 @@ def assert_close(ref, got, what, rtol=RTOL):
     assert e <= rtol, f"{what}: relative error {e:.3e} > {rtol:.1e}"
 
 
+Q_RTOL = 1e-9      # generalized coordinates (north_star)
+QDOT_RTOL = 1e-6   # see assert_state_close
+
+
+def assert_state_close(q_ref, qd_ref, q, qd, h, what):
+    """q within 1e-9 relative. qdot is the derived quantity (q1 - q0) / h (Simulation.cpp:1259):
+    a 1e-9 relative perturbation of q moves it by 1e-9 |q| / h, and the Newton tolerance
+    (|g| < 1e-8, Simulation.cpp:1008) is amplified by 1/h as well, so qdot is held to
+    1e-6 relative plus that absolute floor."""
+    assert rel_err(q_ref, q) <= Q_RTOL, f"{what}: q relative error {rel_err(q_ref, q):.3e}"
+    q_ref, qd_ref = np.asarray(q_ref), np.asarray(qd_ref)
+    tol = QDOT_RTOL * float(np.max(np.abs(qd_ref))) + Q_RTOL * float(np.max(np.abs(q_ref))) / h
+    err = float(np.max(np.abs(qd_ref - np.asarray(qd))))
+    assert err <= tol, f"{what}: qdot error {err:.3e} > {tol:.3e}"
+
+
 class GoldenContact:
     def __init__(self, z):
         self.z = z

@@ -1,14 +1,13 @@
 """GPU parity of the batched BDF1 stepper (sdfc_sim_*, through the C-ABI) against
 the reference's own trajectories (tests/golden/traj_small.npz) and the CPU oracle.
-Bars as in tests/test_sim_oracle.py: q 1e-9 relative, qdot 1e-6 relative,
-convergence flags / contact history exact."""
+Bars (tests/helpers.assert_state_close): q 1e-9 relative; qdot 1e-6 relative plus
+the 1e-9 |q| / h floor of a derived quantity; convergence flags / contact history exact."""
 import numpy as np
 import pytest
 
-from tests.helpers import load_traj_golden, oracle_sim, rel_err, traj_bodies
+from tests.helpers import assert_state_close, load_traj_golden, oracle_sim, rel_err, traj_bodies
 
 pytestmark = pytest.mark.gpu
-Q_RTOL, QDOT_RTOL = 1e-9, 1e-6
 
 
 def build(ctx, G, T, joint_type, n_envs, kn=1e6, kt=1e3, mu=0.0, damping=0.0):
@@ -36,8 +35,7 @@ def test_trajectory_matches_reference_golden(cuda_ctx, golden_contact, joint_typ
     Qr, QDr, CV = T[f"{key}_q"], T[f"{key}_qdot"], T[f"{key}_converged"]
     for s in range(steps):
         for e in range(3):
-            assert rel_err(Qr[s + 1], Q[s, e]) <= Q_RTOL, f"step {s} env {e}: q"
-            assert rel_err(QDr[s + 1], QD[s, e]) <= QDOT_RTOL, f"step {s} env {e}: qdot"
+            assert_state_close(Qr[s + 1], QDr[s + 1], Q[s, e], QD[s, e], sim.h, f"step {s} env {e}")
     # identical environments are bit-identical (fixed-order reductions)
     assert np.array_equal(Q[:, 0], Q[:, 1]) and np.array_equal(QD[:, 0], QD[:, 2])
     q, qd = sim.get_state()
@@ -97,8 +95,7 @@ def test_heterogeneous_envs_match_oracle(cuda_ctx, golden_contact, joint_type, m
         ref.f_ext[0] = force[e]
         for s in range(steps):
             ref.step()
-            assert rel_err(ref.q, Q[s, e]) <= Q_RTOL, f"env {e} step {s}: q"
-            assert rel_err(ref.qdot, QD[s, e]) <= QDOT_RTOL, f"env {e} step {s}: qdot"
+            assert_state_close(ref.q, ref.qdot, Q[s, e], QD[s, e], sim.h, f"env {e} step {s}")
         assert bool(conv[e]) == ref.converged
         assert np.array_equal(hist[e], ref.touched)
     sim.close()
@@ -121,7 +118,7 @@ def test_large_rotation_reparam(cuda_ctx, golden_contact):
     for s in range(5):
         ref.step()
         wrapped |= np.linalg.norm(ref.q[3:]) < 4.0
-        assert rel_err(ref.q, Q[s, 0]) <= Q_RTOL and rel_err(ref.qdot, QD[s, 0]) <= QDOT_RTOL
+        assert_state_close(ref.q, ref.qdot, Q[s, 0], QD[s, 0], sim.h, f"step {s}")
     assert wrapped
     sim.close()
 
@@ -140,3 +137,30 @@ def test_rejects_unsupported_models(cuda_ctx, golden_contact):
         batch = contact.ContactBatch(cuda_ctx, 1, 2, [pair], [0], [1])
         sim = contact.BatchedSimulation(batch, bodies, [0, 0, 0], 1e-3)
     assert sim is None
+
+
+@pytest.mark.parametrize("joint_type,n_envs", [("translational", 12), ("free3d-exp", 12)])
+def test_rollouts_match_reference_forward(cuda_ctx, joint_type, n_envs):
+    """The planner rollouts bench.py times (small mesh): batched stepper against the
+    UNMODIFIED reference's Simulation::forward with the same injected inputs."""
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    from assemble_them_all_b200 import scenes
+    sc = scenes.c2_planner_rollouts(n_envs=n_envs, n_vertices=600, sdf_dx=0.1, joint_type=joint_type)
+    sim, batch, pairs, sdfs, pts = sc.upload(cuda_ctx)
+    sim.reset(sc.q0, sc.qdot0)
+    for b in range(len(sc.bodies)):
+        sim.set_body_external_force(b, sc.f_ext[:, b])
+    steps = 100
+    Q, QD = sim.forward(steps, trajectory=True)
+    conv = sim.is_converged()
+    hist = sim.get_contact_history()
+    p = ref_scene.make_probe(sc.bodies, sc.kn, sc.kt, sc.mu, sc.damping, joint_type=joint_type, inject_frames=True)
+    for e in range(n_envs):
+        _, q, qd, Qr, QDr = ref_scene.rollout(p, sc.q0[e], sc.qdot0[e], sc.f_ext[e, 0], steps, trajectory=True)
+        for s in range(steps):
+            assert_state_close(Qr[s], QDr[s], Q[s, e], QD[s, e], sim.h, f"env {e} step {s}")
+        assert bool(conv[e]) == p.is_converged()
+        assert bool(hist[e].any()) == (len(p.get_contact_bodies("part0")) > 0)
+    sim.close()

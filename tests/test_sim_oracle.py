@@ -2,15 +2,15 @@
 against per-step q / qdot of the UNMODIFIED reference (tests/golden/traj_small.npz,
 produced by oracle/make_golden.py through oracle/_ref/ref_probe).
 
-Bars: q within 1e-9 relative (north_star); qdot = (q1 - q0) / h amplifies the
-Newton tolerance (|g| < 1e-8, Simulation.cpp:1008) by 1/h = 1000, so it is held
-to 1e-6 relative; Newton convergence flags and the contact history bit-exact."""
+Bars (tests/helpers.assert_state_close): q within 1e-9 relative (north_star); qdot =
+(q1 - q0) / h amplifies the Newton tolerance (|g| < 1e-8, Simulation.cpp:1008) and
+any perturbation of q by 1/h = 1000, so it is held to 1e-6 relative plus a
+1e-9 |q| / h floor; Newton convergence flags and the contact history bit-exact."""
 import numpy as np
 import pytest
 
-from tests.helpers import load_traj_golden, oracle_sim, rel_err
+from tests.helpers import assert_state_close, load_traj_golden, oracle_sim, rel_err
 
-Q_RTOL, QDOT_RTOL = 1e-9, 1e-6
 
 
 @pytest.mark.parametrize("joint_type", ["translational", "free3d-exp"])
@@ -23,8 +23,7 @@ def test_trajectory_matches_reference(golden_contact, joint_type):
     assert np.array_equal(sim.q, Q[0]) and np.array_equal(sim.qdot, QD[0])
     for s in range(int(T["steps"])):
         sim.step()
-        assert rel_err(Q[s + 1], sim.q) <= Q_RTOL, f"step {s}: q"
-        assert rel_err(QD[s + 1], sim.qdot) <= QDOT_RTOL, f"step {s}: qdot"
+        assert_state_close(Q[s + 1], QD[s + 1], sim.q, sim.qdot, sim.h, f"step {s}")
         assert sim.converged == bool(CV[s]), f"step {s}: Newton convergence flag"
     # contact history: part0 touched part1 (CollisionDetection.cpp:143-146)
     assert sim.touched.any() and [str(x) for x in T[f"{key}_touched"]] == ["part1"]
