@@ -1,0 +1,159 @@
+// See ForceGeneralSDFContactB200.h. Host glue only: all arithmetic of the contact
+// path runs in libsdfcontact_b200.so (CUDA, sm_100a). No CPU fallback: if the
+// library cannot create a device context the constructor's first use throws in
+// the reference's convention (throw_error -> std::string, Common.h:58-61).
+#include "ForceGeneralSDFContactB200.h"
+
+#include "Body/Body.h"
+#include "Body/BodySDFObj.h"
+#include "Robot.h"
+#include "Simulation.h"
+
+#include "sdfcontact_b200.h"
+
+#include <cstdlib>
+#include <map>
+
+namespace redmax {
+
+namespace {
+
+void check(sdfc_status st, const char* what) {
+    if (st != SDFC_OK) throw_error(std::string(what) + ": " + sdfc_last_error());
+}
+
+// one device context per process (device from SDFC_DEVICE, default 0); geometry is
+// shared between the forces that use the same body
+struct DeviceCache {
+    sdfc_context* ctx = nullptr;
+    std::map<const BodySDFObj*, sdfc_sdf*> sdf;
+    std::map<const Body*, sdfc_points*> pts;
+};
+DeviceCache& cache() {
+    static DeviceCache c;
+    if (c.ctx == nullptr) {
+        const char* dev = std::getenv("SDFC_DEVICE");
+        check(sdfc_context_create(dev ? std::atoi(dev) : 0, &c.ctx), "ForceGeneralSDFContactB200: no CUDA device");
+    }
+    return c;
+}
+
+}  // namespace
+
+ForceGeneralSDFContactB200::ForceGeneralSDFContactB200(Simulation* sim, Body* contact_body, Body* SDF_body, dtype kn,
+                                                       dtype kt, dtype mu, dtype damping)
+    : ForceGeneralSDFContact(sim, contact_body, SDF_body, kn, kt, mu, damping) {}
+
+void ForceGeneralSDFContactB200::init() { ensure_uploaded(); }
+
+void ForceGeneralSDFContactB200::ensure_uploaded() {
+    if (_pair != nullptr) return;
+    DeviceCache& c = cache();
+    _ctx = c.ctx;
+    auto is = c.sdf.find(_SDF_body);
+    if (is == c.sdf.end()) {
+        // fields of BodySDFObj (Body/BodySDFObj.h:13-16); grid a[i + ni*(j + nj*k)]
+        const auto& G = _SDF_body->_SDF;
+        sdfc_sdf* s = nullptr;
+        check(sdfc_sdf_create(_ctx, G.ni, G.nj, G.nk, _SDF_body->_min_box.data(), _SDF_body->_max_box.data(),
+                              _SDF_body->_dx, _SDF_body->_dy, _SDF_body->_dz, _SDF_body->_col_th, G.a.data(), &s),
+              "ForceGeneralSDFContactB200: SDF upload");
+        is = c.sdf.emplace(_SDF_body, s).first;
+    }
+    _sdf = is->second;
+    auto ip = c.pts.find(_contact_body);
+    if (ip == c.pts.end()) {
+        std::vector<Vector3> cp = _contact_body->get_contact_points();  // Body.h:129
+        std::vector<double> xyz(3 * cp.size());
+        for (size_t i = 0; i < cp.size(); ++i) { xyz[3 * i] = cp[i](0); xyz[3 * i + 1] = cp[i](1); xyz[3 * i + 2] = cp[i](2); }
+        sdfc_points* p = nullptr;
+        check(sdfc_points_create(_ctx, (int)cp.size(), xyz.data(), /*morton_sort=*/1, &p),
+              "ForceGeneralSDFContactB200: contact point upload");
+        ip = c.pts.emplace(_contact_body, p).first;
+    }
+    _pts = ip->second;
+    check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
+    _synced = false;
+}
+
+void ForceGeneralSDFContactB200::sync_parameters() {
+    const dtype cs = _contact_body->_contact_scale, cth = _SDF_body->_col_th;
+    if (_synced && _sync_kn == _kn && _sync_kt == _kt && _sync_mu == _mu && _sync_damping == _damping &&
+        _sync_scale == _scale && _sync_contact_scale == cs && _sync_col_th == cth)
+        return;
+    check(sdfc_pair_set_stiffness(_pair, _kn, _kt), "set_stiffness");
+    check(sdfc_pair_set_friction(_pair, _mu), "set_friction");
+    check(sdfc_pair_set_damping(_pair, _damping), "set_damping");
+    check(sdfc_pair_set_scale(_pair, _scale), "set_scale");
+    check(sdfc_pair_set_contact_scale(_pair, cs), "set_contact_scale");
+    if (!_synced || _sync_col_th != cth) check(sdfc_sdf_set_col_th(_sdf, cth), "set_col_th");
+    _sync_kn = _kn; _sync_kt = _kt; _sync_mu = _mu; _sync_damping = _damping; _sync_scale = _scale;
+    _sync_contact_scale = cs; _sync_col_th = cth;
+    _synced = true;
+}
+
+void ForceGeneralSDFContactB200::record_history(int n_active) {
+    if (n_active > 0) {  // CollisionDetection.cpp:143-146
+        _contact_body->add_contact_body(_SDF_body->_name);
+        _SDF_body->add_contact_body(_contact_body->_name);
+    }
+}
+
+void ForceGeneralSDFContactB200::computeForce(VectorX& fm, VectorX& fr, bool verbose) {
+    auto t0 = clock();
+    ensure_uploaded();
+    sync_parameters();
+    double fm_sub[12];
+    int32_t n_active = 0;
+    const Matrix4 E1 = _contact_body->_E_0i, E2 = _SDF_body->_E_0i;  // column-major, as the C-ABI expects
+    const Vector6 phi1 = _contact_body->_phi, phi2 = _SDF_body->_phi;
+    check(sdfc_pair_force(_pair, E1.data(), phi1.data(), E2.data(), phi2.data(), fm_sub, &n_active),
+          "ForceGeneralSDFContactB200::computeForce");
+    record_history(n_active);
+    sdfc_scatter_force(_contact_body->_index[0], _SDF_body->_index[0], fm_sub, fm.data());  // .cpp:60-61
+    ++_n_evaluations;
+    _time.add("collision detection", 0);
+    _time.add("compute force", clock() - t0);
+}
+
+void ForceGeneralSDFContactB200::computeForceWithDerivative(VectorX& fm, VectorX& fr, MatrixX& Km, MatrixX& Dm,
+                                                            MatrixX& Kr, MatrixX& Dr, bool verbose) {
+    auto t0 = clock();
+    ensure_uploaded();
+    sync_parameters();
+    double fm_sub[12], Km_sub[144], Dm_sub[144];
+    int32_t n_active = 0;
+    const Matrix4 E1 = _contact_body->_E_0i, E2 = _SDF_body->_E_0i;
+    const Vector6 phi1 = _contact_body->_phi, phi2 = _SDF_body->_phi;
+    check(sdfc_pair_force_deriv(_pair, E1.data(), phi1.data(), E2.data(), phi2.data(), fm_sub, Km_sub, Dm_sub, &n_active),
+          "ForceGeneralSDFContactB200::computeForceWithDerivative");
+    record_history(n_active);
+    const int ia = _contact_body->_index[0], ib = _SDF_body->_index[0];
+    sdfc_scatter_force(ia, ib, fm_sub, fm.data());                                      // .cpp:88-89
+    sdfc_scatter_deriv((int)Km.rows(), ia, ib, Km_sub, Dm_sub, Km.data(), Dm.data());   // .cpp:91-99 (column-major)
+    ++_n_evaluations;
+    _time.add("collision detection", 0);
+    _time.add("compute force", clock() - t0);
+}
+
+void ForceGeneralSDFContactB200::computeForceWithDerivative(VectorX&, VectorX&, MatrixX&, MatrixX&, MatrixX&, MatrixX&,
+                                                            MatrixX&, MatrixX&, bool) {
+    throw_error("ForceGeneralSDFContactB200: design-parameter derivatives are not implemented on the B200 path");
+}
+
+int ForceGeneralSDFContactB200::replace_all(Simulation* sim) {
+    int n = 0;
+    for (auto& f : sim->_robot->_forces) {
+        auto* ref = dynamic_cast<ForceGeneralSDFContact*>(f);
+        if (ref == nullptr || dynamic_cast<ForceGeneralSDFContactB200*>(f) != nullptr) continue;
+        auto* mine = new ForceGeneralSDFContactB200(sim, ref->_contact_body, ref->_SDF_body, ref->_kn, ref->_kt, ref->_mu,
+                                                    ref->_damping);
+        mine->_scale = ref->_scale;
+        mine->init();
+        f = mine;  // forces are leaked by the reference as well (Robot.h:20)
+        ++n;
+    }
+    return n;
+}
+
+}  // namespace redmax
