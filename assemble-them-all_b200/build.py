@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("SDFC_OUT") or os.path.join(HERE, "libsdfcontact_b200.so")
 SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu"]
 FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7
-HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_step.cuh", FORCE_INST,
+HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_host.h", FORCE_INST,
            os.path.join("..", "..", "include", "sdfcontact_b200.h")]
 
 NVCC_FLAGS = [
@@ -57,6 +57,9 @@ def build(force=False, verbose=False):
     jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), []) for s in srcs]
     min_blocks = os.environ.get("SDFC_FORCE_MIN_BLOCKS")  # tuning knob: __launch_bounds__(128, n) of k_force
     extra_all = [f"-DSDFC_FORCE_MIN_BLOCKS={int(min_blocks)}"] if min_blocks else []
+    nf_blocks = os.environ.get("SDFC_FORCE_NF_MIN_BLOCKS")  # same knob for the planner fast path (k_force<1,0,0>)
+    if nf_blocks:
+        extra_all.append(f"-DSDFC_FORCE_NF_MIN_BLOCKS={int(nf_blocks)}")
     jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"),
               [f"-DSDFC_FORCE_VARIANT={v}", *extra_all]) for v in range(8)]
     for s, o, extra in jobs:

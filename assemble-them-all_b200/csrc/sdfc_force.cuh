@@ -102,6 +102,26 @@ struct WarpSink {
     }
 };
 
+// Sink of contact_eval_nf: one 12-value column at a time.
+struct ColSink {
+    double acc[kNfCols];
+    unsigned lane;
+    bool valid;
+    __device__ __forceinline__ void init(unsigned l) {
+        lane = l;
+        valid = false;
+#pragma unroll
+        for (int j = 0; j < kNfCols; ++j) acc[j] = 0.0;
+    }
+    __device__ __forceinline__ void emit(int j, const double* c12) {
+        double v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = valid ? c12[i] : 0.0;
+        TransposeReduce<12, 16>::run(v, lane);
+        acc[j] += v[0];
+    }
+};
+
 // Pose of (env, body) from column-major E[env][body][16] into row-major R, p.
 __device__ __forceinline__ void stage_pose(const double* E, int n_bodies, int env, int body, double* R, double* p,
                                            int t) {
@@ -117,6 +137,7 @@ __device__ __forceinline__ void stage_pose(const double* E, int n_bodies, int en
 struct ForceShared {
     PairDev pd;
     PairPose pose;
+    PairPoseNF nf;
     int warp_tot[kNumWarps];
     int ids[kForceThreads * 32];
 };
@@ -133,14 +154,31 @@ __device__ __forceinline__ void force_rounds(const ForceShared& S, int total, Si
     }
 }
 
+template <bool F32>
+__device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total, ColSink& sink) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = warp * 32; base < total; base += kForceThreads) {
+        const int c = base + lane;
+        sink.valid = c < total;
+        const int id = S.ids[sink.valid ? c : base];
+        const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
+        contact_eval_nf<F32>(S.pd.grid, S.nf, S.pd.prm.kn, xi1, sink);
+    }
+}
+
 #ifndef SDFC_FORCE_MIN_BLOCKS
 #define SDFC_FORCE_MIN_BLOCKS 2
 #endif
+#ifndef SDFC_FORCE_NF_MIN_BLOCKS
+#define SDFC_FORCE_NF_MIN_BLOCKS 3  // planner fast path: 168 registers, 12 warps / SM
+#endif
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
-__global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(BatchDev B, const double* __restrict__ E,
+__global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP) ? SDFC_FORCE_NF_MIN_BLOCKS
+                                                                                : SDFC_FORCE_MIN_BLOCKS) k_force(BatchDev B, const double* __restrict__ E,
                                                          const double* __restrict__ phi) {
     constexpr bool DM = ANYFRIC || ANYDAMP;
-    constexpr int NPART = DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    constexpr bool NF = DERIV && !DM;  // planner fast path (contact_eval_nf)
+    constexpr int NPART = NF ? kPartialNF : (DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ForceShared& S = *reinterpret_cast<ForceShared*>(smem_raw);
     double* red = reinterpret_cast<double*>(smem_raw + sizeof(ForceShared));  // [kNumWarps][NPART]
@@ -161,8 +199,20 @@ __global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(
     else if (tid >= 64 && tid < 70) S.pose.phi1[tid - 64] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + tid - 64);
     else if (tid >= 96 && tid < 102) S.pose.phi2[tid - 96] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + tid - 96);
 
-    WarpSink<DERIV, DM> sink;
-    sink.init(lane);
+    if constexpr (NF) {
+        __syncthreads();
+        if (tid < 9) {
+            const int r = tid / 3, c = tid % 3;  // R21 = R2^T R1
+            S.nf.R21[tid] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
+        } else if (tid >= 32 && tid < 41) {
+            S.nf.R1[tid - 32] = S.pose.R1[tid - 32]; S.nf.R2[tid - 32] = S.pose.R2[tid - 32];
+        } else if (tid >= 64 && tid < 67) {
+            S.nf.p1[tid - 64] = S.pose.p1[tid - 64]; S.nf.p2[tid - 64] = S.pose.p2[tid - 64];
+        }
+    }
+    WarpSink<DERIV && !NF, DM> sink;
+    ColSink csink;
+    if constexpr (NF) csink.init(lane); else sink.init(lane);
 
     const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
     const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
@@ -197,6 +247,10 @@ __global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(
         }
         __syncthreads();
         if (total == 0) continue;
+        if constexpr (NF) {
+            if (f32) force_rounds_nf<true>(S, total, csink); else force_rounds_nf<false>(S, total, csink);
+            continue;
+        }
         // CTA-uniform variant dispatch (template flags prune what cannot occur)
         if (f32) {
             if (fric) { if (damp) force_rounds<true, DERIV, ANYFRIC, ANYDAMP>(S, total, sink); else force_rounds<true, DERIV, ANYFRIC, false>(S, total, sink); }
@@ -209,7 +263,10 @@ __global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(
 
     // cross-warp combine in fixed order
     double* mine = red + (size_t)warp * NPART;
-    if (DERIV) {
+    if constexpr (NF) {
+#pragma unroll
+        for (int j = 0; j < kNfCols; ++j) mine[j * 32 + lane] = csink.acc[j];
+    } else if (DERIV) {
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -238,7 +295,7 @@ __global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_MIN_BLOCKS) k_force(
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
 void launch_force_t(const BatchDev& B, const double* E, const double* phi, cudaStream_t stream) {
     constexpr bool DM = ANYFRIC || ANYDAMP;
-    constexpr int NPART = DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    constexpr int NPART = (DERIV && !DM) ? kPartialNF : (DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
     const size_t smem = sizeof(ForceShared) + sizeof(double) * kNumWarps * NPART;
     static bool configured = false;
     if (!configured) {

@@ -159,14 +159,21 @@ __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restric
     }
     const size_t ep = (size_t)env * B.n_pairs + pair;
     const bool empty = B.n_active[ep] == 0;
-    const int npart = deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue;
+    const bool nf = deriv && !dm;  // layout of contact_eval_nf: 12 Km columns + fm
+    const int npart = nf ? kPartialNF : (deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
     const double* part = B.partial + ep * B.splits * npart;
     for (int slot = threadIdx.x; slot < npart; slot += blockDim.x) {
         double s = 0.0;
         if (!empty)
             for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * npart + slot];
         const int lane = slot & 31;
-        if (!deriv) {
+        if (nf) {
+            const int j = slot >> 5, e = tr_index<12>(lane, 0);
+            if (e >= 0) {
+                if (j < 12) Km_sub[ep * 144 + e + 12 * j] = s;
+                else fm_sub[ep * 12 + e] = s;
+            }
+        } else if (!deriv) {
             const int e = tr_index<12>(lane, slot >> 5);
             if (e >= 0) fm_sub[ep * 12 + e] = s;
         } else if (slot < kPartialDeriv) {

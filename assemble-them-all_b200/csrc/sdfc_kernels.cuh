@@ -45,6 +45,10 @@ constexpr int kOutF = tr_out(12);  // 1
 constexpr int kPartialDeriv = 4 * kOutK * 32;         // 256 doubles
 constexpr int kPartialDerivDM = kPartialDeriv + 4 * kOutD * 32;  // 512 doubles
 constexpr int kPartialValue = kOutF * 32;             // 32 doubles
+// planner fast path (derivatives, no friction, no damping): 12 Km columns + fm,
+// each reduced as 12 values -> 1 per lane
+constexpr int kNfCols = 13;
+constexpr int kPartialNF = kNfCols * 32;               // 416 doubles
 
 struct BatchDev {
     const PairDev* pairs;  // [n_pairs]

@@ -489,7 +489,7 @@ def run_ours(args):
         n_active = torch.stack(gathered).sum(dim=0)
     contacts_per_step = int(n_active.sum().item())
 
-    env_steps = env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream)
+    env_steps = None if args.skip_env_steps else env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream)
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -540,6 +540,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
     ap.add_argument("--ref-envs-per-core", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-env-steps", action="store_true", help="tuning runs: contact pass only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
