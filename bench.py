@@ -353,8 +353,16 @@ def env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream):
         "queries_per_sec_while_stepping": world * (d["deriv_env_evals"] + d["value_env_evals"]) *
         (rs.queries_per_eval // rs.n_envs) / t_dev,
         "gpu_launches_per_forward": launches / reps,
-        "converged_fraction": float(sim.is_converged().mean()),
     }
+    # the planner's only exchange: one all_gather of per-rollout outcome records (NCCL), in rollout order
+    from assemble_them_all_b200 import sharding
+    n_total = world * rs.n_envs
+    lo, hi = sharding.shard_bounds(n_total, rank, world)
+    rec = sharding.make_records(np.arange(lo, hi), sim.is_converged().astype(np.float64), np.full(rs.n_envs, n),
+                                np.arange(rs.n_envs) % 6, sim.get_contact_history().any(axis=1).astype(np.float64), Q[-1])
+    table = sharding.gather_records(rec, n_total, dist if world > 1 else None, dev)
+    out["outcomes"] = {"rollouts": int(len(table)), "converged": int(table[:, 1].sum()), "touched": int(table[:, 4].sum()),
+                       "gather": "one all_gather of %d x %d fp64 records" % (n_total, sharding.RECORD_WIDTH)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # reference Simulation::forward on one core over a bounded sample of the same rollouts + parity of final states
         _ref_worker_init(scene_blob(rs), have_ref())
