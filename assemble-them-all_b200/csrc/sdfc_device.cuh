@@ -735,6 +735,161 @@ __device__ __forceinline__ int contact_eval(const GridDev& G, const PairPose& P,
 
 
 // ---------------------------------------------------------------------------
+// The 26 SDF samples BodySDFObj::collision takes around x (BodySDFObj.cpp:176-205,
+// 254-303): centre, 6 axis samples at +-1e-5, 12 diagonal samples at +-0.5e-5 ->
+// d = sdf(x) + col_th, FD gradient g, FD Hessian H, every value bit-identical to
+// the reference's query_SDF sequence.
+// Fast path: the stencil almost always lies inside one cell. Each axis has only 5
+// distinct coordinates (0, +e, -e, +h, -h), so 15 divisions / floors / fractions
+// replace 78, and the trilinear form factors stage by stage (x-lerps depend on the
+// x variant only, ...): 71 lerps instead of 182 — the same operations on the same
+// operands, so the same bits. Falls back to sample-by-sample evaluation when any
+// coordinate leaves the centre cell or the grid box.
+template <bool F32>
+__device__ __forceinline__ void sdf_stencil_generic(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
+    CellCache cc;
+    {
+        const double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
+        const double cj = exact_div(__dsub_rn(x[1], G.mn[1]), G.dy, G.rdy);
+        const double ck = exact_div(__dsub_rn(x[2], G.mn[2]), G.dz, G.rdz);
+        cc.i = (int)floor(ci); cc.j = (int)floor(cj); cc.k = (int)floor(ck);
+        load_cell<F32>(G, cc.i, cc.j, cc.k, cc.v);
+    }
+    const double s0 = query_sdf<F32>(G, x[0], x[1], x[2], true, &cc);
+    d = __dadd_rn(query_sdf<F32>(G, x[0], x[1], x[2], false, &cc), G.col_th);
+    double qp[3], qm[3];
+    qp[0] = query_sdf<F32>(G, __dadd_rn(x[0], kFdEps), x[1], x[2], true, &cc);
+    qm[0] = query_sdf<F32>(G, __dsub_rn(x[0], kFdEps), x[1], x[2], true, &cc);
+    qp[1] = query_sdf<F32>(G, x[0], __dadd_rn(x[1], kFdEps), x[2], true, &cc);
+    qm[1] = query_sdf<F32>(G, x[0], __dsub_rn(x[1], kFdEps), x[2], true, &cc);
+    qp[2] = query_sdf<F32>(G, x[0], x[1], __dadd_rn(x[2], kFdEps), true, &cc);
+    qm[2] = query_sdf<F32>(G, x[0], x[1], __dsub_rn(x[2], kFdEps), true, &cc);
+    constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g[a] = exact_div(__dsub_rn(qp[a], qm[a]), kTwoEps, kRTwoEps);
+    const double h = kFdEps / 2;
+    const double two_s0 = __dmul_rn(2.0, s0);
+    H[0] = __dsub_rn(__dadd_rn(qp[0], qm[0]), two_s0);
+    H[4] = __dsub_rn(__dadd_rn(qp[1], qm[1]), two_s0);
+    H[8] = __dsub_rn(__dadd_rn(qp[2], qm[2]), two_s0);
+    const double xp = __dadd_rn(x[0], h), xm = __dsub_rn(x[0], h);
+    const double yp = __dadd_rn(x[1], h), ym = __dsub_rn(x[1], h);
+    const double zp = __dadd_rn(x[2], h), zm = __dsub_rn(x[2], h);
+    const double xy = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, yp, x[2], true, &cc), query_sdf<F32>(G, xm, ym, x[2], true, &cc)),
+                                          query_sdf<F32>(G, xp, ym, x[2], true, &cc)), query_sdf<F32>(G, xm, yp, x[2], true, &cc));
+    const double xz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, x[1], zp, true, &cc), query_sdf<F32>(G, xm, x[1], zm, true, &cc)),
+                                          query_sdf<F32>(G, xp, x[1], zm, true, &cc)), query_sdf<F32>(G, xm, x[1], zp, true, &cc));
+    const double yz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, x[0], yp, zp, true, &cc), query_sdf<F32>(G, x[0], ym, zm, true, &cc)),
+                                          query_sdf<F32>(G, x[0], yp, zm, true, &cc)), query_sdf<F32>(G, x[0], ym, zp, true, &cc));
+    H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
+    constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = exact_div(H[i], kEps2, kREps2);
+}
+
+// Cell index and fractional coordinate of the 5 stencil variants of one axis:
+// 0: x, 1: x+e, 2: x-e, 3: x+h, 4: x-h (BodySDFObj.cpp:132-134 per variant). base = lowest
+// cell index among them, off[v] = cell(v) - base. Returns false if a variant is outside
+// [mn, mx] or the variants span more than two cells.
+__device__ __forceinline__ bool axis_variants(double xa, double mn, double mx, double dx, double rdx, int& base, int off[5],
+                                              double f[5], int& cross) {
+    constexpr double h = kFdEps / 2;
+    const double t[5] = {xa, __dadd_rn(xa, kFdEps), __dsub_rn(xa, kFdEps), __dadd_rn(xa, h), __dsub_rn(xa, h)};
+    bool ok = true;
+    int cell[5], lo = 0x7fffffff, hi = -0x7fffffff;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+        const double c = exact_div(__dsub_rn(t[v], mn), dx, rdx);
+        cell[v] = (int)floor(c);
+        ok = ok && (t[v] >= mn) && (t[v] <= mx);
+        f[v] = __dsub_rn(c, (double)cell[v]);
+        lo = min(lo, cell[v]); hi = max(hi, cell[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < 5; ++v) off[v] = cell[v] - lo;
+    base = lo;
+    cross = hi - lo;
+    return ok && cross <= 1;
+}
+
+// The 19 distinct stencil samples on ONE cell's corner values: the trilinear form is
+// evaluated stage by stage so that x-lerps are shared by all samples with the same x
+// variant and so on (71 lerps instead of 19 x 7); same operations on the same
+// operands as sample-by-sample evaluation, hence the same bits.
+// Order: 0 centre; 1,2 x+-e; 3,4 y+-e; 5,6 z+-e; 7-10 xy (++,--,+-,-+); 11-14 xz; 15-18 yz.
+__device__ __forceinline__ void stencil_on_cell(const double c[8], const double fi[5], const double fj[5], const double fk[5],
+                                                double s[19]) {
+    auto S = [&](int vi, int vj, int vk) {
+        const double v00 = lerp1(fi[vi], c[0], c[1]);
+        const double v10 = lerp1(fi[vi], c[2], c[3]);
+        const double v01 = lerp1(fi[vi], c[4], c[5]);
+        const double v11 = lerp1(fi[vi], c[6], c[7]);
+        const double w0 = lerp1(fj[vj], v00, v10);
+        const double w1 = lerp1(fj[vj], v01, v11);
+        return lerp1(fk[vk], w0, w1);
+    };
+    s[0] = S(0, 0, 0);
+    s[1] = S(1, 0, 0); s[2] = S(2, 0, 0); s[3] = S(0, 1, 0); s[4] = S(0, 2, 0); s[5] = S(0, 0, 1); s[6] = S(0, 0, 2);
+    s[7] = S(3, 3, 0); s[8] = S(4, 4, 0); s[9] = S(3, 4, 0); s[10] = S(4, 3, 0);
+    s[11] = S(3, 0, 3); s[12] = S(4, 0, 4); s[13] = S(3, 0, 4); s[14] = S(4, 0, 3);
+    s[15] = S(0, 3, 3); s[16] = S(0, 4, 4); s[17] = S(0, 3, 4); s[18] = S(0, 4, 3);
+}
+
+// Must be called by all 32 lanes of a warp (uses a warp vote).
+template <bool F32>
+__device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
+    double fi[5], fj[5], fk[5];
+    int oi[5], oj[5], ok_[5], bi, bj, bk, cx, cy, cz;
+    bool ok = axis_variants(x[0], G.mn[0], G.mx[0], G.dx, G.rdx, bi, oi, fi, cx);
+    ok = axis_variants(x[1], G.mn[1], G.mx[1], G.dy, G.rdy, bj, oj, fj, cy) && ok;
+    ok = axis_variants(x[2], G.mn[2], G.mx[2], G.dz, G.rdz, bk, ok_, fk, cz) && ok;
+    // fast path: the stencil touches the base cell and at most one neighbour along one axis
+    ok = ok && (cx + cy + cz <= 1);
+    double s[19];
+    if (ok) {
+        double c[8];
+        load_cell<F32>(G, bi, bj, bk, c);
+        stencil_on_cell(c, fi, fj, fk, s);
+    }
+    const bool crossing = ok && (cx + cy + cz == 1);
+    if (__any_sync(0xffffffffu, crossing)) {
+        if (crossing) {
+            double c[8], t[19];
+            load_cell<F32>(G, bi + cx, bj + cy, bk + cz, c);
+            stencil_on_cell(c, fi, fj, fk, t);
+            // sample (vi, vj, vk) lives in the neighbour cell iff its variant on the crossing axis does
+#define SDFC_PICK(n, vi, vj, vk) s[n] = (oi[vi] + oj[vj] + ok_[vk]) ? t[n] : s[n]
+            SDFC_PICK(0, 0, 0, 0);
+            SDFC_PICK(1, 1, 0, 0); SDFC_PICK(2, 2, 0, 0); SDFC_PICK(3, 0, 1, 0); SDFC_PICK(4, 0, 2, 0);
+            SDFC_PICK(5, 0, 0, 1); SDFC_PICK(6, 0, 0, 2);
+            SDFC_PICK(7, 3, 3, 0); SDFC_PICK(8, 4, 4, 0); SDFC_PICK(9, 3, 4, 0); SDFC_PICK(10, 4, 3, 0);
+            SDFC_PICK(11, 3, 0, 3); SDFC_PICK(12, 4, 0, 4); SDFC_PICK(13, 3, 0, 4); SDFC_PICK(14, 4, 0, 3);
+            SDFC_PICK(15, 0, 3, 3); SDFC_PICK(16, 0, 4, 4); SDFC_PICK(17, 0, 3, 4); SDFC_PICK(18, 0, 4, 3);
+#undef SDFC_PICK
+        }
+    }
+    if (!ok) { sdf_stencil_generic<F32>(G, x, d, g, H); return; }
+    const double s0 = s[0];
+    d = __dadd_rn(s0, G.col_th);
+    constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
+    g[0] = exact_div(__dsub_rn(s[1], s[2]), kTwoEps, kRTwoEps);
+    g[1] = exact_div(__dsub_rn(s[3], s[4]), kTwoEps, kRTwoEps);
+    g[2] = exact_div(__dsub_rn(s[5], s[6]), kTwoEps, kRTwoEps);
+    const double two_s0 = __dmul_rn(2.0, s0);
+    H[0] = __dsub_rn(__dadd_rn(s[1], s[2]), two_s0);
+    H[4] = __dsub_rn(__dadd_rn(s[3], s[4]), two_s0);
+    H[8] = __dsub_rn(__dadd_rn(s[5], s[6]), two_s0);
+    // v = q(++) + q(--) - q(+-) - q(-+), left to right (BodySDFObj.cpp:196-203)
+    const double xy = __dsub_rn(__dsub_rn(__dadd_rn(s[7], s[8]), s[9]), s[10]);
+    const double xz = __dsub_rn(__dsub_rn(__dadd_rn(s[11], s[12]), s[13]), s[14]);
+    const double yz = __dsub_rn(__dsub_rn(__dadd_rn(s[15], s[16]), s[17]), s[18]);
+    H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
+    constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = exact_div(H[i], kEps2, kREps2);
+}
+
+// ---------------------------------------------------------------------------
 // Planner fast path: mu <= eps and damping == 0 (run_joint_plan.py:153), with
 // derivatives. Same SDF samples as contact_eval (bit-faithful: the FD Hessian's
 // round-off enters Km at ~1e-7 relative, so it must be reproduced), but the
@@ -762,46 +917,8 @@ __device__ __forceinline__ void contact_eval_nf(const GridDev& G, const PairPose
     double xw1[3], x[3];
     to_world(P.R1, P.p1, xi1[0], xi1[1], xi1[2], xw1);
     to_local(P.R2, P.p2, xw1, x);
-    CellCache cc;
-    {
-        const double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
-        const double cj = exact_div(__dsub_rn(x[1], G.mn[1]), G.dy, G.rdy);
-        const double ck = exact_div(__dsub_rn(x[2], G.mn[2]), G.dz, G.rdz);
-        cc.i = (int)floor(ci); cc.j = (int)floor(cj); cc.k = (int)floor(ck);
-        load_cell<F32>(G, cc.i, cc.j, cc.k, cc.v);
-    }
-    const double s0 = query_sdf<F32>(G, x[0], x[1], x[2], true, &cc);
-    const double d = __dadd_rn(query_sdf<F32>(G, x[0], x[1], x[2], false, &cc), G.col_th);
-    double qp[3], qm[3], g[3], H[9];
-    qp[0] = query_sdf<F32>(G, __dadd_rn(x[0], kFdEps), x[1], x[2], true, &cc);
-    qm[0] = query_sdf<F32>(G, __dsub_rn(x[0], kFdEps), x[1], x[2], true, &cc);
-    qp[1] = query_sdf<F32>(G, x[0], __dadd_rn(x[1], kFdEps), x[2], true, &cc);
-    qm[1] = query_sdf<F32>(G, x[0], __dsub_rn(x[1], kFdEps), x[2], true, &cc);
-    qp[2] = query_sdf<F32>(G, x[0], x[1], __dadd_rn(x[2], kFdEps), true, &cc);
-    qm[2] = query_sdf<F32>(G, x[0], x[1], __dsub_rn(x[2], kFdEps), true, &cc);
-    {
-        constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) g[a] = exact_div(__dsub_rn(qp[a], qm[a]), kTwoEps, kRTwoEps);
-        const double h = kFdEps / 2;
-        const double two_s0 = __dmul_rn(2.0, s0);
-        H[0] = __dsub_rn(__dadd_rn(qp[0], qm[0]), two_s0);
-        H[4] = __dsub_rn(__dadd_rn(qp[1], qm[1]), two_s0);
-        H[8] = __dsub_rn(__dadd_rn(qp[2], qm[2]), two_s0);
-        const double xp = __dadd_rn(x[0], h), xm = __dsub_rn(x[0], h);
-        const double yp = __dadd_rn(x[1], h), ym = __dsub_rn(x[1], h);
-        const double zp = __dadd_rn(x[2], h), zm = __dsub_rn(x[2], h);
-        const double xy = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, yp, x[2], true, &cc), query_sdf<F32>(G, xm, ym, x[2], true, &cc)),
-                                              query_sdf<F32>(G, xp, ym, x[2], true, &cc)), query_sdf<F32>(G, xm, yp, x[2], true, &cc));
-        const double xz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, xp, x[1], zp, true, &cc), query_sdf<F32>(G, xm, x[1], zm, true, &cc)),
-                                              query_sdf<F32>(G, xp, x[1], zm, true, &cc)), query_sdf<F32>(G, xm, x[1], zp, true, &cc));
-        const double yz = __dsub_rn(__dsub_rn(__dadd_rn(query_sdf<F32>(G, x[0], yp, zp, true, &cc), query_sdf<F32>(G, x[0], ym, zm, true, &cc)),
-                                              query_sdf<F32>(G, x[0], yp, zm, true, &cc)), query_sdf<F32>(G, x[0], ym, zp, true, &cc));
-        H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
-        constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) H[i] = exact_div(H[i], kEps2, kREps2);
-    }
+    double d, g[3], H[9];
+    sdf_stencil<F32>(G, x, d, g, H);
     const double gn = sqrt(dot3(g, g));
     const double rgn = 1.0 / gn;
     double e[3];

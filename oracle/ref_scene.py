@@ -65,13 +65,13 @@ def make_probe(bodies, kn, kt, mu, damping, joint_type="translational", inject_f
     return p
 
 
-def rollout(p, q0, qdot0, f_ext0, n_steps, trajectory=False):
+def rollout(p, q0, qdot0, f_ext0, n_steps, trajectory=False, move_name="part0"):
     """reset -> set_state -> external force on part0 -> forward: what BFSPlanner does
     per action (run_joint_plan.py:543-554). -> (seconds in forward, q, qdot[, Q, QD])."""
     p.reset()
     p.set_state_init(np.asarray(q0, dtype=np.float64), np.asarray(qdot0, dtype=np.float64))
     p.reset()
-    p.set_body_external_force("part0", np.asarray(f_ext0, dtype=np.float64))
+    p.set_body_external_force(move_name, np.asarray(f_ext0, dtype=np.float64))
     if not trajectory:
         t = p.time_forward(int(n_steps))
         return t, p.get_q(), p.get_qdot()
@@ -81,3 +81,35 @@ def rollout(p, q0, qdot0, f_ext0, n_steps, trajectory=False):
         Q.append(p.get_q())
         QD.append(p.get_qdot())
     return t, p.get_q(), p.get_qdot(), np.array(Q), np.array(QD)
+
+
+def probe_from_assembly(parts, move_id, still_ids, joint_type="translational", sdf_dx=0.1, col_th=0.01, **xml_kw):
+    """Reference Simulation built the way the planners build it: OBJ files on disk +
+    the planner XML (the reference's own tinyobj loader, principal-axes frames, sdfgen)."""
+    from assemble_them_all_b200 import synth
+    ref_probe = _import_probe()
+    tmp = tempfile.mkdtemp(prefix="ref_asm_")
+    synth.write_assembly(parts, tmp)
+    xml = synth.planner_xml(tmp, move_id, still_ids, joint_type=joint_type, sdf_dx=sdf_dx, col_th=col_th, **xml_kw)
+    return ref_probe.Probe(xml, tmp)
+
+
+def extract_scene(p):
+    """Everything the contact path and the stepper consume, read back from a constructed
+    reference Simulation: per body (robot order) contact points, SDF grid fields, joint
+    type, E_pj_0, E_ji, inertia, mass; per force (force order) bodies and parameters."""
+    names = p.body_names()
+    jt = {0: "fixed", 3: "translational", 6: "free3d-exp"}
+    bodies = []
+    for n in names:
+        bi, ji = p.body_info(n), p.joint_info(n)
+        bodies.append({"name": n, "points": np.asarray(p.contact_points(n)), "grid": dict(p.sdf_grid(n)),
+                       "joint_type": jt[int(ji["ndof"])], "E_pj_0": np.asarray(ji["E_pj_0"]),
+                       "E_ji": np.asarray(bi["E_ji"]), "inertia": np.asarray(bi["inertia"]), "mass": float(bi["mass"]),
+                       "index": int(bi["index"])})
+    forces = []
+    for fi in range(p.num_forces()):
+        info = p.force_info(fi)
+        forces.append({"a": names.index(info["contact_body"]), "b": names.index(info["sdf_body"]), "kn": info["kn"],
+                       "kt": info["kt"], "mu": info["mu"], "damping": info["damping"]})
+    return {"bodies": bodies, "forces": forces, "h": float(p.timestep()), "gravity": np.asarray(p.gravity())}
