@@ -69,6 +69,7 @@ SIGNATURES = {
     "sdfc_sim_get_state": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "sdfc_sim_set_external_force": (C.c_int, [C.c_void_p, c_double_p]),
     "sdfc_sim_clear_contact_history": (C.c_int, [C.c_void_p]),
+    "sdfc_sim_set_active": (C.c_int, [C.c_void_p, c_uint8_p]),
     "sdfc_sim_forward": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "sdfc_sim_get_status": (C.c_int, [C.c_void_p, c_uint8_p, c_uint8_p]),
     "sdfc_sim_get_poses": (C.c_int, [C.c_void_p, c_double_p]),

@@ -364,6 +364,15 @@ class BatchedSimulation:
         self._fext[:] = 0.0
         check(self._lib.sdfc_sim_set_external_force(self._h, _dp(self._fext)))
 
+    def set_active(self, active=None):
+        """Only environments with active[e] True take part in the following forward()
+        calls (None = all); the others keep their state."""
+        if active is None:
+            check(self._lib.sdfc_sim_set_active(self._h, None))
+            return
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(active, dtype=bool), (self.n_envs,)), dtype=np.uint8)
+        check(self._lib.sdfc_sim_set_active(self._h, a.ctypes.data_as(_lib.c_uint8_p)))
+
     # ---- stepping
     def forward(self, n_steps, trajectory=False):
         """n BDF1 steps of every environment. trajectory=True -> (q, qdot) of shape
@@ -402,3 +411,26 @@ class BatchedSimulation:
         if self._h:
             self._lib.sdfc_sim_destroy(self._h)
             self._h = C.c_void_p()
+
+
+def build_simulation(ctx, scene, n_envs):
+    """BatchedSimulation for `n_envs` copies of one constructed assembly.
+
+    scene: {"bodies": [{points (n,3), grid {ni,nj,nk,min_box,max_box,dx,dy,dz,col_th,grid},
+    joint_type, E_pj_0, E_ji, inertia, mass}, ...] in robot order, "forces": [{a, b, kn, kt,
+    mu, damping}, ...] in Robot::_forces order, "h", "gravity"} - the state a constructed
+    reference Simulation holds for this path (Simulation_Constructor.cpp:143-714)."""
+    bodies, forces = scene["bodies"], scene["forces"]
+    sdf_of, pts_of = {}, {}
+    pairs = []
+    for f in forces:
+        a, b = f["a"], f["b"]
+        if b not in sdf_of:
+            sdf_of[b] = SdfGrid.from_dict(ctx, bodies[b]["grid"])
+        if a not in pts_of:
+            pts_of[a] = ContactPoints(ctx, bodies[a]["points"])
+        pairs.append(ForceGeneralSDFContact(ctx, pts_of[a], sdf_of[b], f["kn"], f["kt"], f["mu"], f["damping"], 6 * a, 6 * b))
+    batch = ContactBatch(ctx, n_envs, len(bodies), pairs, [f["a"] for f in forces], [f["b"] for f in forces])
+    sim = BatchedSimulation(batch, bodies, scene["gravity"], scene["h"])
+    sim._keep = (batch, pairs, sdf_of, pts_of)
+    return sim

@@ -51,6 +51,7 @@ struct SimDev {
     double *gnorm, *alpha;                   // [n_envs]
     int *phase, *trial, *iter, *strike, *steps_left, *step_idx;
     uint8_t *converged, *touched;
+    const uint8_t* active;                   // [n_envs] or nullptr (all environments step)
     const double* fext;                      // [n_envs][n_bodies][6]
     double *E, *phi;                         // contact-path inputs
     int* env_mode;
@@ -341,11 +342,13 @@ __device__ void body_pose(const BodyDev& b, const JointKin& k, const double* qd,
 // ------------------------------------------------------------------ kernels
 __global__ void k_sim_begin(SimDev S, int n_steps) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env == 0) *S.n_unfinished = (n_steps > 0) ? S.n_envs : 0;
     if (env >= S.n_envs) return;
-    S.steps_left[env] = n_steps;
+    // environments masked out by sdfc_sim_set_active keep their state untouched
+    const bool on = n_steps > 0 && (S.active == nullptr || S.active[env] != 0);
+    if (on) atomicAdd(S.n_unfinished, 1);
+    S.steps_left[env] = on ? n_steps : 0;
     S.step_idx[env] = 0;
-    S.phase[env] = (n_steps > 0) ? PH_DERIV : PH_DONE;
+    S.phase[env] = on ? PH_DERIV : PH_DONE;
     S.iter[env] = 0;
     S.strike[env] = 0;
     const size_t o = (size_t)env * S.nr;
@@ -758,7 +761,8 @@ struct sdfc_sim {
     double* d_state = nullptr;   // q, qdot, q0, qdot0, x, dx
     double* d_scalars = nullptr; // gnorm, alpha
     int* d_ints = nullptr;       // phase, trial, iter, strike, steps_left, step_idx, env_mode
-    uint8_t *d_converged = nullptr, *d_touched = nullptr;
+    uint8_t *d_converged = nullptr, *d_touched = nullptr, *d_active = nullptr;
+    bool use_active = false;
     double* d_fext = nullptr;
     int* d_unfinished = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -829,6 +833,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     A(dev_alloc(&s->d_ints, (size_t)7 * ne));
     A(dev_alloc(&s->d_converged, (size_t)ne));
     A(dev_alloc(&s->d_touched, (size_t)ne * np));
+    A(dev_alloc(&s->d_active, (size_t)ne));
     A(dev_alloc(&s->d_fext, (size_t)ne * nb * 6));
     A(dev_alloc(&s->d_unfinished, (size_t)1));
     A(dev_alloc(&s->d_counters, (size_t)4));
@@ -859,7 +864,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     D.gnorm = s->d_scalars; D.alpha = s->d_scalars + ne;
     D.phase = s->d_ints; D.trial = s->d_ints + ne; D.iter = s->d_ints + 2 * ne; D.strike = s->d_ints + 3 * ne;
     D.steps_left = s->d_ints + 4 * ne; D.step_idx = s->d_ints + 5 * ne; D.env_mode = s->d_ints + 6 * ne;
-    D.converged = s->d_converged; D.touched = s->d_touched; D.fext = s->d_fext;
+    D.converged = s->d_converged; D.touched = s->d_touched; D.fext = s->d_fext; D.active = nullptr;
     D.E = batch->d_E; D.phi = batch->d_phi;
     D.fm_sub = batch->d_fm_sub; D.Km_sub = batch->d_Km_sub; D.Dm_sub = batch->d_Dm_sub; D.n_active = batch->d_n_active;
     D.q_traj = nullptr; D.qdot_traj = nullptr;
@@ -872,7 +877,7 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     if (!s) return SDFC_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_bodies); cudaFree(s->d_pair_a); cudaFree(s->d_pair_b); cudaFree(s->d_state); cudaFree(s->d_scalars);
-    cudaFree(s->d_ints); cudaFree(s->d_converged); cudaFree(s->d_touched); cudaFree(s->d_fext); cudaFree(s->d_unfinished);
+    cudaFree(s->d_ints); cudaFree(s->d_converged); cudaFree(s->d_touched); cudaFree(s->d_active); cudaFree(s->d_fext); cudaFree(s->d_unfinished);
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
     delete s;
@@ -917,6 +922,17 @@ sdfc_status sdfc_sim_clear_contact_history(sdfc_sim* s) {
     return SDFC_OK;
 }
 
+sdfc_status sdfc_sim_set_active(sdfc_sim* s, const uint8_t* active_host) {
+    SDFC_REQUIRE(s != nullptr, "sdfc_sim_set_active: sim is NULL");
+    SDFC_CUDA(cudaSetDevice(s->ctx->device));
+    s->use_active = active_host != nullptr;
+    if (active_host) {
+        SDFC_CUDA(cudaMemcpyAsync(s->d_active, active_host, (size_t)s->n_envs, cudaMemcpyHostToDevice, s->ctx->stream));
+        SDFC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    }
+    return SDFC_OK;
+}
+
 sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, double* qdot_traj_host) {
     SDFC_REQUIRE(s != nullptr, "sdfc_sim_forward: sim is NULL");
     SDFC_REQUIRE(n_steps >= 0, "sdfc_sim_forward: negative step count");
@@ -937,7 +953,9 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     SimDev D = s->dev;
     D.q_traj = q_traj_host ? s->d_traj_q : nullptr;
     D.qdot_traj = qdot_traj_host ? s->d_traj_qd : nullptr;
+    D.active = s->use_active ? s->d_active : nullptr;
     const int blocks = (s->n_envs + 31) / 32;
+    SDFC_CUDA(cudaMemsetAsync(s->d_unfinished, 0, sizeof(int), st));
     k_sim_begin<<<blocks, 32, 0, st>>>(D, n_steps);
     s->ctx->launches += 1;
     // every step needs at least two rounds (one Newton evaluation, one line-search

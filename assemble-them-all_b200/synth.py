@@ -172,6 +172,29 @@ def peg_array(nx=4, ny=5, n_vertices=10000, n_parts=20):
     return parts
 
 
+def l_channel(h=0.25, clearance=0.1):
+    """Depth-2 planning scene: a unit cube (part 0) at the blind end of an L-shaped channel
+    cut into a 5x3x4 block (part 1). The cube has to slide +x to the corner of the channel
+    and then leave through the vertical shaft (+z); every other axis move stalls at once."""
+    w = 0.5 + clearance
+    xs = _axis([-2.0, -w, 1.5 - w, 1.5 + w, 3.0], h)
+    ys = _axis([-1.5, -w, w, 1.5], h)
+    zs = _axis([-2.0, -w, w, 2.0], h)
+    xc, yc, zc = (0.5 * (a[:-1] + a[1:]) for a in (xs, ys, zs))
+    X, Y, Z = np.meshgrid(xc, yc, zc, indexing="ij")
+    tunnel = (X > -w) & (X < 1.5 + w) & (np.abs(Y) < w) & (np.abs(Z) < w)
+    shaft = (np.abs(X - 1.5) < w) & (np.abs(Y) < w) & (Z > -w)
+    Vb, Fb = lattice_surface(xs, ys, zs, ~(tunnel | shaft))
+    Vc, Fc = box_mesh((1.0, 1.0, 1.0), (0.0, 0.0, 0.0), h)
+    return {"0": (Vc, Fc), "1": (Vb, Fb)}
+
+
+def reorient(parts, R):
+    """The same assembly with every vertex rotated by R (3x3)."""
+    R = np.asarray(R, dtype=np.float64)
+    return {k: (V @ R.T, F) for k, (V, F) in parts.items()}
+
+
 def write_assembly(parts, folder):
     os.makedirs(folder, exist_ok=True)
     for pid, (V, F) in parts.items():

@@ -220,6 +220,12 @@ SDFC_API sdfc_status sdfc_sim_get_state(sdfc_sim* sim, double* q_host, double* q
 SDFC_API sdfc_status sdfc_sim_set_external_force(sdfc_sim* sim, const double* f_host);
 /* Simulation::reset's clear_all_contact_bodies (Simulation.cpp:896). */
 SDFC_API sdfc_status sdfc_sim_clear_contact_history(sdfc_sim* sim);
+/* Restrict the following sdfc_sim_forward calls to the environments with
+ * active_host[env] != 0 (n_envs bytes); the others keep q, qdot, convergence flag
+ * and contact history untouched and cost no contact work. NULL = every
+ * environment steps. A batched BFS stage uses this to retire rollouts that hit
+ * their stop rule (run_joint_plan.py:556-567) while the rest continue. */
+SDFC_API sdfc_status sdfc_sim_set_active(sdfc_sim* sim, const uint8_t* active_host);
 /* Simulation::forward(n_steps) (Simulation.cpp:914) for every environment.
  * q_traj_host / qdot_traj_host: [n_steps][n_envs][ndof_r] or NULL; with NULL the
  * call moves no per-step data to the host (state stays in HBM). */

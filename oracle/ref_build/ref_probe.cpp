@@ -422,6 +422,8 @@ struct Probe {
     void set_joint_q(const std::string& name, const Eigen::VectorXd& q) { sim->set_joint_q(name, q); }
     Eigen::VectorXd get_joint_qdot(const std::string& name) { return sim->get_joint_qdot(name); }
     void zero_joint_qdot(const std::string& name) { sim->zero_joint_qdot(name); }
+    Matrix4 get_body_E0i(const std::string& name) { return sim->get_body_E0i(name); }
+    Matrix3X get_body_vertices(const std::string& name, bool world_frame) { return sim->get_body_vertices(name, world_frame); }
 
     void reset_time_report() { sim->_robot->reset_time_report(); }
 
@@ -502,6 +504,8 @@ PYBIND11_MODULE(ref_probe, m) {
         .def("set_joint_q", &Probe::set_joint_q)
         .def("get_joint_qdot", &Probe::get_joint_qdot)
         .def("zero_joint_qdot", &Probe::zero_joint_qdot)
+        .def("get_body_E0i", &Probe::get_body_E0i)
+        .def("get_body_vertices", &Probe::get_body_vertices, py::arg("name"), py::arg("world_frame") = false)
         .def("reset_time_report", &Probe::reset_time_report)
         .def("time_force_evals", &Probe::time_force_evals, py::arg("reps"), py::arg("deriv"),
              py::call_guard<py::gil_scoped_release>());

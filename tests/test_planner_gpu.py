@@ -1,0 +1,88 @@
+"""GPU: planner decisions. The batched BFS planner on the CUDA stepper (through the C-ABI)
+against the sequential planner loop on the UNMODIFIED reference simulator
+(oracle/_ref/ref_probe, CPU) on the same synthetic assemblies, built by the reference
+itself from OBJ files. Integer outcomes (status, action sequence, stages, rollouts
+consumed, substeps per rollout) must be identical; the substep path agrees to 1e-9
+relative."""
+import numpy as np
+import pytest
+
+from assemble_them_all_b200 import planner as PL
+from assemble_them_all_b200 import synth
+from tests.drivers import seq_planner as SP
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cuda_ctx, parts, joint_type, dx, n_envs):
+    from assemble_them_all_b200 import contact
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    p = ref_scene.probe_from_assembly(parts, "0", ["1"], joint_type, sdf_dx=dx)
+    hulls = PL.HullPair(np.array(p.get_body_vertices("part0")).T, np.array(p.get_body_vertices("part1", True)).T)
+    sim = contact.build_simulation(cuda_ctx, ref_scene.extract_scene(p), n_envs)
+    return p, hulls, sim
+
+
+@pytest.mark.parametrize("n_envs", [6, 64])
+def test_translational_depth2_plan_matches_reference(cuda_ctx, n_envs):
+    p, hulls, sim = _setup(cuda_ctx, synth.l_channel(), "translational", 0.1, n_envs)
+    seq = SP.SequentialBFSPlanner(p, "part0", hulls)
+    st, path, acts, stages = seq.plan(PL.TRANS_ACTIONS, max_depth=8)
+    assert st == "Success" and acts == [4, 0]
+    r = PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=8)
+    assert (r.status, r.actions, r.stages, r.rollouts) == (st, acts, stages, seq.rollouts)
+    assert r.path.shape == path.shape
+    assert rel_err(path, r.path) <= 1e-9
+    if n_envs == 64:  # the whole second level ran as one wave
+        assert r.forward_calls < 30
+    sim.close()
+
+
+def test_action_order_on_reoriented_peg(cuda_ctx):
+    R = synth.axis_angle_rotation(np.array([0.0, 1.0, 0.0]), -np.pi / 2)
+    parts = synth.reorient(synth.peg_in_hole(n_vertices=1500, peg_z=(-1.0, 4.0)), R)
+    p, hulls, sim = _setup(cuda_ctx, parts, "translational", 0.1, 6)
+    seq = SP.SequentialBFSPlanner(p, "part0", hulls)
+    st, path, acts, stages = seq.plan(PL.TRANS_ACTIONS, max_depth=1)
+    r = PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=1)
+    assert (r.status, r.actions, r.stages, r.rollouts) == (st, acts, stages, seq.rollouts)
+    assert st == "Success" and r.path.shape == path.shape and rel_err(path, r.path) <= 1e-9
+    sim.close()
+
+
+def test_rotational_level_matches_reference(cuda_ctx):
+    """12 actions (6 translations, 6 torques) from the start state; every rollout's stop
+    chunk and final state must match the reference rollout by rollout."""
+    p, hulls, sim = _setup(cuda_ctx, synth.l_channel(), "free3d-exp", 0.1, 12)
+    seq = SP.SequentialBFSPlanner(p, "part0", hulls, rotation=True)
+    ref = [seq._rollout(np.zeros(6), [], a) for a in PL.ROT_ACTIONS]
+    bp = PL.BatchedBFSPlanner(sim, 0, hulls, rotation=True)
+    got = bp._run_wave([(np.zeros(6), np.zeros((0, 6)), a) for a in range(12)])
+    for a in range(12):
+        st, new_q, temp_path = ref[a]
+        gst, gpath, chunks = got[a]
+        assert gst == st and len(temp_path) == len(gpath) == 100 * chunks, f"action {a}"
+        assert rel_err(np.array(temp_path), gpath) <= 1e-9, f"action {a}"
+    r = bp.plan(max_depth=1)
+    assert r.status == "Failure" and r.rollouts == 12
+    sim.close()
+
+
+def test_inactive_environments_keep_their_state(cuda_ctx):
+    p, hulls, sim = _setup(cuda_ctx, synth.l_channel(), "translational", 0.1, 4)
+    q0 = np.array([[0.0, 0, 0], [0.1, 0, 0], [0.2, 0, 0], [0.3, 0, 0]])
+    sim.reset(q0, np.zeros_like(q0))
+    sim.set_body_external_force(0, np.array([0, 0, 0, 100.0, 0, 0]))
+    sim.set_active([True, False, True, False])
+    sim.forward(10)
+    q, qd = sim.get_state()
+    assert np.array_equal(q[[1, 3]], q0[[1, 3]]) and not qd[[1, 3]].any()
+    assert (q[[0, 2], 0] > q0[[0, 2], 0]).all()
+    assert sim.stats()["env_steps"] == 20
+    sim.set_active(None)
+    sim.forward(1)
+    assert sim.stats()["env_steps"] == 24
+    sim.close()
