@@ -62,6 +62,17 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "sdfc_batch_detect_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdfc_batch_queries_per_eval": (C.c_int64, [C.c_void_p]),
+    "sdfc_ground_create": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_double, C.c_double, c_void_pp]),
+    "sdfc_ground_set_transform": (C.c_int, [C.c_void_p, c_double_p]),
+    "sdfc_ground_set_stiffness": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "sdfc_ground_set_friction": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_ground_set_damping": (C.c_int, [C.c_void_p, C.c_double]),
+    "sdfc_ground_destroy": (C.c_int, [C.c_void_p]),
+    "sdfc_ground_force": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "sdfc_ground_force_deriv": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "sdfc_batch_set_grounds": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), c_int32_p]),
+    "sdfc_batch_get_ground_active": (C.c_int, [C.c_void_p, c_int32_p]),
+    "sdfc_sim_get_ground_history": (C.c_int, [C.c_void_p, c_uint8_p]),
     "sdfc_sim_create": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, c_void_pp]),
     "sdfc_sim_destroy": (C.c_int, [C.c_void_p]),
     "sdfc_sim_ndof_r": (C.c_int, [C.c_void_p]),

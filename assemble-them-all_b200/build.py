@@ -18,7 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("SDFC_OUT") or os.path.join(HERE, "libsdfcontact_b200.so")
-SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu"]
+SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu", "sdfc_ground.cu"]
 FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7
 HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_host.h", FORCE_INST,
            os.path.join("..", "..", "include", "sdfcontact_b200.h")]

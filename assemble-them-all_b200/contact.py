@@ -246,6 +246,68 @@ class ForceGeneralSDFContact:
             self._h = C.c_void_p()
 
 
+class ForceGroundContact:
+    """ForceGroundContact (Force/ForceGroundContact.h): contact points of one body against
+    the plane through E_g's origin with normal E_g[:3, 2]."""
+
+    def __init__(self, ctx, contact_points, E_g, kn=1.0, kt=0.0, mu=0.0, damping=0.0, index_contact=0):
+        self.ctx, self._lib = ctx, ctx._lib
+        self.contact_points = contact_points
+        self.index_contact = int(index_contact)
+        self._h = C.c_void_p()
+        check(self._lib.sdfc_ground_create(ctx._h, contact_points._h, _dp(_colmajor44(E_g)), float(kn), float(kt), float(mu),
+                                           float(damping), C.byref(self._h)))
+        self.touched = False  # body->add_contact_body("ground"), CollisionDetection.cpp:67
+
+    def set_transform(self, E_g):
+        check(self._lib.sdfc_ground_set_transform(self._h, _dp(_colmajor44(E_g))))
+
+    def set_stiffness(self, kn, kt):
+        check(self._lib.sdfc_ground_set_stiffness(self._h, float(kn), float(kt)))
+
+    def set_friction(self, mu):
+        check(self._lib.sdfc_ground_set_friction(self._h, float(mu)))
+
+    def set_damping(self, damping):
+        check(self._lib.sdfc_ground_set_damping(self._h, float(damping)))
+
+    def force_sub(self, E, phi):
+        """-> fm_sub (6,), n_active"""
+        fm = np.empty(6)
+        n = C.c_int32(0)
+        check(self._lib.sdfc_ground_force(self._h, _dp(_colmajor44(E)), _dp(_f64(phi)), _dp(fm), C.byref(n)))
+        self.touched |= n.value > 0
+        return fm, n.value
+
+    def force_deriv_sub(self, E, phi):
+        """-> fm_sub (6,), Km_sub (6,6), Dm_sub (6,6), n_active"""
+        fm, Km, Dm = np.empty(6), np.empty((6, 6)), np.empty((6, 6))
+        n = C.c_int32(0)
+        check(self._lib.sdfc_ground_force_deriv(self._h, _dp(_colmajor44(E)), _dp(_f64(phi)), _dp(fm), _dp(Km), _dp(Dm),
+                                                C.byref(n)))
+        self.touched |= n.value > 0
+        return fm, np.ascontiguousarray(Km.T), np.ascontiguousarray(Dm.T), n.value
+
+    def computeForce(self, fm, E, phi):
+        """Accumulates into the system vector like ForceGroundContact.cpp:129."""
+        f, n = self.force_sub(E, phi)
+        fm[self.index_contact:self.index_contact + 6] += f
+        return n
+
+    def computeForceWithDerivative(self, fm, Km, Dm, E, phi):
+        f, K, D, n = self.force_deriv_sub(E, phi)
+        s = slice(self.index_contact, self.index_contact + 6)
+        fm[s] += f
+        Km[s, s] += K
+        Dm[s, s] += D
+        return n
+
+    def close(self):
+        if self._h:
+            self._lib.sdfc_ground_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class ContactBatch:
     """E environments x P pairs sharing geometry (device-resident)."""
 
@@ -265,6 +327,20 @@ class ContactBatch:
     @property
     def queries_per_eval(self):
         return int(self._lib.sdfc_batch_queries_per_eval(self._h))
+
+    def set_grounds(self, grounds, bodies):
+        """ForceGroundContact forces of every environment: grounds[g] acts on body bodies[g]."""
+        self.grounds = list(grounds)
+        arr = (C.c_void_p * len(grounds))(*[g._h for g in grounds])
+        b = np.ascontiguousarray(bodies, dtype=np.int32)
+        check(self._lib.sdfc_batch_set_grounds(self._h, len(grounds), arr, b.ctypes.data_as(_lib.c_int32_p)))
+        self.n_grounds = len(grounds)
+
+    def ground_active(self):
+        """(n_envs, n_grounds) contact counts of the last evaluation."""
+        n = np.empty((self.n_envs, self.n_grounds), dtype=np.int32)
+        check(self._lib.sdfc_batch_get_ground_active(self._h, n.ctypes.data_as(_lib.c_int32_p)))
+        return n
 
     def eval(self, E, phi, deriv=True):
         """E: (n_envs, n_bodies, 4, 4); phi: (n_envs, n_bodies, 6). Host arrays in and out.
@@ -396,6 +472,13 @@ class BatchedSimulation:
         check(self._lib.sdfc_sim_get_status(self._h, None, t.ctypes.data_as(_lib.c_uint8_p)))
         return t.astype(bool)
 
+    def get_ground_history(self):
+        """(n_envs, n_grounds) bool: the body recorded "ground" since the last reset."""
+        ng = getattr(self.batch, "n_grounds", 0)
+        t = np.empty((self.n_envs, ng), dtype=np.uint8)
+        check(self._lib.sdfc_sim_get_ground_history(self._h, t.ctypes.data_as(_lib.c_uint8_p)))
+        return t.astype(bool)
+
     def get_body_E0i(self):
         """(n_envs, n_bodies, 4, 4) body poses at the current state."""
         E = np.empty((self.n_envs, self.n_bodies, 4, 4))
@@ -431,6 +514,14 @@ def build_simulation(ctx, scene, n_envs):
             pts_of[a] = ContactPoints(ctx, bodies[a]["points"])
         pairs.append(ForceGeneralSDFContact(ctx, pts_of[a], sdf_of[b], f["kn"], f["kt"], f["mu"], f["damping"], 6 * a, 6 * b))
     batch = ContactBatch(ctx, n_envs, len(bodies), pairs, [f["a"] for f in forces], [f["b"] for f in forces])
+    grounds = []
+    for g in scene.get("grounds", []):
+        a = g["body"]
+        if a not in pts_of:
+            pts_of[a] = ContactPoints(ctx, bodies[a]["points"])
+        grounds.append(ForceGroundContact(ctx, pts_of[a], g["E_g"], g["kn"], g["kt"], g["mu"], g["damping"], 6 * a))
+    if grounds:
+        batch.set_grounds(grounds, [g["body"] for g in scene["grounds"]])
     sim = BatchedSimulation(batch, bodies, scene["gravity"], scene["h"])
-    sim._keep = (batch, pairs, sdf_of, pts_of)
+    sim._keep = (batch, pairs, sdf_of, pts_of, grounds)
     return sim

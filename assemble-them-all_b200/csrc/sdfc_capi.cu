@@ -88,11 +88,19 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     c->end();
     c->begin(2); launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
     c->launches += 3;
+    if (b->gset) {
+        st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, deriv, env_mode_dev);
+        if (st != SDFC_OK) return st;
+    }
     if (scatter) {
         c->begin(3);
         launch_scatter_system(dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
         c->end();
         c->launches += 1;
+        if (b->gset) {
+            st = sdfc_host::ground_set_scatter(b->gset, deriv, fm_dev, Km_dev, Dm_dev);
+            if (st != SDFC_OK) return st;
+        }
     }
     if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
@@ -638,7 +646,28 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_nact) cudaFreeHost(b->h_nact);
+    sdfc_host::ground_set_destroy(b->gset);
     delete b;
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_set_grounds(sdfc_batch* b, int n_grounds, sdfc_ground* const* grounds, const int32_t* body) {
+    SDFC_REQUIRE(b && grounds && body && n_grounds > 0, "sdfc_batch_set_grounds: bad argument");
+    SDFC_REQUIRE(b->gset == nullptr, "sdfc_batch_set_grounds: grounds already set");
+    for (int i = 0; i < n_grounds; ++i)
+        SDFC_REQUIRE(grounds[i] && body[i] >= 0 && body[i] < b->n_bodies, "sdfc_batch_set_grounds: NULL ground or body out of range");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    return sdfc_host::ground_set_create(b->ctx, b->n_envs, b->n_bodies, n_grounds, grounds, body, &b->gset);
+}
+
+sdfc_status sdfc_batch_get_ground_active(sdfc_batch* b, int32_t* n_active_out) {
+    SDFC_REQUIRE(b && n_active_out, "sdfc_batch_get_ground_active: NULL argument");
+    SDFC_REQUIRE(b->gset != nullptr, "sdfc_batch_get_ground_active: the batch has no ground contacts");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    SDFC_CUDA(cudaMemcpyAsync(n_active_out, sdfc_host::ground_set_n_active(b->gset),
+                              sizeof(int32_t) * (size_t)b->n_envs * sdfc_host::ground_set_count(b->gset),
+                              cudaMemcpyDeviceToHost, b->ctx->stream));
+    SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
     return SDFC_OK;
 }
 

@@ -95,8 +95,11 @@ struct sdfc_pair {
     double* d_E = nullptr;  // 32 doubles
 };
 
+struct sdfc_ground_set;  // sdfc_ground.cu: E environments x G ground contacts
+
 struct sdfc_batch {
     sdfc_context* ctx = nullptr;
+    sdfc_ground_set* gset = nullptr;  // optional ForceGroundContact forces of every environment
     int n_envs = 0, n_bodies = 0, n_pairs = 0;
     std::vector<sdfc_pair*> pairs;
     std::vector<int32_t> body_a, body_b;
@@ -123,4 +126,19 @@ namespace sdfc_host {
 // (both force variants are launched; CTAs of non-matching environments exit at once).
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
                       bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev);
+}  // namespace sdfc_host
+
+namespace sdfc_host {
+// ForceGroundContact forces of a batch (sdfc_ground.cu). Outputs per (env, ground):
+// 78 doubles = fm[6], Km[36], Dm[36] (6x6 body-diagonal blocks, column-major).
+sdfc_status ground_set_create(sdfc_context* ctx, int n_envs, int n_bodies, int n, sdfc_ground* const* grounds,
+                              const int32_t* body, sdfc_ground_set** out);
+void ground_set_destroy(sdfc_ground_set* s);
+sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
+                           const int* env_mode_dev);
+sdfc_status ground_set_scatter(sdfc_ground_set* s, int deriv, double* fm_dev, double* Km_dev, double* Dm_dev);
+const double* ground_set_out(const sdfc_ground_set* s);
+const int32_t* ground_set_n_active(const sdfc_ground_set* s);
+int ground_set_count(const sdfc_ground_set* s);
+const int32_t* ground_set_bodies(const sdfc_ground_set* s);
 }  // namespace sdfc_host

@@ -57,6 +57,11 @@ struct SimDev {
     int* env_mode;
     const double *fm_sub, *Km_sub, *Dm_sub;  // contact-path outputs per (env, pair)
     const int32_t* n_active;
+    int n_grounds;                           // ForceGroundContact forces (0 = none)
+    const int* ground_body;                  // [n_grounds]
+    const double* g_out;                     // [n_envs][n_grounds][78]: fm 6, Km 36, Dm 36 (column-major)
+    const int32_t* g_n_active;               // [n_envs][n_grounds]
+    uint8_t* touched_ground;                 // [n_envs][n_grounds]
     double *q_traj, *qdot_traj;              // [steps][n_envs][nr] or nullptr
     int* n_unfinished;
     unsigned long long* counters;            // deriv evals, value evals, steps
@@ -543,6 +548,22 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
         }
     }
 
+    // ---- ground contact blocks (ForceGroundContact.cpp:129,186-189): body-diagonal
+    for (int gi = 0; gi < S.n_grounds; ++gi) {
+        const size_t eg = (size_t)env * S.n_grounds + gi;
+        if (S.g_n_active[eg] > 0) S.touched_ground[eg] = 1;  // CollisionDetection.cpp:67
+        const int sl = S.bodies[S.ground_body[gi]].dyn;
+        if (sl < 0) continue;
+        const double* o = S.g_out + eg * 78;
+        for (int r = 0; r < 6; ++r) dyn[sl].fm[r] += o[r];
+        if (!deriv) continue;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) {
+                Kmm[sl][sl][r * 6 + c] += o[6 + r + 6 * c];
+                Dmm[sl][sl][r * 6 + c] += o[42 + r + 6 * c];
+            }
+    }
+
     // ---- reduced assembly (Simulation.cpp:379-503) and BDF1 residual (:1081-1112)
     double g[kMaxR], H[kMaxR * kMaxR];
     for (int i = 0; i < nr; ++i) {
@@ -761,7 +782,9 @@ struct sdfc_sim {
     double* d_state = nullptr;   // q, qdot, q0, qdot0, x, dx
     double* d_scalars = nullptr; // gnorm, alpha
     int* d_ints = nullptr;       // phase, trial, iter, strike, steps_left, step_idx, env_mode
-    uint8_t *d_converged = nullptr, *d_touched = nullptr, *d_active = nullptr;
+    uint8_t *d_converged = nullptr, *d_touched = nullptr, *d_active = nullptr, *d_touched_ground = nullptr;
+    int* d_ground_body = nullptr;
+    int n_grounds = 0;
     bool use_active = false;
     double* d_fext = nullptr;
     int* d_unfinished = nullptr;
@@ -834,6 +857,10 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     A(dev_alloc(&s->d_converged, (size_t)ne));
     A(dev_alloc(&s->d_touched, (size_t)ne * np));
     A(dev_alloc(&s->d_active, (size_t)ne));
+    const int ng = batch->gset ? sdfc_host::ground_set_count(batch->gset) : 0;
+    s->n_grounds = ng;
+    A(dev_alloc(&s->d_touched_ground, (size_t)ne * ng));
+    A(dev_alloc(&s->d_ground_body, (size_t)ng));
     A(dev_alloc(&s->d_fext, (size_t)ne * nb * 6));
     A(dev_alloc(&s->d_unfinished, (size_t)1));
     A(dev_alloc(&s->d_counters, (size_t)4));
@@ -847,6 +874,8 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         if (e == cudaSuccess) e = cudaMemset(s->d_ints, 0, sizeof(int) * 7 * ne);
         if (e == cudaSuccess) e = cudaMemset(s->d_converged, 1, ne);
         if (e == cudaSuccess) e = cudaMemset(s->d_touched, 0, (size_t)ne * np);
+        if (e == cudaSuccess && ng) e = cudaMemset(s->d_touched_ground, 0, (size_t)ne * ng);
+        if (e == cudaSuccess && ng) e = cudaMemcpy(s->d_ground_body, sdfc_host::ground_set_bodies(batch->gset), sizeof(int) * ng, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(s->d_fext, 0, sizeof(double) * ne * nb * 6);
         if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * 4);
         if (e != cudaSuccess) st = fail(SDFC_ERR_CUDA, std::string("sdfc_sim_create: ") + cudaGetErrorString(e));
@@ -867,6 +896,9 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     D.converged = s->d_converged; D.touched = s->d_touched; D.fext = s->d_fext; D.active = nullptr;
     D.E = batch->d_E; D.phi = batch->d_phi;
     D.fm_sub = batch->d_fm_sub; D.Km_sub = batch->d_Km_sub; D.Dm_sub = batch->d_Dm_sub; D.n_active = batch->d_n_active;
+    D.n_grounds = ng; D.ground_body = s->d_ground_body; D.touched_ground = s->d_touched_ground;
+    D.g_out = ng ? sdfc_host::ground_set_out(batch->gset) : nullptr;
+    D.g_n_active = ng ? sdfc_host::ground_set_n_active(batch->gset) : nullptr;
     D.q_traj = nullptr; D.qdot_traj = nullptr;
     D.n_unfinished = s->d_unfinished; D.counters = s->d_counters;
     *out = s;
@@ -877,7 +909,7 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     if (!s) return SDFC_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_bodies); cudaFree(s->d_pair_a); cudaFree(s->d_pair_b); cudaFree(s->d_state); cudaFree(s->d_scalars);
-    cudaFree(s->d_ints); cudaFree(s->d_converged); cudaFree(s->d_touched); cudaFree(s->d_active); cudaFree(s->d_fext); cudaFree(s->d_unfinished);
+    cudaFree(s->d_ints); cudaFree(s->d_converged); cudaFree(s->d_touched); cudaFree(s->d_active); cudaFree(s->d_touched_ground); cudaFree(s->d_ground_body); cudaFree(s->d_fext); cudaFree(s->d_unfinished);
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
     delete s;
@@ -919,6 +951,8 @@ sdfc_status sdfc_sim_clear_contact_history(sdfc_sim* s) {
     SDFC_REQUIRE(s != nullptr, "sdfc_sim_clear_contact_history: sim is NULL");
     SDFC_CUDA(cudaSetDevice(s->ctx->device));
     SDFC_CUDA(cudaMemsetAsync(s->d_touched, 0, (size_t)s->n_envs * s->n_pairs, s->ctx->stream));
+    if (s->n_grounds)
+        SDFC_CUDA(cudaMemsetAsync(s->d_touched_ground, 0, (size_t)s->n_envs * s->n_grounds, s->ctx->stream));
     return SDFC_OK;
 }
 
@@ -987,6 +1021,16 @@ sdfc_status sdfc_sim_get_status(sdfc_sim* s, uint8_t* converged, uint8_t* touche
     SDFC_CUDA(cudaSetDevice(s->ctx->device));
     if (converged) SDFC_CUDA(cudaMemcpyAsync(converged, s->d_converged, s->n_envs, cudaMemcpyDeviceToHost, s->ctx->stream));
     if (touched) SDFC_CUDA(cudaMemcpyAsync(touched, s->d_touched, (size_t)s->n_envs * s->n_pairs, cudaMemcpyDeviceToHost, s->ctx->stream));
+    SDFC_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_sim_get_ground_history(sdfc_sim* s, uint8_t* touched_ground) {
+    SDFC_REQUIRE(s && touched_ground, "sdfc_sim_get_ground_history: NULL argument");
+    SDFC_REQUIRE(s->n_grounds > 0, "sdfc_sim_get_ground_history: the simulation has no ground contacts");
+    SDFC_CUDA(cudaSetDevice(s->ctx->device));
+    SDFC_CUDA(cudaMemcpyAsync(touched_ground, s->d_touched_ground, (size_t)s->n_envs * s->n_grounds, cudaMemcpyDeviceToHost,
+                              s->ctx->stream));
     SDFC_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return SDFC_OK;
 }

@@ -46,6 +46,7 @@ typedef struct sdfc_sdf sdfc_sdf;         /* device copy of one body's voxel SDF
 typedef struct sdfc_points sdfc_points;   /* device copy of one body's contact points */
 typedef struct sdfc_pair sdfc_pair;       /* one ForceGeneralSDFContact */
 typedef struct sdfc_batch sdfc_batch;     /* E environments x P pairs, device-resident */
+typedef struct sdfc_ground sdfc_ground;   /* one ForceGroundContact */
 
 /* ---- library ---------------------------------------------------------- */
 SDFC_API int sdfc_version(void);
@@ -148,6 +149,28 @@ SDFC_API void sdfc_scatter_force(int idx_contact, int idx_sdf, const double fm_s
 SDFC_API void sdfc_scatter_deriv(int ndof_m, int idx_contact, int idx_sdf, const double Km_sub[144],
                                  const double Dm_sub[144], double* Km_sys, double* Dm_sys);
 
+/* ---- ground: ForceGroundContact (Force/ForceGroundContact.h, .cpp:9-38) ---- */
+/* The second Force plug-in of the free-fall configuration (examples/test_joint_sim.py:
+ * 36,54): contact points of one body against the plane through E_g's origin with normal
+ * E_g's z axis. E_g: column-major double[16] (Simulation_Constructor.cpp:172-190). */
+SDFC_API sdfc_status sdfc_ground_create(sdfc_context* ctx, sdfc_points* contact_points, const double E_g[16],
+                                        double kn, double kt, double mu, double damping, sdfc_ground** out);
+SDFC_API sdfc_status sdfc_ground_set_transform(sdfc_ground* g, const double E_g[16]);   /* .cpp:22 */
+SDFC_API sdfc_status sdfc_ground_set_stiffness(sdfc_ground* g, double kn, double kt);   /* .cpp:26 */
+SDFC_API sdfc_status sdfc_ground_set_friction(sdfc_ground* g, double mu);               /* .cpp:31 */
+SDFC_API sdfc_status sdfc_ground_set_damping(sdfc_ground* g, double damping);           /* .cpp:35 */
+SDFC_API sdfc_status sdfc_ground_destroy(sdfc_ground* g);
+/* ForceGroundContact::computeForce (.cpp:39-57,106-153): detection
+ * (collision_detection_ground_object, CollisionDetection.cpp:37-68: active iff d <= 0)
+ * + force. fm_sub[6] is OVERWRITTEN with the body's block; n_active > 0 means the body
+ * records "ground" in its contact history. */
+SDFC_API sdfc_status sdfc_ground_force(sdfc_ground* g, const double E[16], const double phi[6], double fm_sub[6],
+                                       int32_t* n_active);
+/* ForceGroundContact::computeForceWithDerivative (.cpp:59-81,155-242): Km_sub / Dm_sub are
+ * the body-diagonal 6x6 blocks, COLUMN-MAJOR double[36]. */
+SDFC_API sdfc_status sdfc_ground_force_deriv(sdfc_ground* g, const double E[16], const double phi[6], double fm_sub[6],
+                                             double Km_sub[36], double Dm_sub[36], int32_t* n_active);
+
 /* ---- batched: E independent environments, device-resident -------------- */
 /* An environment is one Simulation's worth of bodies: n_bodies poses, and
  * n_pairs contact forces pair[p] = (body_a[p] -> contact points, body_b[p] ->
@@ -158,6 +181,14 @@ SDFC_API sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodi
                                        sdfc_pair* const* pairs, const int32_t* body_a, const int32_t* body_b,
                                        sdfc_batch** out);
 SDFC_API sdfc_status sdfc_batch_destroy(sdfc_batch* batch);
+/* Adds the environment's ForceGroundContact forces (ground g acts on body[g]); they are
+ * evaluated by every sdfc_batch_eval* call and by the stepper, and summed into the system
+ * arrays together with the SDF pairs (Robot.cpp:513-551 loops every force). Call once,
+ * before the first evaluation; the batch does not own the ground objects. */
+SDFC_API sdfc_status sdfc_batch_set_grounds(sdfc_batch* batch, int n_grounds, sdfc_ground* const* grounds,
+                                            const int32_t* body);
+/* Ground contact counts of the last evaluation: [n_envs][n_grounds], host. */
+SDFC_API sdfc_status sdfc_batch_get_ground_active(sdfc_batch* batch, int32_t* n_active_out);
 
 /* Host-buffer entry (the plug-in-facing call): E_host [n_envs][n_bodies][16],
  * phi_host [n_envs][n_bodies][6]. Outputs, per environment, the caller-zeroed
@@ -234,6 +265,9 @@ SDFC_API sdfc_status sdfc_sim_forward(sdfc_sim* sim, int n_steps, double* q_traj
  * touched[n_envs][n_pairs]: contact history since the last clear
  * (CollisionDetection.cpp:143-146). Either may be NULL. */
 SDFC_API sdfc_status sdfc_sim_get_status(sdfc_sim* sim, uint8_t* converged, uint8_t* touched);
+/* touched_ground[n_envs][n_grounds]: "ground" entries of the contact history
+ * (CollisionDetection.cpp:67) since the last clear. */
+SDFC_API sdfc_status sdfc_sim_get_ground_history(sdfc_sim* sim, uint8_t* touched_ground);
 /* Simulation::get_body_E0i (Simulation.cpp:248) at the current state:
  * [n_envs][n_bodies][16] column-major. */
 SDFC_API sdfc_status sdfc_sim_get_poses(sdfc_sim* sim, double* E_host);

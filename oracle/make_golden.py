@@ -17,6 +17,13 @@ Fixtures (all seeded, small):
   traj_small.npz      per-step q, qdot of the reference's BDF1 integration of the
                       same pair under the planner's XML (translational and
                       free3d-exp joints, external push), for the batched stepper.
+  freefall_small.npz  the free-fall configuration (examples/test_joint_sim.py:24-63: two
+                      free3d-exp parts, gravity 9.8, ground plane z = -5 with mu 0.8 /
+                      damping 50, SDF contact kn 1e5): the constructed scene (points,
+                      grids, frames, mass properties, forces), ForceGroundContact outputs
+                      (contact ids, d, fm/Km/Dm) for seeded poses and parameter sets that
+                      hit the static and the dynamic Coulomb branch, and a 400-step drop
+                      trajectory of both parts.
 """
 from __future__ import annotations
 
@@ -173,8 +180,99 @@ def make_traj_small(steps=120):
     return path
 
 
+GROUND_CASES = [  # (kn, kt, mu, damping)
+    (1e6, 1e3, 0.8, 5e1),   # test_joint_sim.py:36
+    (1e6, 1e3, 0.0, 0.0),
+    (1e6, 1e3, 0.02, 5e1),  # dynamic branch for most contacts
+    (1e5, 2e3, 0.4, 0.0),
+]
+
+
+def make_freefall_small(steps=400):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import ref_scene
+    rng = np.random.default_rng(synth.MESH_SEED + 5)
+    tmp = tempfile.mkdtemp(prefix="golden_fall_")
+    synth.write_assembly(synth.peg_in_hole(n_vertices=600), tmp)
+    p = ref_probe.Probe(synth.freefall_xml(tmp, sdf_dx=0.1, gravity=9.8, friction=0), tmp)
+    sc = ref_scene.extract_scene(p)
+    out = {"names": np.array(p.body_names()), "h": np.array(sc["h"]), "gravity": sc["gravity"],
+           "n_forces": np.array(len(sc["forces"])), "n_grounds": np.array(len(sc["grounds"])),
+           "n_cases": np.array(len(GROUND_CASES)), "steps": np.array(steps)}
+    for b in sc["bodies"]:
+        n = b["name"]
+        out[f"{n}_points"] = b["points"]
+        pack_grid(out, f"{n}_", b["grid"])
+        for k in ("E_pj_0", "E_ji", "inertia"):
+            out[f"{n}_{k}"] = np.asarray(b[k])
+        out[f"{n}_mass"] = np.array(b["mass"])
+        out[f"{n}_joint_type"] = np.array(b["joint_type"])
+    for i, f in enumerate(sc["forces"]):
+        out[f"f{i}"] = np.array([f["a"], f["b"], f["kn"], f["kt"], f["mu"], f["damping"]], dtype=np.float64)
+    for i, g in enumerate(sc["grounds"]):
+        out[f"g{i}_body"] = np.array(g["body"])
+        out[f"g{i}_E_g"] = g["E_g"]
+        out[f"g{i}_params"] = np.array([g["kn"], g["kt"], g["mu"], g["damping"]])
+    # which entries of Robot::_forces are the ground contacts
+    gfi = [fi for fi in range(p.num_forces()) if p.force_info(fi)["type"] == "ground_contact"]
+    n_static_dynamic = [0, 0]
+    for c, (kn, kt, mu, damp) in enumerate(GROUND_CASES):
+        out[f"c{c}_params"] = np.array([kn, kt, mu, damp])
+        q = np.zeros(12)
+        qd = rng.normal(size=12) * (0.0 if c == 1 else 0.6)
+        q[2] = -3.02 - 0.01 * c          # peg: lowest face slightly below the plane
+        q[8] = -3.01 - 0.01 * c          # block
+        q[3:6] = rng.normal(size=3) * 0.04
+        q[9:12] = rng.normal(size=3) * 0.02
+        p.set_state(q, qd)
+        p.update_robot()
+        out[f"c{c}_q"], out[f"c{c}_qdot"] = q, qd
+        for gi, fi in enumerate(gfi):
+            p.set_force_params(fi, kn, kt, mu, damp, 1.0)
+            name = p.force_info(fi)["contact_body"]
+            bi = p.body_info(name)
+            idx = bi["index"]
+            out[f"c{c}_g{gi}_E"] = np.asarray(bi["E_0i"])
+            out[f"c{c}_g{gi}_phi"] = np.asarray(bi["phi"])
+            det = p.ground_detect(fi)
+            out[f"c{c}_g{gi}_active"] = np.array(det["active_ids"], dtype=np.int32)
+            out[f"c{c}_g{gi}_d"] = np.array(det["d"], dtype=np.float64)
+            fm, Km, Dm = p.force_deriv_public(fi)
+            out[f"c{c}_g{gi}_fm"] = fm[idx:idx + 6]
+            out[f"c{c}_g{gi}_Km"] = Km[idx:idx + 6, idx:idx + 6]
+            out[f"c{c}_g{gi}_Dm"] = Dm[idx:idx + 6, idx:idx + 6]
+            out[f"c{c}_g{gi}_fm_value"] = p.force_public(fi)[idx:idx + 6]
+            assert len(det["active_ids"]) > 0
+    # restore the XML parameters and drop both parts onto the plane
+    for gi, fi in enumerate(gfi):
+        g = sc["grounds"][gi]
+        p.set_force_params(fi, g["kn"], g["kt"], g["mu"], g["damping"], 1.0)
+    q0 = np.zeros(12)
+    q0[2], q0[8] = -2.5, -2.9
+    q0[3:6] = [0.03, -0.02, 0.01]
+    qd0 = np.zeros(12)
+    qd0[0], qd0[7] = 0.4, -0.3
+    p.reset()
+    p.set_state(q0, qd0)
+    Q, QD, CONV = [p.get_q()], [p.get_qdot()], []
+    for _ in range(steps):
+        p.forward(1)
+        Q.append(p.get_q())
+        QD.append(p.get_qdot())
+        CONV.append(p.is_converged())
+    out["traj_q"], out["traj_qdot"], out["traj_converged"] = np.array(Q), np.array(QD), np.array(CONV)
+    for n in p.body_names():
+        out[f"traj_{n}_touched"] = np.array(p.get_contact_bodies(n))
+        out[f"traj_{n}_E_final"] = np.asarray(p.body_info(n)["E_0i"])
+    path = os.path.join(GOLDEN, "freefall_small.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    for fn in (make_contact_small, make_traj_small):
+    fns = {"contact": make_contact_small, "traj": make_traj_small, "freefall": make_freefall_small}
+    sel = [a for a in sys.argv[1:] if a in fns] or list(fns)
+    for fn in (fns[k] for k in sel):
         path = fn()
         print(path, "%.1f KB" % (os.path.getsize(path) / 1024))

@@ -216,6 +216,10 @@ struct Probe {
         return std::chrono::duration<double>(t1 - t0).count();
     }
     void set_force_params(int i, double kn, double kt, double mu, double damping, double scale) {
+        if (auto* g = dynamic_cast<ForceGroundContact*>(sim->_robot->_forces.at(i))) {
+            g->_kn = kn; g->_kt = kt; g->_mu = mu; g->_damping = damping;  // no _scale on the ground force
+            return;
+        }
         auto* f = sdf_force(i);
         f->_kn = kn; f->_kt = kt; f->_mu = mu; f->_damping = damping; f->_scale = scale;
     }
@@ -285,6 +289,19 @@ struct Probe {
         for (auto& c : contacts) ids.push_back(c._id);
         py::dict out;
         out["d"] = d; out["xw"] = xw; out["x_local"] = xl; out["cell"] = cell; out["active_ids"] = ids;
+        return out;
+    }
+
+    // ground contact: the reference's own contact list (ids, d) for force fi
+    py::dict ground_detect(int fi) {
+        auto* g = dynamic_cast<ForceGroundContact*>(sim->_robot->_forces.at(fi));
+        if (!g) throw std::runtime_error("force is not ForceGroundContact");
+        std::vector<Contact> contacts;
+        collision_detection_ground_object(g->_E_g, g->_contact_body, contacts);
+        std::vector<int> ids; std::vector<double> d;
+        for (auto& c : contacts) { ids.push_back(c._id); d.push_back(c._d); }
+        py::dict out;
+        out["active_ids"] = ids; out["d"] = d;
         return out;
     }
 
@@ -474,6 +491,7 @@ PYBIND11_MODULE(ref_probe, m) {
         .def("grid_location", &Probe::grid_location)
         .def("distance", &Probe::distance)
         .def("detect", &Probe::detect)
+        .def("ground_detect", &Probe::ground_detect)
         .def("force_sub", &Probe::force_sub)
         .def("force_deriv_sub", &Probe::force_deriv_sub)
         .def("force_deriv_per_contact", &Probe::force_deriv_per_contact)

@@ -107,9 +107,13 @@ def extract_scene(p):
                        "joint_type": jt[int(ji["ndof"])], "E_pj_0": np.asarray(ji["E_pj_0"]),
                        "E_ji": np.asarray(bi["E_ji"]), "inertia": np.asarray(bi["inertia"]), "mass": float(bi["mass"]),
                        "index": int(bi["index"])})
-    forces = []
+    forces, grounds = [], []
     for fi in range(p.num_forces()):
         info = p.force_info(fi)
+        if info["type"] == "ground_contact":
+            grounds.append({"body": names.index(info["contact_body"]), "E_g": np.asarray(info["E_g"]), "kn": info["kn"],
+                            "kt": info["kt"], "mu": info["mu"], "damping": info["damping"]})
+            continue
         forces.append({"a": names.index(info["contact_body"]), "b": names.index(info["sdf_body"]), "kn": info["kn"],
                        "kt": info["kt"], "mu": info["mu"], "damping": info["damping"]})
-    return {"bodies": bodies, "forces": forces, "h": float(p.timestep()), "gravity": np.asarray(p.gravity())}
+    return {"bodies": bodies, "forces": forces, "grounds": grounds, "h": float(p.timestep()), "gravity": np.asarray(p.gravity())}

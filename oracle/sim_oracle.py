@@ -191,6 +191,97 @@ class PairDesc:
     damping: float = 0.0
 
 
+@dataclass
+class GroundDesc:
+    """One ForceGroundContact (Force/ForceGroundContact.cpp:9-20): contact body + ground frame."""
+    body: int
+    points: np.ndarray
+    E_g: np.ndarray
+    kn: float
+    kt: float
+    mu: float = 0.0
+    damping: float = 0.0
+
+
+CONST_EPS = 1e-8  # constants::eps, Utils.h:9
+
+
+def _gamma(x):  # math::gamma, Utils.h:196-201
+    return np.hstack([-skew(x), np.eye(3)])
+
+
+def ground_detect(E_g, E, points):
+    """collision_detection_ground_object (CollisionDetection.cpp:37-68), mesh branch:
+    d = ng . (xw - xg) per contact point, active iff d <= 0. -> (d, active mask)."""
+    xg, ng = E_g[:3, 3], E_g[:3, 2]
+    R, p = E[:3, :3], E[:3, 3]
+    X = np.asarray(points)
+    # xw = E_0i * [xi; 1]: ((R0 x + R1 y) + R2 z) + p, no contraction
+    xw = ((R[:, 0][None, :] * X[:, 0:1] + R[:, 1][None, :] * X[:, 1:2]) + R[:, 2][None, :] * X[:, 2:3]) + p[None, :]
+    v = xw - xg[None, :]
+    d = (ng[0] * v[:, 0] + ng[1] * v[:, 1]) + ng[2] * v[:, 2]
+    return d, d <= 0.0
+
+
+def ground_force(g: GroundDesc, E, phi, deriv):
+    """ForceGroundContact::computeForce / computeForceWithDerivative
+    (Force/ForceGroundContact.cpp:106-242). -> fm[6], Km[6,6], Dm[6,6], n_active, n_static."""
+    xg, ng = g.E_g[:3, 3], g.E_g[:3, 2]
+    N = np.outer(ng, ng)
+    I3 = np.eye(3)
+    T = I3 - N
+    R, p = E[:3, :3], E[:3, 3]
+    eb = [skew(I3[:, k]) for k in range(3)]
+    RNR = R.T @ N @ R
+    pxg = skew(R.T @ N @ (p - xg))
+    fm = np.zeros(6)
+    Km = np.zeros((6, 6))
+    Dm = np.zeros((6, 6))
+    d_all, act = ground_detect(g.E_g, E, g.points)
+    n_static = 0
+    for i in np.nonzero(act)[0]:
+        xi = g.points[i]
+        d = d_all[i]
+        G = _gamma(xi)
+        J = R @ G
+        Gphi = G @ phi
+        vwi = R @ Gphi
+        fc = -g.kn * ng * d - g.damping * (N @ vwi)                       # :127 / :173
+        fm += J.T @ fc
+        if deriv:
+            RNRxi = RNR @ xi
+            RNRGphi = RNR @ Gphi
+            tmp1 = np.column_stack([-e @ RNRxi for e in eb]) - RNR @ skew(xi) + pxg       # :176-178
+            tmp2 = np.column_stack([-e @ RNRGphi for e in eb]) - RNR @ skew(Gphi)         # :180-182
+            Km -= g.kn * G.T @ np.hstack([tmp1, RNR]) + g.damping * G.T @ np.hstack([tmp2, np.zeros((3, 3))])
+            Dm -= g.damping * G.T @ RNR @ G
+        if g.mu < CONST_EPS:                                              # :132 / :191
+            continue
+        a = T @ vwi
+        an = np.linalg.norm(a)
+        if g.mu * abs(g.kn * d) >= g.kt * an - CONST_EPS:                 # :137 / :197
+            n_static += 1
+            fm += J.T @ (-g.kt * a)
+            if deriv:
+                B = R.T @ T @ R
+                tmp3 = np.hstack([np.column_stack([(B @ e - e @ B) @ Gphi for e in eb]), np.zeros((3, 3))])
+                Dm += -g.kt * J.T @ T @ J
+                Km += -g.kt * G.T @ tmp3
+        else:
+            mukn = g.mu * g.kn
+            t = a / an
+            fm += J.T @ (mukn * d * t)
+            if deriv:
+                A = (I3 - np.outer(t, t)) / an
+                Dm += mukn * J.T @ (d * A) @ T @ J
+                Rt = R.T @ t
+                K1 = -d * np.hstack([np.column_stack([e @ Rt for e in eb]), np.zeros((3, 3))])
+                K2 = np.outer(R.T @ t, ng) @ J
+                K3 = -d * R.T @ A @ T @ R @ np.hstack([skew(Gphi), np.zeros((3, 3))])
+                Km += mukn * G.T @ (K1 + K2 + K3)
+    return fm, Km, Dm, int(act.sum()), n_static
+
+
 def joint_kinematics(bd: BodyDesc, q, qdot, deriv):
     """-> Q (4x4), S_j, S_j_dot (6 x ndof), dSj_dq[k], dSjdot_dq[k]."""
     n = bd.ndof
@@ -248,7 +339,9 @@ class Sim:
     qdot: np.ndarray = None
     f_ext: np.ndarray = None          # (n_bodies, 6)
     converged: bool = True
+    grounds: list = field(default_factory=list)   # GroundDesc, evaluated before the SDF pairs (XML order)
     touched: np.ndarray = None        # per pair, contact history (CollisionDetection.cpp:143-146)
+    touched_ground: np.ndarray = None
     stats: dict = field(default_factory=lambda: {"deriv_evals": 0, "value_evals": 0, "newton_iters": 0})
 
     def __post_init__(self):
@@ -262,6 +355,7 @@ class Sim:
         if self.f_ext is None:
             self.f_ext = np.zeros((len(self.bodies), 6))
         self.touched = np.zeros(len(self.pairs), dtype=bool)
+        self.touched_ground = np.zeros(len(self.grounds), dtype=bool)
         self.A_ij = [Ad(Einv(b.E_ji)) for b in self.bodies]
 
     # ---- kinematics: Robot::update for root joints
@@ -326,6 +420,15 @@ class Sim:
         return fm, Km, Dm
 
     def contact_forces(self, E, phi, fm, Km, Dm, deriv):
+        for gi, g in enumerate(self.grounds):
+            f, K, D, cnt, _ = ground_force(g, E[g.body], phi[g.body], deriv)
+            s = slice(6 * g.body, 6 * g.body + 6)
+            fm[s] += f
+            if cnt > 0:
+                self.touched_ground[gi] = True
+            if deriv:
+                Km[s, s] += K
+                Dm[s, s] += D
         for pi, p in enumerate(self.pairs):
             f, K, D, cnt = O.pair_force(p.grid, E[p.a], phi[p.a], E[p.b], phi[p.b], p.points, p.kn, p.kt, p.mu,
                                         p.damping, deriv)

@@ -118,3 +118,42 @@ def oracle_sim(G, T, joint_type, kn=1e6, kt=1e3, mu=0.0, damping=0.0):
              S.PairDesc(1, 0, grids["part0"], G.points("part1"), kn, kt, mu, damping)]
     key = JOINT_KEYS[joint_type]
     return S.Sim(bodies, pairs, float(T[f"{key}_h"]), np.array([0.0, 0.0, 1e-12]))
+
+
+def load_freefall_golden():
+    """tests/golden/freefall_small.npz -> (npz, scene dict in the layout of
+    contact.build_simulation / oracle.ref_scene.extract_scene)."""
+    z = np.load(os.path.join(GOLDEN, "freefall_small.npz"))
+    names = [str(n) for n in z["names"]]
+    bodies = []
+    for n in names:
+        ni, nj, nk = (int(v) for v in z[f"{n}_dims"])
+        sp = z[f"{n}_spacing"]
+        grid = {"ni": ni, "nj": nj, "nk": nk, "min_box": z[f"{n}_min_box"], "max_box": z[f"{n}_max_box"],
+                "dx": float(sp[0]), "dy": float(sp[1]), "dz": float(sp[2]), "col_th": float(z[f"{n}_col_th"]),
+                "grid": z[f"{n}_grid_f32"].astype(np.float64)}
+        bodies.append({"name": n, "points": z[f"{n}_points"], "grid": grid, "joint_type": str(z[f"{n}_joint_type"]),
+                       "E_pj_0": z[f"{n}_E_pj_0"], "E_ji": z[f"{n}_E_ji"], "inertia": z[f"{n}_inertia"],
+                       "mass": float(z[f"{n}_mass"])})
+    forces = []
+    for i in range(int(z["n_forces"])):
+        a, b, kn, kt, mu, damping = z[f"f{i}"]
+        forces.append({"a": int(a), "b": int(b), "kn": kn, "kt": kt, "mu": mu, "damping": damping})
+    grounds = []
+    for i in range(int(z["n_grounds"])):
+        kn, kt, mu, damping = z[f"g{i}_params"]
+        grounds.append({"body": int(z[f"g{i}_body"]), "E_g": z[f"g{i}_E_g"], "kn": kn, "kt": kt, "mu": mu, "damping": damping})
+    return z, {"bodies": bodies, "forces": forces, "grounds": grounds, "h": float(z["h"]), "gravity": z["gravity"]}
+
+
+def oracle_sim_from_scene(sc):
+    from oracle import sdfc_oracle as O, sim_oracle as S
+    O.build()
+    jt = {"fixed": S.FIXED, "translational": S.TRANSLATIONAL, "free3d-exp": S.FREE3D_EXP}
+    grids = [O.Grid.from_dict(b["grid"]) for b in sc["bodies"]]
+    bodies = [S.BodyDesc(jt[b["joint_type"]], b["E_pj_0"], b["E_ji"], b["inertia"], b["mass"]) for b in sc["bodies"]]
+    pairs = [S.PairDesc(f["a"], f["b"], grids[f["b"]], sc["bodies"][f["a"]]["points"], f["kn"], f["kt"], f["mu"],
+                        f["damping"]) for f in sc["forces"]]
+    grounds = [S.GroundDesc(g["body"], sc["bodies"][g["body"]]["points"], g["E_g"], g["kn"], g["kt"], g["mu"],
+                            g["damping"]) for g in sc.get("grounds", [])]
+    return S.Sim(bodies, pairs, sc["h"], sc["gravity"], grounds=grounds)
