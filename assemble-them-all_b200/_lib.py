@@ -21,6 +21,8 @@ SIGNATURES = {
     "sdfc_version": (C.c_int, []),
     "sdfc_last_error": (C.c_char_p, []),
     "sdfc_device_count": (C.c_int, []),
+    "sdfc_pinned_alloc": (C.c_int, [C.c_size_t, c_void_pp]),
+    "sdfc_pinned_free": (C.c_int, [C.c_void_p]),
     "sdfc_context_create": (C.c_int, [C.c_int, c_void_pp]),
     "sdfc_context_destroy": (C.c_int, [C.c_void_p]),
     "sdfc_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -40,6 +40,32 @@ def _colmajor44(E):
     return np.ascontiguousarray(np.swapaxes(E, -1, -2))
 
 
+class PinnedArray:
+    """numpy array over page-locked host memory (sdfc_pinned_alloc): what the host-buffer
+    entries DMA from / into without a staging copy. Keep the object alive while `.a` is used."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._lib = _lib.load()
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        self._p = C.c_void_p()
+        check(self._lib.sdfc_pinned_alloc(n, C.byref(self._p)))
+        buf = (C.c_char * max(n, 1)).from_address(self._p.value)
+        self.a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.a = None
+            self._lib.sdfc_pinned_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     def __init__(self, device=0):
         self._lib = _lib.load()
@@ -359,6 +385,14 @@ class ContactBatch:
             Km = np.ascontiguousarray(np.swapaxes(Km, 1, 2))
             Dm = np.ascontiguousarray(np.swapaxes(Dm, 1, 2))
         return fm, Km, Dm, nact
+
+    def eval_into(self, E_col, phi, deriv, fm, Km, Dm, nact=None):
+        """The host-buffer C-ABI call without any Python-side copies: E_col is
+        (n_envs, n_bodies, 16) COLUMN-major poses, outputs are written in the library's
+        layout (Km, Dm column-major per environment). Pass PinnedArray buffers for direct DMA."""
+        check(self._lib.sdfc_batch_eval(self._h, _dp(E_col), _dp(phi), int(bool(deriv)), _dp(fm),
+                                        _dp(Km) if deriv else None, _dp(Dm) if deriv else None,
+                                        nact.ctypes.data_as(_lib.c_int32_p) if nact is not None else None))
 
     def eval_device(self, E_ptr, phi_ptr, deriv, fm_ptr, Km_ptr, Dm_ptr, nact_ptr):
         """Raw device pointers (ints). E is column-major per pose. Asynchronous."""

@@ -693,6 +693,23 @@ sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t
     return SDFC_OK;
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+sdfc_status sdfc_pinned_alloc(size_t bytes, void** out) {
+    SDFC_REQUIRE(out != nullptr, "sdfc_pinned_alloc: out is NULL");
+    *out = nullptr;
+    SDFC_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return SDFC_OK;
+}
+sdfc_status sdfc_pinned_free(void* p) {
+    if (p) SDFC_CUDA(cudaFreeHost(p));
+    return SDFC_OK;
+}
+
 sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* phi_host, int deriv, double* fm_out,
                             double* Km_out, double* Dm_out, int32_t* n_active_out) {
     SDFC_REQUIRE(b && E_host && phi_host && fm_out, "sdfc_batch_eval: NULL argument");
@@ -701,25 +718,38 @@ sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* p
     cudaStream_t s = b->ctx->stream;
     const size_t nE = (size_t)b->n_envs * b->n_bodies * 16, nP = (size_t)b->n_envs * b->n_bodies * 6;
     const size_t nm = 6 * (size_t)b->n_bodies, nF = b->n_envs * nm, nK = b->n_envs * nm * nm;
-    std::memcpy(b->h_in, E_host, nE * sizeof(double));
-    std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double));
-    SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, nE * sizeof(double), cudaMemcpyHostToDevice, s));
-    SDFC_CUDA(cudaMemcpyAsync(b->d_phi, b->h_in + nE, nP * sizeof(double), cudaMemcpyHostToDevice, s));
+    const size_t nA = (size_t)b->n_envs * b->n_pairs;
+    // Page-locked caller buffers (sdfc_pinned_alloc, cudaHostRegister, torch pin_memory) are
+    // DMA'd directly; pageable ones go through the library's pinned staging buffers.
+    const double* srcE = E_host;
+    const double* srcP = phi_host;
+    if (!is_pinned(E_host)) { std::memcpy(b->h_in, E_host, nE * sizeof(double)); srcE = b->h_in; }
+    if (!is_pinned(phi_host)) { std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double)); srcP = b->h_in + nE; }
+    SDFC_CUDA(cudaMemcpyAsync(b->d_E, srcE, nE * sizeof(double), cudaMemcpyHostToDevice, s));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_phi, srcP, nP * sizeof(double), cudaMemcpyHostToDevice, s));
     sdfc_status st = batch_run(b, b->d_E, b->d_phi, deriv, nullptr, /*scatter=*/true, b->d_fm, b->d_Km, deriv ? b->d_Dm : nullptr, nullptr);
     if (st != SDFC_OK) return st;
-    SDFC_CUDA(cudaMemcpyAsync(b->h_out, b->d_fm, nF * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // without friction, damping and ground contact Dm is identically zero
+    // (ForceGeneralSDFContact.cpp:352-445 is skipped): filled on the host, no transfer
+    const bool dm_zero = deriv && !b->any_fric && !b->any_damp && b->gset == nullptr;
+    const bool pf = is_pinned(fm_out), pk = deriv && is_pinned(Km_out), pd = deriv && is_pinned(Dm_out);
+    const bool pa = n_active_out && is_pinned(n_active_out);
+    SDFC_CUDA(cudaMemcpyAsync(pf ? fm_out : b->h_out, b->d_fm, nF * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (deriv) {
-        SDFC_CUDA(cudaMemcpyAsync(b->h_out + nF, b->d_Km, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
-        SDFC_CUDA(cudaMemcpyAsync(b->h_out + nF + nK, b->d_Dm, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SDFC_CUDA(cudaMemcpyAsync(pk ? Km_out : b->h_out + nF, b->d_Km, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (!dm_zero)
+            SDFC_CUDA(cudaMemcpyAsync(pd ? Dm_out : b->h_out + nF + nK, b->d_Dm, nK * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
-    SDFC_CUDA(cudaMemcpyAsync(b->h_nact, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs, cudaMemcpyDeviceToHost, s));
+    if (n_active_out)
+        SDFC_CUDA(cudaMemcpyAsync(pa ? n_active_out : b->h_nact, b->d_n_active, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, s));
+    if (dm_zero) std::memset(Dm_out, 0, nK * sizeof(double));  // overlaps the device work
     SDFC_CUDA(cudaStreamSynchronize(s));
-    std::memcpy(fm_out, b->h_out, nF * sizeof(double));
+    if (!pf) std::memcpy(fm_out, b->h_out, nF * sizeof(double));
     if (deriv) {
-        std::memcpy(Km_out, b->h_out + nF, nK * sizeof(double));
-        std::memcpy(Dm_out, b->h_out + nF + nK, nK * sizeof(double));
+        if (!pk) std::memcpy(Km_out, b->h_out + nF, nK * sizeof(double));
+        if (!pd && !dm_zero) std::memcpy(Dm_out, b->h_out + nF + nK, nK * sizeof(double));
     }
-    if (n_active_out) std::memcpy(n_active_out, b->h_nact, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs);
+    if (n_active_out && !pa) std::memcpy(n_active_out, b->h_nact, sizeof(int32_t) * nA);
     return SDFC_OK;
 }
 

@@ -55,6 +55,12 @@ SDFC_API int sdfc_version(void);
 SDFC_API const char* sdfc_last_error(void);
 SDFC_API int sdfc_device_count(void);
 
+/* Page-locked host memory for the host-buffer entries: buffers allocated here (or
+ * registered with cudaHostRegister / torch pin_memory) are DMA'd directly by
+ * sdfc_batch_eval; pageable buffers go through an internal pinned staging copy. */
+SDFC_API sdfc_status sdfc_pinned_alloc(size_t bytes, void** out);
+SDFC_API sdfc_status sdfc_pinned_free(void* p);
+
 /* ---- context ---------------------------------------------------------- */
 SDFC_API sdfc_status sdfc_context_create(int device, sdfc_context** out);
 SDFC_API sdfc_status sdfc_context_destroy(sdfc_context* ctx);
@@ -194,8 +200,9 @@ SDFC_API sdfc_status sdfc_batch_get_ground_active(sdfc_batch* batch, int32_t* n_
  * phi_host [n_envs][n_bodies][6]. Outputs, per environment, the caller-zeroed
  * -then-accumulated system arrays exactly as Robot hands them to the forces:
  * fm_out [n_envs][6*n_bodies]; Km_out, Dm_out [n_envs][(6*n_bodies)^2] column-
- * major (NULL when deriv == 0); n_active_out [n_envs][n_pairs]. Arrays are
- * overwritten (contact contribution only). Includes H2D and D2H copies. */
+ * major (NULL when deriv == 0); n_active_out [n_envs][n_pairs] or NULL. Arrays are
+ * overwritten (contact contribution only). Includes H2D and D2H copies; Dm is not
+ * transferred when it is identically zero (no friction, damping or ground force). */
 SDFC_API sdfc_status sdfc_batch_eval(sdfc_batch* batch, const double* E_host, const double* phi_host, int deriv,
                                      double* fm_out, double* Km_out, double* Dm_out, int32_t* n_active_out);
 
