@@ -54,12 +54,13 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), []) for s in srcs]
     min_blocks = os.environ.get("SDFC_FORCE_MIN_BLOCKS")  # tuning knob: __launch_bounds__(128, n) of k_force
     extra_all = [f"-DSDFC_FORCE_MIN_BLOCKS={int(min_blocks)}"] if min_blocks else []
+    extra_all += os.environ.get("SDFC_EXTRA_FLAGS", "").split()  # tuning builds, e.g. "-DSDFC_LDG256=0"
     nf_blocks = os.environ.get("SDFC_FORCE_NF_MIN_BLOCKS")  # same knob for the planner fast path (k_force<1,0,0>)
     if nf_blocks:
         extra_all.append(f"-DSDFC_FORCE_NF_MIN_BLOCKS={int(nf_blocks)}")
+    jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), list(extra_all)) for s in srcs]
     jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"),
               [f"-DSDFC_FORCE_VARIANT={v}", *extra_all]) for v in range(8)]
     for s, o, extra in jobs:

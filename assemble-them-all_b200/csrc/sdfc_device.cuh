@@ -70,7 +70,19 @@ __device__ __forceinline__ void load_cell(const GridDev& G, int i, int j, int k,
     i = max(0, min(i, G.ni - 1)); j = max(0, min(j, G.nj - 1)); k = max(0, min(k, G.nk - 1));
     if (F32) {
         const size_t idx = (size_t)i + (size_t)G.ni * ((size_t)j + (size_t)G.nj * (size_t)k);
-        const float4 a = __ldg(G.c32 + 2 * idx), b = __ldg(G.c32 + 2 * idx + 1);
+        // one 256-bit read-only load of the 32-byte cell record (LDG.E.256 on sm_100a):
+        // half the L1 wavefronts of two 128-bit gathers
+#ifndef SDFC_LDG256
+#define SDFC_LDG256 0  // measured on B200: the 256-bit form costs registers (occupancy) and was 20 % slower
+#endif
+        float4 a, b;
+#if SDFC_LDG256
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+            : "l"(G.c32 + 2 * idx));
+#else
+        a = __ldg(G.c32 + 2 * idx); b = __ldg(G.c32 + 2 * idx + 1);
+#endif
         v[0] = (double)a.x; v[1] = (double)a.y; v[2] = (double)a.z; v[3] = (double)a.w;
         v[4] = (double)b.x; v[5] = (double)b.y; v[6] = (double)b.z; v[7] = (double)b.w;
         return;

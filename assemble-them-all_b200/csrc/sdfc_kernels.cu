@@ -49,21 +49,24 @@ __device__ __forceinline__ double detect_point(const GridDev& G, const double* R
 
 template <bool F32>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
-                                            const double* p2, int word0, uint32_t* mask_row, int* s_count) {
+                                            const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
+                                            int* s_count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int U = 2;  // words in flight per warp: all point loads of a group are issued before any use
-    int cnt = 0;
-    const int wbase = word0 + warp * kDetectWordsPerWarp;
-    // Broad phase, one lane per word: transform the word's bounding sphere centre
-    // into the SDF frame and test it against the grid box grown by the radius.
-    // Rigid motions preserve distances, so a culled word has no point inside the
-    // box (1e-7 absolute slack covers the rounding of the rotation); every such
-    // point would evaluate to FLT_MAX + col_th > 0, i.e. inactive.
-    unsigned live;
-    {
+#ifndef SDFC_DETECT_U
+#define SDFC_DETECT_U 1
+#endif
+    constexpr int U = SDFC_DETECT_U;  // words in flight per warp: all point loads of a group are issued before any use
+    // Broad phase over the whole tile, one thread per word: transform the word's bounding
+    // sphere centre into the SDF frame and test it against the grid box grown by the
+    // radius. Rigid motions preserve distances, so a culled word has no point inside the
+    // box (1e-7 absolute slack covers the rounding of the rotation); every such point
+    // would evaluate to FLT_MAX + col_th > 0, i.e. inactive. Surviving words are compacted
+    // (in word order) into shared memory and dealt round-robin to the warps, so that the
+    // warps of a CTA finish together even when the contact region covers a few words only.
+    if (threadIdx.x < kDetectTileWords) {
+        const int w = word0 + threadIdx.x;
         bool keep = false;
-        const int w = wbase + lane;
-        if (lane < kDetectWordsPerWarp && w < pd.n_words) {
+        if (w < pd.n_words) {
             const double* sp = pd.wsphere + 4 * (size_t)w;
             double cw[3], cl[3];
             to_world(R1, p1, __ldg(sp), __ldg(sp + 1), __ldg(sp + 2), cw);
@@ -72,20 +75,31 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
             keep = cl[0] >= pd.grid.mn[0] - r && cl[0] <= pd.grid.mx[0] + r &&
                    cl[1] >= pd.grid.mn[1] - r && cl[1] <= pd.grid.mx[1] + r &&
                    cl[2] >= pd.grid.mn[2] - r && cl[2] <= pd.grid.mx[2] + r;
+            if (!keep) mask_row[pd.word_offset + w] = 0u;  // culled words: empty mask
         }
-        live = __ballot_sync(0xffffffffu, keep);
+        const unsigned live = __ballot_sync(0xffffffffu, keep);
+        // kDetectTileWords == 64: warps 0 and 1 hold the two ballots
+        if (lane == 0) s_nlive[warp] = __popc(live);
+        __syncwarp();
+        s_live[32 * warp + lane] = keep ? (__popc(live & ((1u << lane) - 1u))) : -1;  // rank inside this warp's ballot
     }
-    if (lane < kDetectWordsPerWarp && wbase + lane < pd.n_words && !((live >> lane) & 1u))
-        mask_row[pd.word_offset + wbase + lane] = 0u;  // culled words: empty mask
-    // surviving words, U at a time
-    while (live) {
+    __syncthreads();
+    const int n0 = s_nlive[0], nlive = n0 + s_nlive[1];
+    // rank -> word: scatter into a dense list (second half of s_live)
+    int* list = s_live + kDetectTileWords;
+    if (threadIdx.x < kDetectTileWords) {
+        const int rk = s_live[threadIdx.x];
+        if (rk >= 0) list[rk + (threadIdx.x >= 32 ? n0 : 0)] = word0 + threadIdx.x;
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int k = warp * U; k < nlive; k += (kDetectThreads / 32) * U) {
         int ws[U];
         double px[U], py[U], pz[U];
         bool inr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            ws[u] = -1;
-            if (live) { ws[u] = wbase + (__ffs(live) - 1); live &= live - 1; }
+            ws[u] = (k + u < nlive) ? list[k + u] : -1;
             const int idx = ws[u] * 32 + lane;
             inr[u] = (ws[u] >= 0) && (idx < pd.n);
             px[u] = inr[u] ? __ldg(pd.sx + idx) : 0.0;
@@ -104,10 +118,16 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     if (lane == 0 && cnt) atomicAdd(s_count, cnt);
 }
 
-__global__ void __launch_bounds__(kDetectThreads) k_detect_mask(BatchDev B, const double* __restrict__ E) {
+#ifndef SDFC_DETECT_MIN_BLOCKS
+#define SDFC_DETECT_MIN_BLOCKS 6  // 40 registers: the kernel is latency-bound on the cell gathers, occupancy wins
+#endif
+__global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_detect_mask(BatchDev B, const double* __restrict__ E) {
     __shared__ PairDev pd;
     __shared__ double R1[9], p1[3], R2[9], p2[3];
     __shared__ int s_count;
+    __shared__ int s_live[2 * kDetectTileWords];
+    __shared__ int s_nlive[kDetectThreads / 32];
+    static_assert(kDetectTileWords == 64, "the broad phase compaction assumes two ballots per tile");
     const int tile = blockIdx.x, env = blockIdx.y;
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;  // CTA-uniform
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
@@ -122,8 +142,8 @@ __global__ void __launch_bounds__(kDetectThreads) k_detect_mask(BatchDev B, cons
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
     __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
-    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
-    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, &s_count);
+    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count);
+    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
 }

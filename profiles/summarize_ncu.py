@@ -48,6 +48,14 @@ def main():
         for w in WANT:
             if w in idx:
                 print(f"| {w} | {units[idx[w]]} | {r[idx[w]]} |")
+        # every other warp-stall reason that matters (> 0.3 warps per issue)
+        for h in hdr:
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and h not in WANT:
+                try:
+                    if float(r[idx[h]]) > 0.3:
+                        print(f"| {h} | {units[idx[h]]} | {r[idx[h]]} |")
+                except ValueError:
+                    pass
         print()
 
 
