@@ -39,6 +39,13 @@ SIGNATURES = {
     "sdfc_sdf_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
     "sdfc_sdf_min_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
     "sdfc_sdf_distance_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdfc_make_level_set3": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                       C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sdfc_sdf_layout": (C.c_int, [C.c_int, c_double_p, C.c_double, C.c_int, c_double_p, C.c_void_p, C.c_void_p, c_int32_p]),
+    "sdfc_sdf_save_text": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double,
+                                     C.c_double, c_double_p]),
+    "sdfc_sdf_load_text_header": (C.c_int, [C.c_char_p, c_int32_p]),
+    "sdfc_sdf_load_text": (C.c_int, [C.c_char_p, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64]),
     "sdfc_points_create": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_void_pp]),
     "sdfc_points_count": (C.c_int, [C.c_void_p]),
     "sdfc_points_destroy": (C.c_int, [C.c_void_p]),

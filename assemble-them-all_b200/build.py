@@ -18,7 +18,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("SDFC_OUT") or os.path.join(HERE, "libsdfcontact_b200.so")
-SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu", "sdfc_ground.cu"]
+SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu", "sdfc_ground.cu", "sdfc_sdfgen.cu"]
+# sdfgen's fp32 / fp64 arithmetic has to match the reference's x86-64 build bit for bit: no FMA contraction
+PER_SOURCE_FLAGS = {"sdfc_sdfgen.cu": ["-fmad=false"]}
 FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7
 HEADERS = ["sdfc_device.cuh", "sdfc_kernels.cuh", "sdfc_force.cuh", "sdfc_host.h", FORCE_INST,
            os.path.join("..", "..", "include", "sdfcontact_b200.h")]
@@ -60,7 +62,8 @@ def build(force=False, verbose=False):
     nf_blocks = os.environ.get("SDFC_FORCE_NF_MIN_BLOCKS")  # same knob for the planner fast path (k_force<1,0,0>)
     if nf_blocks:
         extra_all.append(f"-DSDFC_FORCE_NF_MIN_BLOCKS={int(nf_blocks)}")
-    jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"), list(extra_all)) for s in srcs]
+    jobs = [(s, os.path.join(objdir, os.path.basename(s) + ".o"),
+             list(extra_all) + PER_SOURCE_FLAGS.get(os.path.basename(s), [])) for s in srcs]
     jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"),
               [f"-DSDFC_FORCE_VARIANT={v}", *extra_all]) for v in range(8)]
     for s, o, extra in jobs:

@@ -165,6 +165,64 @@ class SdfGrid:
             self._h = C.c_void_p()
 
 
+def make_level_set3(ctx, tri, x, origin, dx, dy, dz, ni, nj, nk, exact_band=1):
+    """sdfgen::make_level_set3 on the GPU -> phi (ni*nj*nk,) float32, x fastest."""
+    tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+    origin = np.ascontiguousarray(origin, dtype=np.float32)
+    phi = np.empty(int(ni) * int(nj) * int(nk), dtype=np.float32)
+    check(ctx._lib.sdfc_make_level_set3(ctx._h, len(tri), tri.ctypes.data, len(x), x.ctypes.data, origin.ctypes.data,
+                                        np.float32(dx), np.float32(dy), np.float32(dz), int(ni), int(nj), int(nk),
+                                        int(exact_band), phi.ctypes.data))
+    return phi
+
+
+def sdf_layout(V, dx, res=20):
+    """BodySDFObj::precompute_SDF's grid layout -> dict(spacing (3,) f64, min_box, max_box (3,) f32, dims (3,) i32)."""
+    lib = _lib.load()
+    V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1, 3)
+    spacing = np.empty(3)
+    mn, mx = np.empty(3, dtype=np.float32), np.empty(3, dtype=np.float32)
+    dims = np.empty(3, dtype=np.int32)
+    check(lib.sdfc_sdf_layout(len(V), _dp(V), float(dx), int(res), _dp(spacing), mn.ctypes.data, mx.ctypes.data,
+                              dims.ctypes.data_as(_lib.c_int32_p)))
+    return {"spacing": spacing, "min_box": mn, "max_box": mx, "dims": dims}
+
+
+def precompute_sdf(ctx, V, F, dx, col_th=0.0, res=20):
+    """BodySDFObj::precompute_SDF (BodySDFObj.cpp:38-84) on the GPU: body-frame vertices V (n,3)
+    fp64 and faces F (m,3) -> grid dict in the layout of SdfGrid.from_dict (fp64 values that are
+    exactly the fp32 sdfgen output widened, as the reference stores them)."""
+    lay = sdf_layout(V, dx, res)
+    ni, nj, nk = (int(v) for v in lay["dims"])
+    sp = lay["spacing"]
+    phi = make_level_set3(ctx, F, np.asarray(V, dtype=np.float64).astype(np.float32), lay["min_box"], np.float32(sp[0]),
+                          np.float32(sp[1]), np.float32(sp[2]), ni, nj, nk)
+    return {"ni": ni, "nj": nj, "nk": nk, "min_box": lay["min_box"].astype(np.float64),
+            "max_box": lay["max_box"].astype(np.float64), "dx": float(sp[0]), "dy": float(sp[1]), "dz": float(sp[2]),
+            "col_th": float(col_th), "grid": phi.astype(np.float64)}
+
+
+def save_sdf_text(path, g):
+    """BodySDFObj::save_SDF: the `.sdf` cache next to the OBJ (6 significant digits)."""
+    lib = _lib.load()
+    grid = _f64(g["grid"]).reshape(-1)
+    check(lib.sdfc_sdf_save_text(str(path).encode(), int(g["ni"]), int(g["nj"]), int(g["nk"]), _dp(_f64(g["min_box"])),
+                                 _dp(_f64(g["max_box"])), float(g["dx"]), float(g["dy"]), float(g["dz"]), _dp(grid)))
+
+
+def load_sdf_text(path, col_th=0.0):
+    """BodySDFObj::load_SDF -> grid dict."""
+    lib = _lib.load()
+    dims = np.empty(3, dtype=np.int32)
+    check(lib.sdfc_sdf_load_text_header(str(path).encode(), dims.ctypes.data_as(_lib.c_int32_p)))
+    n = int(dims[0]) * int(dims[1]) * int(dims[2])
+    mn, mx, sp, grid = np.empty(3), np.empty(3), np.empty(3), np.empty(n)
+    check(lib.sdfc_sdf_load_text(str(path).encode(), _dp(mn), _dp(mx), _dp(sp), _dp(grid), n))
+    return {"ni": int(dims[0]), "nj": int(dims[1]), "nk": int(dims[2]), "min_box": mn, "max_box": mx, "dx": float(sp[0]),
+            "dy": float(sp[1]), "dz": float(sp[2]), "col_th": float(col_th), "grid": grid}
+
+
 class ContactPoints:
     def __init__(self, ctx, xyz, morton_sort=True):
         self.ctx = ctx

@@ -107,6 +107,31 @@ SDFC_API sdfc_status sdfc_sdf_min_distance(sdfc_sdf* sdf, int64_t n, const doubl
 SDFC_API sdfc_status sdfc_sdf_distance_device(sdfc_sdf* sdf, int64_t n, const double* dx, const double* dy,
                                               const double* dz, double* dout);
 
+/* ---- SDF construction: sdfgen::make_level_set3 + BodySDFObj::precompute_SDF ---- */
+/* Drop-in for sdfgen::make_level_set3 (externals/sdfgen/makelevelset3.h:15-17, .cpp:164-226)
+ * as called by BodySDFObj::precompute_SDF (Body/BodySDFObj.cpp:75) and SDFMesh
+ * (Mesh.cpp:54-100). tri: [n_tri][3] vertex indices; x: [n_vert][3] fp32 vertices;
+ * phi_out: ni*nj*nk fp32, x fastest (Array3f). The result is bit-identical to the CPU
+ * routine (exact band, 2 x 8 sweeps in the reference's dependency order, parity signs).
+ * Host buffers in and out. */
+SDFC_API sdfc_status sdfc_make_level_set3(sdfc_context* ctx, int n_tri, const uint32_t* tri, int n_vert, const float* x,
+                                          const float origin[3], float dx, float dy, float dz, int ni, int nj, int nk,
+                                          int exact_band, float* phi_out);
+/* Grid layout of BodySDFObj::precompute_SDF (BodySDFObj.cpp:41-70): V = body-frame
+ * vertices [n_vert][3] fp64, dx = requested spacing, res = min cells per axis (20,
+ * Simulation_Constructor.cpp:568). Outputs: spacing[3] = min(dx, bbox/res) per axis,
+ * fp32 min_box / max_box with one cell of padding, dims[3]. Host only. */
+SDFC_API sdfc_status sdfc_sdf_layout(int n_vert, const double* V, double dx, int res, double spacing[3], float min_box[3],
+                                     float max_box[3], int32_t dims[3]);
+/* The `.sdf` text cache of BodySDFObj::save_SDF / load_SDF (BodySDFObj.cpp:86-116): same
+ * token order and the same 6-significant-digit formatting (so a reloaded grid is NOT
+ * fp32-lossless and stays fp64 in sdfc_sdf_create). Host only. */
+SDFC_API sdfc_status sdfc_sdf_save_text(const char* path, int ni, int nj, int nk, const double min_box[3],
+                                        const double max_box[3], double dx, double dy, double dz, const double* grid);
+SDFC_API sdfc_status sdfc_sdf_load_text_header(const char* path, int32_t dims[3]);
+SDFC_API sdfc_status sdfc_sdf_load_text(const char* path, double min_box[3], double max_box[3], double spacing[3],
+                                        double* grid, int64_t capacity);
+
 /* ---- contact points: Body::_contact_points (Body/Body.h:36,129) -------- */
 /* morton_sort != 0 stores a spatially sorted SoA copy for the force path (the
  * original order is kept for every per-point output). */

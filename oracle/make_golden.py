@@ -269,9 +269,42 @@ def make_freefall_small(steps=400):
     return path
 
 
+def make_sdfgen_small():
+    """Grids of the reference's own sdfgen::make_level_set3 (called directly) and of a constructed
+    BodySDFObj, for a convex part and a concave block with an internal L-shaped channel."""
+    from oracle import ref_scene
+    out = {}
+    parts = synth.l_channel(h=0.3)
+    p = ref_scene.probe_from_assembly(parts, "0", ["1"], "translational", sdf_dx=0.15)
+    names = p.body_names()
+    out["names"] = np.array(names)
+    out["dx_request"] = np.array(float(np.float32(0.15)))   # the XML scalar goes through float (Simulation_Constructor.cpp:566)
+    for n in names:
+        V = np.array(p.get_body_vertices(n)).T.copy()
+        F = np.array(p.get_body_faces(n)).T.copy().astype(np.uint32)
+        g = p.sdf_grid(n)
+        out[f"{n}_V"] = V
+        out[f"{n}_F"] = F
+        out[f"{n}_dims"] = np.array([g["ni"], g["nj"], g["nk"]], dtype=np.int32)
+        out[f"{n}_min_box"] = np.asarray(g["min_box"])
+        out[f"{n}_max_box"] = np.asarray(g["max_box"])
+        out[f"{n}_spacing"] = np.array([g["dx"], g["dy"], g["dz"]])
+        grid = np.asarray(g["grid"])
+        assert np.array_equal(grid.astype(np.float32).astype(np.float64), grid)
+        out[f"{n}_grid_f32"] = grid.astype(np.float32)            # BodySDFObj::precompute_SDF, exact_band = 1
+        sp = np.array([g["dx"], g["dy"], g["dz"]]).astype(np.float32)
+        phi2 = ref_probe.make_level_set3(F, V.astype(np.float32), np.asarray(g["min_box"]).astype(np.float32), sp[0], sp[1],
+                                         sp[2], g["ni"], g["nj"], g["nk"], 2)
+        out[f"{n}_grid_band2_f32"] = np.asarray(phi2)
+    path = os.path.join(GOLDEN, "sdfgen_small.npz")
+    np.savez_compressed(path, **out)
+    return path
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    fns = {"contact": make_contact_small, "traj": make_traj_small, "freefall": make_freefall_small}
+    fns = {"contact": make_contact_small, "traj": make_traj_small, "freefall": make_freefall_small,
+           "sdfgen": make_sdfgen_small}
     sel = [a for a in sys.argv[1:] if a in fns] or list(fns)
     for fn in (fns[k] for k in sel):
         path = fn()

@@ -441,6 +441,7 @@ struct Probe {
     void zero_joint_qdot(const std::string& name) { sim->zero_joint_qdot(name); }
     Matrix4 get_body_E0i(const std::string& name) { return sim->get_body_E0i(name); }
     Matrix3X get_body_vertices(const std::string& name, bool world_frame) { return sim->get_body_vertices(name, world_frame); }
+    Eigen::Matrix<int, 3, Eigen::Dynamic> get_body_faces(const std::string& name) { return sim->get_body_faces(name); }
 
     void reset_time_report() { sim->_robot->reset_time_report(); }
 
@@ -466,8 +467,26 @@ struct Probe {
 
 }  // namespace
 
+// sdfgen::make_level_set3 of the reference, called directly (externals/sdfgen/makelevelset3.cpp)
+static py::array_t<float> ref_make_level_set3(const Eigen::Matrix<unsigned, Eigen::Dynamic, 3, Eigen::RowMajor>& tri,
+                                              const Eigen::Matrix<float, Eigen::Dynamic, 3, Eigen::RowMajor>& x,
+                                              const Eigen::Vector3f& origin, float dx, float dy, float dz, int ni, int nj,
+                                              int nk, int exact_band) {
+    std::vector<sdfgen::Vec3ui> faces;
+    std::vector<sdfgen::Vec3f> verts;
+    for (int i = 0; i < tri.rows(); ++i) faces.push_back(sdfgen::Vec3ui(tri(i, 0), tri(i, 1), tri(i, 2)));
+    for (int i = 0; i < x.rows(); ++i) verts.push_back(sdfgen::Vec3f(x(i, 0), x(i, 1), x(i, 2)));
+    sdfgen::Array3f phi;
+    sdfgen::make_level_set3(faces, verts, sdfgen::Vec3f(origin[0], origin[1], origin[2]), dx, dy, dz, ni, nj, nk, phi, exact_band);
+    py::array_t<float> out((size_t)ni * nj * nk);
+    std::memcpy(out.mutable_data(), &phi.a[0], sizeof(float) * (size_t)ni * nj * nk);
+    return out;
+}
+
 PYBIND11_MODULE(ref_probe, m) {
     m.doc() = "probe harness over the unmodified reference RedMax objects (test infrastructure)";
+    m.def("make_level_set3", &ref_make_level_set3, py::arg("tri"), py::arg("x"), py::arg("origin"), py::arg("dx"),
+          py::arg("dy"), py::arg("dz"), py::arg("ni"), py::arg("nj"), py::arg("nk"), py::arg("exact_band") = 1);
     py::class_<Probe>(m, "Probe")
         .def(py::init<const std::string&, const std::string&>(), py::arg("xml"), py::arg("asset_folder"))
         .def("num_forces", &Probe::num_forces)
@@ -524,6 +543,7 @@ PYBIND11_MODULE(ref_probe, m) {
         .def("zero_joint_qdot", &Probe::zero_joint_qdot)
         .def("get_body_E0i", &Probe::get_body_E0i)
         .def("get_body_vertices", &Probe::get_body_vertices, py::arg("name"), py::arg("world_frame") = false)
+        .def("get_body_faces", &Probe::get_body_faces)
         .def("reset_time_report", &Probe::reset_time_report)
         .def("time_force_evals", &Probe::time_force_evals, py::arg("reps"), py::arg("deriv"),
              py::call_guard<py::gil_scoped_release>());
