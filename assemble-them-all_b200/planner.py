@@ -331,3 +331,109 @@ class BatchedBFSPlanner:
                 if max_depth is not None and stages == max_depth:
                     return PlanResult("Failure", None, [], stages, consumed, self.rollouts_run, self.env_steps,
                                       self.forward_calls)
+
+
+# ------------------------------------------------------------------ sequence planning
+SUCCESS_STATUS = ("Success", "Start with goal")   # run_multi_plan.py:36-38
+FAILURE_STATUS = ("Timeout", "Failure")
+
+
+@dataclass
+class SequenceResult:
+    status: str                 # "Success" | "Failure"
+    sequence: list              # part ids in removal order
+    trials: int                 # seq_count
+    log: list = field(default_factory=list)   # (move_id, max_depth, rotation tried, status) per trial
+
+
+class SequencePlanner:
+    """The sequence planners of examples/run_multi_plan.py on top of a path-planner factory.
+
+    plan_path(move_id, still_ids, rotation, max_depth) -> status string; with the batched BFS
+    planner every call is one stage-parallel plan on the device. The trial order reproduces
+    the reference's use of numpy's legacy global RNG (seed, shuffle / choice, one randint per
+    trial), so a given seed visits the candidate parts in the same order.
+    variant: "random" (:69-133), "queue" (:136-225), "prog-queue" (:228-330)."""
+
+    def __init__(self, part_ids, plan_path):
+        self.part_ids = [str(p) for p in part_ids]
+        assert len(self.part_ids) > 1
+        self.plan_path = plan_path
+        n = len(self.part_ids)
+        self.max_seq_count = (1 + n) * n // 2 - 1
+
+    def _attempt(self, move_id, nodes, rotation, max_depth, log):
+        still = [p for p in nodes if p != move_id]
+        status = self.plan_path(move_id, still, False, max_depth)
+        tried_rot = False
+        if status in FAILURE_STATUS and rotation:
+            status = self.plan_path(move_id, still, True, max_depth)
+            tried_rot = True
+        log.append((move_id, max_depth, tried_rot, status))
+        return status
+
+    def plan_sequence(self, variant="prog-queue", rotation=False, seed=1, max_trials=None):
+        np.random.seed(seed)
+        nodes = list(self.part_ids)
+        sequence, log = [], []
+        seq_count = 0
+        status = "Failure"
+        if variant == "random":
+            while seq_count < self.max_seq_count:
+                move_id = str(np.random.choice(nodes))
+                np.random.randint(self.max_seq_count)      # curr_seed
+                st = self._attempt(move_id, nodes, rotation, None, log)
+                seq_count += 1
+                if st in SUCCESS_STATUS:
+                    nodes.remove(move_id)
+                    sequence.append(move_id)
+                if len(nodes) == 1:
+                    status = "Success"
+                    break
+            return SequenceResult(status, sequence, seq_count, log)
+        if variant == "queue":
+            active = list(nodes)
+            np.random.shuffle(active)
+            last_active, inactive = list(active), []
+            while seq_count < self.max_seq_count:
+                move_id = active.pop(0)
+                np.random.randint(self.max_seq_count)
+                st = self._attempt(move_id, nodes, rotation, None, log)
+                seq_count += 1
+                if st in SUCCESS_STATUS:
+                    nodes.remove(move_id)
+                    sequence.append(move_id)
+                else:
+                    inactive.append(move_id)
+                if len(nodes) == 1:
+                    status = "Success"
+                    break
+                if len(active) == 0:
+                    active, inactive = list(inactive), []
+                    if active == last_active:
+                        break
+                    last_active = list(active)
+            return SequenceResult(status, sequence, seq_count, log)
+        if variant != "prog-queue":
+            raise ValueError(f"unknown sequence planner {variant}")
+        active = [(p, 1) for p in nodes]
+        np.random.shuffle(active)
+        inactive = []
+        while True:
+            move_id, max_depth = active.pop(0)
+            np.random.randint(self.max_seq_count)
+            st = self._attempt(move_id, nodes, rotation, max_depth, log)
+            seq_count += 1
+            if st in SUCCESS_STATUS:
+                nodes.remove(move_id)
+                sequence.append(move_id)
+            else:
+                inactive.append((move_id, max_depth + 1))
+            if len(nodes) == 1:
+                status = "Success"
+                break
+            if len(active) == 0:
+                active, inactive = list(inactive), []
+            if max_trials is not None and seq_count >= max_trials:   # stands in for seq_max_time (:321-323)
+                break
+        return SequenceResult(status, sequence, seq_count, log)

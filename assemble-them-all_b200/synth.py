@@ -189,6 +189,16 @@ def l_channel(h=0.25, clearance=0.1):
     return {"0": (Vc, Fc), "1": (Vb, Fb)}
 
 
+def l_channel_with_plug(h=0.25, clearance=0.1):
+    """Three-part sequence-planning scene: the L-channel block (part 1) and cube (part 0) of
+    l_channel() plus a plug (part 2) sitting in the vertical shaft. The cube can only leave
+    after the plug has been pulled out (+z)."""
+    parts = l_channel(h, clearance)
+    Vp, Fp = box_mesh((1.0, 1.0, 1.0), (1.5, 0.0, 1.4), h)
+    parts["2"] = (Vp, Fp)
+    return parts
+
+
 def reorient(parts, R):
     """The same assembly with every vertex rotated by R (3x3)."""
     R = np.asarray(R, dtype=np.float64)

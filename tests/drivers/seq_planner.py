@@ -169,3 +169,42 @@ class RefSimPool:
 
     def get_body_E0i(self):
         return np.array([[np.array(s.get_body_E0i(n)) for n in self.body_names] for s in self.sims])
+
+
+def reference_prog_queue(part_ids, plan_path, rotation, seed, max_trials=None):
+    """ProgressiveQueueSequencePlanner.plan_sequence (examples/run_multi_plan.py:252-330) walked
+    literally; plan_path(move_id, still_ids, rotation, max_depth) -> status."""
+    n = len(part_ids)
+    max_seq_count = (1 + n) * n // 2 - 1
+    np.random.seed(seed)
+    nodes = list(part_ids)
+    seq_status, sequence, seq_count = "Failure", [], 0
+    active_queue = [(node, 1) for node in nodes]
+    np.random.shuffle(active_queue)
+    inactive_queue = []
+    trace = []
+    while True:
+        all_ids = list(nodes)
+        move_id, max_depth = active_queue.pop(0)
+        still_ids = all_ids.copy()
+        still_ids.remove(move_id)
+        np.random.randint(max_seq_count)
+        status = plan_path(move_id, still_ids, False, max_depth)
+        if status in ("Timeout", "Failure") and rotation:
+            status = plan_path(move_id, still_ids, True, max_depth)
+        seq_count += 1
+        trace.append((move_id, max_depth, status))
+        if status in ("Success", "Start with goal"):
+            nodes.remove(move_id)
+            sequence.append(move_id)
+        else:
+            inactive_queue.append([move_id, max_depth + 1])
+        if len(nodes) == 1:
+            seq_status = "Success"
+            break
+        if len(active_queue) == 0:
+            active_queue = inactive_queue.copy()
+            inactive_queue = []
+        if max_trials is not None and seq_count >= max_trials:
+            break
+    return seq_status, sequence, seq_count, trace

@@ -150,3 +150,76 @@ def test_batched_bfs_rotational_level():
     r = bp.plan(max_depth=1)
     assert (r.status, r.actions, r.stages, r.rollouts) == (st, acts, stages, seq.rollouts)
     assert st == "Failure" and r.rollouts == 12
+
+
+# ---------------------------------------------------------------- sequence planning
+def _seq_setup(n_envs_factory):
+    """Three-part scene; returns plan_path callables for the sequential and the batched arm."""
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    # tunnel along +z, shaft along +y: the cube's plan is [+z, +y] = the first child of the root,
+    # so max_depth 2 (node expansions, run_joint_plan.py:574-576) reaches it
+    parts = synth.reorient(synth.l_channel_with_plug(), np.array([[0.0, 1, 0], [0, 0, 1], [1, 0, 0]]))
+    cache = {}
+
+    def scene(move_id, still_ids):
+        key = (move_id, tuple(still_ids))
+        if key not in cache:
+            sub = {k: parts[k] for k in [move_id, *still_ids]}
+            make = lambda: ref_scene.probe_from_assembly(sub, move_id, list(still_ids), "translational", sdf_dx=0.1)  # noqa: E731
+            p = make()
+            names = [f"part{i}" for i in [move_id, *still_ids]]
+            still_v = np.vstack([np.array(p.get_body_vertices(n, True)).T for n in names[1:]])
+            hulls = PL.HullPair(np.array(p.get_body_vertices(names[0])).T, still_v)
+            cache[key] = (make, p, hulls, names)
+        return cache[key]
+
+    def plan_seq(move_id, still_ids, rotation, max_depth):
+        _, p, hulls, names = scene(move_id, still_ids)
+        return SP.SequentialBFSPlanner(p, names[0], hulls).plan(PL.TRANS_ACTIONS, max_depth=max_depth)[0]
+
+    def plan_batched(move_id, still_ids, rotation, max_depth):
+        make, _, hulls, names = scene(move_id, still_ids)
+        sim = n_envs_factory(make, names)
+        return PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=max_depth).status
+
+    return plan_seq, plan_batched
+
+
+def test_sequence_planner_matches_reference_loop():
+    plan_seq, plan_batched = _seq_setup(lambda make, names: SP.RefSimPool(make, 6, names[0], 3, names))
+    for seed in (1, 2):
+        st, seq, count, trace = SP.reference_prog_queue(["0", "1", "2"], plan_seq, False, seed, max_trials=12)
+        r = PL.SequencePlanner(["0", "1", "2"], plan_batched).plan_sequence("prog-queue", False, seed, max_trials=12)
+        assert (r.status, r.sequence, r.trials) == (st, seq, count)
+        assert [(m, d, s) for m, d, _, s in r.log] == trace
+        assert st == "Success" and seq.index("2") < seq.index("0")   # the plug leaves before the cube
+        assert any(s == "Failure" for _, _, s in trace)
+        assert ("0", 2, "Success") in trace                          # the cube needs the deeper search
+
+
+def test_sequence_planner_variants_consume_rng_like_the_reference():
+    """queue / random variants with a scripted path planner: same trial order as a literal walk."""
+    outcomes = {"a": ["Failure", "Success"], "b": ["Success"], "c": ["Failure", "Failure", "Success"]}
+
+    def scripted():
+        seen = {k: 0 for k in outcomes}
+
+        def plan(move_id, still_ids, rotation, max_depth):
+            i = min(seen[move_id], len(outcomes[move_id]) - 1)
+            seen[move_id] += 1
+            return outcomes[move_id][i]
+        return plan
+
+    for seed in (0, 3):
+        r = PL.SequencePlanner(["a", "b", "c"], scripted()).plan_sequence("queue", False, seed)
+        np.random.seed(seed)
+        q = ["a", "b", "c"]
+        np.random.shuffle(q)
+        assert [m for m, *_ in r.log][:3] == q
+        assert r.status == "Success" and len(r.sequence) == 2
+        r2 = PL.SequencePlanner(["a", "b", "c"], scripted()).plan_sequence("random", False, seed)
+        np.random.seed(seed)
+        first = str(np.random.choice(["a", "b", "c"]))
+        assert r2.log[0][0] == first

@@ -90,3 +90,44 @@ def test_inactive_environments_keep_their_state(cuda_ctx):
     sim.forward(1)
     assert sim.stats()["env_steps"] == 24
     sim.close()
+
+
+def test_sequence_plan_matches_reference(cuda_ctx):
+    """C4-style sequence planning (ProgressiveQueueSequencePlanner, run_multi_plan.py:228-330) on a
+    three-part assembly: every candidate removal is one batched BFS plan on the CUDA stepper; trial
+    order, per-trial status and the final removal sequence must equal the reference loop's."""
+    from assemble_them_all_b200 import contact
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    parts = synth.reorient(synth.l_channel_with_plug(), np.array([[0.0, 1, 0], [0, 0, 1], [1, 0, 0]]))
+    cache = {}
+
+    def scene(move_id, still_ids):
+        key = (move_id, tuple(still_ids))
+        if key not in cache:
+            sub = {k: parts[k] for k in [move_id, *still_ids]}
+            p = ref_scene.probe_from_assembly(sub, move_id, list(still_ids), "translational", sdf_dx=0.1)
+            names = [f"part{i}" for i in [move_id, *still_ids]]
+            still_v = np.vstack([np.array(p.get_body_vertices(n, True)).T for n in names[1:]])
+            hulls = PL.HullPair(np.array(p.get_body_vertices(names[0])).T, still_v)
+            cache[key] = (p, hulls, names)
+        return cache[key]
+
+    def plan_ref(move_id, still_ids, rotation, max_depth):
+        p, hulls, names = scene(move_id, still_ids)
+        return SP.SequentialBFSPlanner(p, names[0], hulls).plan(PL.TRANS_ACTIONS, max_depth=max_depth)[0]
+
+    def plan_cuda(move_id, still_ids, rotation, max_depth):
+        p, hulls, names = scene(move_id, still_ids)
+        sim = contact.build_simulation(cuda_ctx, ref_scene.extract_scene(p), 12)
+        try:
+            return PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=max_depth).status
+        finally:
+            sim.close()
+
+    st, seq, count, trace = SP.reference_prog_queue(["0", "1", "2"], plan_ref, False, 1, max_trials=12)
+    r = PL.SequencePlanner(["0", "1", "2"], plan_cuda).plan_sequence("prog-queue", False, 1, max_trials=12)
+    assert (r.status, r.sequence, r.trials) == (st, seq, count)
+    assert [(m, d, s) for m, d, _, s in r.log] == trace
+    assert st == "Success" and seq == ["2", "0"]
