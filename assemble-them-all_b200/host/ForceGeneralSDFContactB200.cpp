@@ -9,36 +9,29 @@
 #include "Robot.h"
 #include "Simulation.h"
 
-#include "sdfcontact_b200.h"
+#include "B200DeviceCache.h"
 
-#include <cstdlib>
-#include <map>
+#include <vector>
 
 namespace redmax {
 
-namespace {
+using b200::cache;
+using b200::check;
+using b200::DeviceCache;
 
-void check(sdfc_status st, const char* what) {
-    if (st != SDFC_OK) throw_error(std::string(what) + ": " + sdfc_last_error());
-}
-
-// one device context per process (device from SDFC_DEVICE, default 0); geometry is
-// shared between the forces that use the same body
-struct DeviceCache {
-    sdfc_context* ctx = nullptr;
-    std::map<const BodySDFObj*, sdfc_sdf*> sdf;
-    std::map<const Body*, sdfc_points*> pts;
-};
-DeviceCache& cache() {
-    static DeviceCache c;
-    if (c.ctx == nullptr) {
-        const char* dev = std::getenv("SDFC_DEVICE");
-        check(sdfc_context_create(dev ? std::atoi(dev) : 0, &c.ctx), "ForceGeneralSDFContactB200: no CUDA device");
+sdfc_points* b200::contact_points_of(Body* body) {
+    DeviceCache& c = cache();
+    auto ip = c.pts.find(body);
+    if (ip == c.pts.end()) {
+        std::vector<Vector3> cp = body->get_contact_points();  // Body.h:129
+        std::vector<double> xyz(3 * cp.size());
+        for (size_t i = 0; i < cp.size(); ++i) { xyz[3 * i] = cp[i](0); xyz[3 * i + 1] = cp[i](1); xyz[3 * i + 2] = cp[i](2); }
+        sdfc_points* p = nullptr;
+        check(sdfc_points_create(c.ctx, (int)cp.size(), xyz.data(), /*morton_sort=*/1, &p), "B200 contact path: contact point upload");
+        ip = c.pts.emplace(body, p).first;
     }
-    return c;
+    return ip->second;
 }
-
-}  // namespace
 
 ForceGeneralSDFContactB200::ForceGeneralSDFContactB200(Simulation* sim, Body* contact_body, Body* SDF_body, dtype kn,
                                                        dtype kt, dtype mu, dtype damping)
@@ -61,17 +54,7 @@ void ForceGeneralSDFContactB200::ensure_uploaded() {
         is = c.sdf.emplace(_SDF_body, s).first;
     }
     _sdf = is->second;
-    auto ip = c.pts.find(_contact_body);
-    if (ip == c.pts.end()) {
-        std::vector<Vector3> cp = _contact_body->get_contact_points();  // Body.h:129
-        std::vector<double> xyz(3 * cp.size());
-        for (size_t i = 0; i < cp.size(); ++i) { xyz[3 * i] = cp[i](0); xyz[3 * i + 1] = cp[i](1); xyz[3 * i + 2] = cp[i](2); }
-        sdfc_points* p = nullptr;
-        check(sdfc_points_create(_ctx, (int)cp.size(), xyz.data(), /*morton_sort=*/1, &p),
-              "ForceGeneralSDFContactB200: contact point upload");
-        ip = c.pts.emplace(_contact_body, p).first;
-    }
-    _pts = ip->second;
+    _pts = b200::contact_points_of(_contact_body);
     check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
     _synced = false;
 }

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--nverts", type=int, default=600)
     ap.add_argument("--dx", type=float, default=0.1)
     ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--scene", default="planner", choices=["planner", "freefall"])
     args = ap.parse_args()
     sys.path.insert(0, os.path.abspath(args.module_dir))
     import redmax_py as redmax
@@ -35,6 +36,8 @@ def main():
 
     tmp = tempfile.mkdtemp(prefix="rollout_asm_")
     synth.write_assembly(synth.peg_in_hole(n_vertices=args.nverts), tmp)
+    if args.scene == "freefall":
+        return freefall(redmax, synth, tmp, args)
     xml = synth.planner_xml(tmp, "0", ["1"], joint_type=args.joint, sdf_dx=args.dx)
     t0 = time.perf_counter()
     sim = redmax.Simulation(xml, tmp)
@@ -77,6 +80,40 @@ def main():
              t_build=t_build, n_env_steps=len(actions) * args.steps)
     print(f"{os.path.basename(os.path.abspath(args.module_dir))}: {len(actions) * args.steps} env-steps in {t_fwd:.3f} s "
           f"({len(actions) * args.steps / t_fwd:.1f} env-steps/s), build {t_build:.2f} s")
+
+
+def freefall(redmax, synth, tmp, args):
+    """examples/test_joint_sim.py: two free parts, ground plane, gravity 9.8; plus the SDFMesh
+    surface the planners use (python_interface.cpp:283-292). Exercises ForceGroundContact,
+    ForceGeneralSDFContact and both sdfgen call sites of the module under test."""
+    t0 = time.perf_counter()
+    sim = redmax.Simulation(synth.freefall_xml(tmp, sdf_dx=args.dx, gravity=9.8, friction=0), tmp)
+    t_build = time.perf_counter() - t0
+    sim.reset()
+    # start just above the plane so that the run covers free flight, impact and sliding
+    sim.set_joint_q("part0", np.array([0.0, 0.0, -2.6, 0.03, -0.02, 0.01]))
+    sim.set_joint_q("part1", np.array([0.0, 0.0, -2.9, 0.0, 0.0, 0.0]))
+    sim.update_robot()
+    Q = np.zeros((1, args.steps, 12))
+    QD = np.zeros_like(Q)
+    conv = np.zeros((1, args.steps), dtype=bool)
+    t_fwd = 0.0
+    for s in range(args.steps):
+        t0 = time.perf_counter()
+        sim.forward(1)
+        t_fwd += time.perf_counter() - t0
+        Q[0, s] = np.concatenate([sim.get_joint_q("part0"), sim.get_joint_q("part1")])
+        QD[0, s] = np.concatenate([sim.get_joint_qdot("part0"), sim.get_joint_qdot("part1")])
+        conv[0, s] = sim.is_converged()
+    touched = [",".join(sorted(sim.get_contact_bodies(n))) for n in ("part0", "part1")]
+    # SDFMesh: grid built by the module's own sdfgen call (Mesh.cpp:90), sampled on seeded points
+    V, F = synth.peg_in_hole(n_vertices=args.nverts)["1"]
+    mesh = redmax.SDFMesh(np.ascontiguousarray(V.T), np.ascontiguousarray(F.T.astype(np.int32)), args.dx)
+    X = np.random.default_rng(5).uniform(-3.2, 3.2, size=(3, 4000))
+    dist = np.asarray(mesh.distance(X))
+    np.savez(args.out, Q=Q, QD=QD, converged=conv, touched=np.array(touched), E_final=np.asarray(sim.get_body_E0i("part0")),
+             t_forward=t_fwd, t_build=t_build, n_env_steps=args.steps, sdfmesh_distance=dist)
+    print(f"{os.path.basename(os.path.abspath(args.module_dir))}: freefall {args.steps} steps in {t_fwd:.3f} s, build {t_build:.2f} s")
 
 
 if __name__ == "__main__":

@@ -25,9 +25,9 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 DRIVER = os.path.join(ROOT, "tests", "drivers", "redmax_rollout.py")
 
 
-def _run(module_dir, out, joint, nverts=600, dx=0.1, steps=100):
+def _run(module_dir, out, joint, nverts=600, dx=0.1, steps=100, scene="planner"):
     r = subprocess.run([sys.executable, DRIVER, module_dir, out, "--joint", joint, "--nverts", str(nverts), "--dx", str(dx),
-                        "--steps", str(steps)], capture_output=True, text=True, timeout=900)
+                        "--steps", str(steps), "--scene", scene], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     return np.load(out), r.stdout.strip()
 
@@ -49,6 +49,27 @@ def test_reference_simulation_with_b200_force_matches_stock(tmp_path, joint):
     assert np.array_equal(stock["converged"], b200["converged"])
     assert [str(t) for t in stock["touched"]] == [str(t) for t in b200["touched"]]
     assert any(str(t) == "part1" for t in stock["touched"])
+    assert rel_err(stock["E_final"], b200["E_final"]) <= 1e-9
+
+
+def test_reference_freefall_with_b200_ground_sdf_contact_and_sdfgen_matches_stock(tmp_path):
+    """test_joint_sim.py's configuration driven through the reference's own Simulation: in the b200
+    module ForceGroundContactB200, ForceGeneralSDFContactB200 and the GPU sdfgen (BodySDFObj and
+    SDFMesh call sites) replace the CPU code. Grids are bit-identical, so SDFMesh.distance is
+    compared bit for bit; the 300-step trajectory to 1e-9."""
+    if not (glob.glob(os.path.join(REF, "redmax_py*.so")) and glob.glob(os.path.join(REF, "b200", "redmax_py*.so"))):
+        pytest.skip("oracle/_ref (stock + b200 redmax_py) not built")
+    stock, msg_s = _run(REF, str(tmp_path / "stock.npz"), "free3d-exp", steps=300, scene="freefall")
+    b200, msg_b = _run(os.path.join(REF, "b200"), str(tmp_path / "b200.npz"), "free3d-exp", steps=300, scene="freefall")
+    print(msg_s)
+    print(msg_b)
+    assert np.array_equal(stock["sdfmesh_distance"], b200["sdfmesh_distance"])
+    h = float(np.float32(1e-3))
+    for s in range(stock["Q"].shape[1]):
+        assert_state_close(stock["Q"][0, s], stock["QD"][0, s], b200["Q"][0, s], b200["QD"][0, s], h, f"step {s}")
+    assert np.array_equal(stock["converged"], b200["converged"])
+    assert [str(t) for t in stock["touched"]] == [str(t) for t in b200["touched"]]
+    assert "ground" in str(stock["touched"][1])
     assert rel_err(stock["E_final"], b200["E_final"]) <= 1e-9
 
 
