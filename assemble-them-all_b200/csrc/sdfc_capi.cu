@@ -68,14 +68,32 @@ sdfc_status batch_refresh(sdfc_batch* b) {
 
 namespace sdfc_host {
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
-                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev) {
+                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev, int env0,
+                      int env_count) {
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
+    if (env_count < 0) { env0 = 0; env_count = b->n_envs; }
+    if (const char* dbg = std::getenv("SDFC_DEBUG_SPLIT_EVAL")) {  // debugging aid: evaluate a full-range call as two ranges
+        const int c0 = std::atoi(dbg);
+        if (!scatter || env0 != 0 || env_count != b->n_envs || c0 <= 0 || c0 >= b->n_envs) goto no_split;
+        st = batch_run(b, E_dev, phi_dev, deriv, env_mode_dev, false, nullptr, nullptr, nullptr, nullptr, 0, c0);
+        if (st != SDFC_OK) return st;
+        st = batch_run(b, E_dev, phi_dev, deriv, env_mode_dev, false, nullptr, nullptr, nullptr, nullptr, c0, b->n_envs - c0);
+        if (st != SDFC_OK) return st;
+        BatchDev dv = b->dev;
+        launch_scatter_system(dv, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, b->ctx->stream);
+        if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
+            SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
+                                      cudaMemcpyDeviceToDevice, b->ctx->stream));
+        return SDFC_OK;
+    }
+no_split:
     cudaStream_t s = b->ctx->stream;
     const bool dm = b->any_fric || b->any_damp;
     sdfc_context* c = b->ctx;
     BatchDev dev = b->dev;
     dev.env_mode = env_mode_dev;
+    dev.env0 = env0; dev.env_count = env_count;
     c->begin(0); launch_detect_mask(dev, E_dev, s); c->end();
     c->begin(1);
     if (env_mode_dev != nullptr) {
@@ -89,7 +107,7 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     c->begin(2); launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
     c->launches += 3;
     if (b->gset) {
-        st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, deriv, env_mode_dev);
+        st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, deriv, env_mode_dev, env0, env_count);
         if (st != SDFC_OK) return st;
     }
     if (scatter) {
@@ -628,6 +646,7 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     if (st != SDFC_OK) { sdfc_batch_destroy(b); return st; }
     b->dev.pairs = b->d_pairs;
     b->dev.n_pairs = n_pairs; b->dev.n_bodies = n_bodies; b->dev.n_envs = n_envs;
+    b->dev.env0 = 0; b->dev.env_count = n_envs;
     b->dev.words_per_env = std::max(words, 1);
     b->dev.tile_pair = b->d_tile_pair; b->dev.tile_word0 = b->d_tile_word0;
     b->dev.n_tiles = (int)tile_pair.size();

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
     ForceShared& S = *reinterpret_cast<ForceShared*>(smem_raw);
     double* red = reinterpret_cast<double*>(smem_raw + sizeof(ForceShared));  // [kNumWarps][NPART]
 
-    const int env = blockIdx.y;
+    const int env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) != (DERIV ? 2 : 1)) return;  // CTA-uniform
     const int pair = blockIdx.x / B.splits, split = blockIdx.x % B.splits;
     if (__ldg(B.n_active + (size_t)env * B.n_pairs + pair) == 0) return;  // CTA-uniform
@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
         for (int j = 0; j < kOutF; ++j) mine[j * 32 + lane] = sink.accF[j];
     }
     __syncthreads();
-    double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * NPART;
+    // fixed slot stride (the largest layout): value-only and derivative environments share the
+    // buffer within one evaluation round of the stepper, so the stride must not depend on the variant
+    double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * kPartialDerivDM;
     for (int i = tid; i < NPART; i += kForceThreads) {
         double s = red[i];
 #pragma unroll
@@ -302,7 +304,7 @@ void launch_force_t(const BatchDev& B, const double* E, const double* phi, cudaS
         cudaFuncSetAttribute(k_force<DERIV, ANYFRIC, ANYDAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    dim3 grid(B.n_pairs * B.splits, B.n_envs);
+    dim3 grid(B.n_pairs * B.splits, B.env_count);
     k_force<DERIV, ANYFRIC, ANYDAMP><<<grid, kForceThreads, smem, stream>>>(B, E, phi);
 }
 

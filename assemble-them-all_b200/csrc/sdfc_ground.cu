@@ -50,6 +50,7 @@ struct GroundBatchDev {
     int32_t* n_active;    // [n_envs][n_grounds]
     unsigned* ticket;     // [n_envs][n_grounds]
     const int* env_mode;  // see BatchDev::env_mode
+    int env0, env_count;  // see BatchDev::env0
 };
 
 __device__ __forceinline__ void cross(const double* a, const double* b, double* c) {
@@ -101,7 +102,7 @@ __device__ __forceinline__ void MG(const double* M, const double* xi, double* P)
 template <bool DERIV>
 __global__ void __launch_bounds__(kGroundThreads) k_ground(GroundBatchDev B, const double* __restrict__ E,
                                                            const double* __restrict__ phi) {
-    const int split = blockIdx.x, gi = blockIdx.y, env = blockIdx.z;
+    const int split = blockIdx.x, gi = blockIdx.y, env = blockIdx.z + B.env0;
     if (B.env_mode != nullptr) {
         const int m = __ldg(B.env_mode + env);
         if (m == 0 || (m == 2) != DERIV) return;  // CTA-uniform
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kGroundThreads) k_ground(GroundBatchDev B, con
 // out [env][ground][78] -> += into the per-environment system arrays (column-major)
 __global__ void k_ground_scatter(GroundBatchDev B, int deriv, double* __restrict__ fm, double* __restrict__ Km,
                                  double* __restrict__ Dm) {
-    const int env = blockIdx.x;
+    const int env = blockIdx.x + B.env0;
     const int nm = 6 * B.n_bodies;
     for (int gi = 0; gi < B.n_grounds; ++gi) {  // serial over grounds: two grounds may share a body
         const double* o = B.out + ((size_t)env * B.n_grounds + gi) * kGroundOut;
@@ -391,15 +392,16 @@ static sdfc_status ground_set_refresh(sdfc_ground_set* s) {
 
 // deriv / env_mode_dev as in batch_run. Results stay in the set's buffers.
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
-                           const int* env_mode_dev) {
+                           const int* env_mode_dev, int env0, int env_count) {
     sdfc_status st = ground_set_refresh(s);
     if (st != SDFC_OK) return st;
     cudaStream_t stream = s->ctx->stream;
     GroundBatchDev D = s->dev;
     D.env_mode = env_mode_dev;
-    const size_t eg = (size_t)s->n_envs * D.n_grounds;
-    SDFC_CUDA(cudaMemsetAsync(s->d_n_active, 0, sizeof(int32_t) * eg, stream));
-    dim3 grid(D.splits, D.n_grounds, s->n_envs);
+    if (env_count < 0) { env0 = 0; env_count = s->n_envs; }
+    D.env0 = env0; D.env_count = env_count;
+    SDFC_CUDA(cudaMemsetAsync(s->d_n_active + (size_t)env0 * D.n_grounds, 0, sizeof(int32_t) * (size_t)env_count * D.n_grounds, stream));
+    dim3 grid(D.splits, D.n_grounds, env_count);
     if (env_mode_dev != nullptr) {
         k_ground<false><<<grid, kGroundThreads, 0, stream>>>(D, E_dev, phi_dev);
         k_ground<true><<<grid, kGroundThreads, 0, stream>>>(D, E_dev, phi_dev);
@@ -414,7 +416,9 @@ sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double
 }
 
 sdfc_status ground_set_scatter(sdfc_ground_set* s, int deriv, double* fm_dev, double* Km_dev, double* Dm_dev) {
-    k_ground_scatter<<<s->n_envs, 96, 0, s->ctx->stream>>>(s->dev, deriv, fm_dev, Km_dev, Dm_dev);
+    GroundBatchDev D = s->dev;
+    D.env0 = 0; D.env_count = s->n_envs;
+    k_ground_scatter<<<s->n_envs, 96, 0, s->ctx->stream>>>(D, deriv, fm_dev, Km_dev, Dm_dev);
     s->ctx->launches += 1;
     SDFC_CUDA(cudaGetLastError());
     return SDFC_OK;
@@ -488,7 +492,7 @@ static sdfc_status ground_eval(sdfc_ground* g, const double E[16], const double 
     std::memcpy(in + 16, phi, 6 * sizeof(double));
     SDFC_CUDA(cudaMemcpyAsync(g->d_in, in, sizeof(in), cudaMemcpyHostToDevice, s));
     SDFC_CUDA(cudaStreamSynchronize(s));  // `in` is pageable stack memory
-    sdfc_status st = sdfc_host::ground_set_run(g->single, g->d_in, g->d_in + 16, deriv, nullptr);
+    sdfc_status st = sdfc_host::ground_set_run(g->single, g->d_in, g->d_in + 16, deriv, nullptr, 0, -1);
     if (st != SDFC_OK) return st;
     double out[kGroundOut];
     int32_t na = 0;

@@ -124,8 +124,10 @@ namespace sdfc_host {
 // env_mode_dev == nullptr: every environment is evaluated, with derivatives iff deriv != 0.
 // env_mode_dev != nullptr: per-environment 0 = skip, 1 = value only, 2 = with derivatives
 // (both force variants are launched; CTAs of non-matching environments exit at once).
+// env0 / env_count: environment range of this call (env_count < 0 = all environments).
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
-                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev);
+                      bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev,
+                      int env0 = 0, int env_count = -1);
 }  // namespace sdfc_host
 
 namespace sdfc_host {
@@ -135,7 +137,7 @@ sdfc_status ground_set_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
                               const int32_t* body, sdfc_ground_set** out);
 void ground_set_destroy(sdfc_ground_set* s);
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
-                           const int* env_mode_dev);
+                           const int* env_mode_dev, int env0, int env_count);
 sdfc_status ground_set_scatter(sdfc_ground_set* s, int deriv, double* fm_dev, double* Km_dev, double* Dm_dev);
 const double* ground_set_out(const sdfc_ground_set* s);
 const int32_t* ground_set_n_active(const sdfc_ground_set* s);

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     __shared__ int s_live[2 * kDetectTileWords];
     __shared__ int s_nlive[kDetectThreads / 32];
     static_assert(kDetectTileWords == 64, "the broad phase compaction assumes two ballots per tile");
-    const int tile = blockIdx.x, env = blockIdx.y;
+    const int tile = blockIdx.x, env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;  // CTA-uniform
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
     {
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
 }
 
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream) {
-    cudaMemsetAsync(B.n_active, 0, sizeof(int32_t) * (size_t)B.n_envs * B.n_pairs, stream);
-    dim3 grid(B.n_tiles, B.n_envs);
+    cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
+    dim3 grid(B.n_tiles, B.env_count);
     k_detect_mask<<<grid, kDetectThreads, 0, stream>>>(B, E);
 }
 
@@ -171,7 +171,7 @@ void launch_force(const BatchDev& B, const double* E, const double* phi, bool de
 // Per-pair block layout (natural): fm_sub[12], Km_sub[144] col-major, Dm_sub[144] col-major.
 __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restrict__ fm_sub, double* __restrict__ Km_sub,
                                 double* __restrict__ Dm_sub) {
-    const int pair = blockIdx.x, env = blockIdx.y;
+    const int pair = blockIdx.x, env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr) {
         const int m = __ldg(B.env_mode + env);
         if (m == 0) return;
@@ -181,11 +181,11 @@ __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restric
     const bool empty = B.n_active[ep] == 0;
     const bool nf = deriv && !dm;  // layout of contact_eval_nf: 12 Km columns + fm
     const int npart = nf ? kPartialNF : (deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
-    const double* part = B.partial + ep * B.splits * npart;
+    const double* part = B.partial + ep * B.splits * kPartialDerivDM;  // fixed slot stride, see k_force
     for (int slot = threadIdx.x; slot < npart; slot += blockDim.x) {
         double s = 0.0;
         if (!empty)
-            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * npart + slot];
+            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * kPartialDerivDM + slot];
         const int lane = slot & 31;
         if (nf) {
             const int j = slot >> 5, e = tr_index<12>(lane, 0);
@@ -223,7 +223,7 @@ __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restric
 __global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict__ fm_sub,
                                  const double* __restrict__ Km_sub, const double* __restrict__ Dm_sub,
                                  double* __restrict__ fm, double* __restrict__ Km, double* __restrict__ Dm) {
-    const int env = blockIdx.x;
+    const int env = blockIdx.x + B.env0;
     const int nm = 6 * B.n_bodies;
     const size_t e0 = (size_t)env * B.n_pairs;
     for (int i = threadIdx.x; i < nm; i += blockDim.x) {
@@ -259,13 +259,13 @@ __global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict
 
 void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
                            cudaStream_t stream) {
-    dim3 grid(B.n_pairs, B.n_envs);
+    dim3 grid(B.n_pairs, B.env_count);
     k_reduce_splits<<<grid, 128, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub);
 }
 
 void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,
                            const double* Dm_sub, double* fm, double* Km, double* Dm, cudaStream_t stream) {
-    k_scatter_system<<<B.n_envs, 256, 0, stream>>>(B, deriv ? 1 : 0, fm_sub, Km_sub, Dm_sub, fm, Km, Dm);
+    k_scatter_system<<<B.env_count, 256, 0, stream>>>(B, deriv ? 1 : 0, fm_sub, Km_sub, Dm_sub, fm, Km, Dm);
 }
 
 // --------------------------------------------------------------------------

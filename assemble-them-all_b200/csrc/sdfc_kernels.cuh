@@ -66,6 +66,10 @@ struct BatchDev {
     // environment, derivative flag taken from the launch; else 0 = skip,
     // 1 = value only, 2 = with derivatives
     const int* env_mode;
+    // environment range of this launch: [env0, env0 + env_count). The stepper runs
+    // disjoint ranges ("lanes") on separate streams so that one lane's latency-bound
+    // assembly / solve kernels overlap another lane's contact kernels.
+    int env0, env_count;
 };
 
 // launches (all asynchronous on `stream`)

@@ -27,8 +27,11 @@
 
 namespace sdfc {
 
-constexpr int kMaxR = 12;    // reduced dofs per environment
-constexpr int kMaxDyn = 2;   // non-fixed bodies per environment
+constexpr int kCapR = 12;    // reduced dofs per environment (largest instantiation)
+constexpr int kCapDyn = 2;   // non-fixed bodies per environment
+// The per-environment kernels are instantiated for <max reduced dofs, max non-fixed bodies,
+// any free3d-exp joint>: the planners' translational case (3, 1, false) keeps its state in
+// registers instead of the ~20 KB of local memory the general (12, 2, true) case needs.
 constexpr double kMathEps = 1e-9;  // math::eps, Utils.h:14
 constexpr double kNewtonTol = 1e-8;  // Simulation.cpp:1008
 constexpr int kMaxLS = 20;           // Simulation.cpp:1012
@@ -65,6 +68,7 @@ struct SimDev {
     double *q_traj, *qdot_traj;              // [steps][n_envs][nr] or nullptr
     int* n_unfinished;
     unsigned long long* counters;            // deriv evals, value evals, steps
+    int env0, env_count;                     // environment range of this launch (a stepper lane)
 };
 
 enum { PH_DERIV = 0, PH_LS = 1, PH_DONE = 2 };
@@ -277,6 +281,7 @@ struct JointKin {
     double dS[3][36], dSd[3][36];  // derivative w.r.t. dof 3 + i
 };
 
+template <bool kFree>
 __device__ __noinline__ void joint_kin(const BodyDev& b, const double* q, const double* qd, bool deriv, JointKin& k,
                                        SphKin& sph) {
     for (int i = 0; i < 36; ++i) { k.S[i] = 0; k.Sd[i] = 0; }
@@ -284,7 +289,7 @@ __device__ __noinline__ void joint_kin(const BodyDev& b, const double* q, const 
     k.p[0] = k.p[1] = k.p[2] = 0;
     if (b.type == SDFC_JOINT_TRANSLATIONAL) {  // JointTranslational.cpp:9-40
         for (int a = 0; a < 3; ++a) { k.p[a] = q[a]; k.S[(3 + a) * 6 + a] = 1.0; }
-    } else if (b.type == SDFC_JOINT_FREE3D_EXP) {  // JointFree3DExp.cpp:13-110
+    } else if (kFree && b.type == SDFC_JOINT_FREE3D_EXP) {  // JointFree3DExp.cpp:13-110
         spherical_exp(q + 3, qd + 3, deriv, sph);
         for (int i = 0; i < 9; ++i) k.R[i] = sph.R[i];
         for (int a = 0; a < 3; ++a) k.p[a] = q[a];
@@ -346,8 +351,8 @@ __device__ void body_pose(const BodyDev& b, const JointKin& k, const double* qd,
 
 // ------------------------------------------------------------------ kernels
 __global__ void k_sim_begin(SimDev S, int n_steps) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= S.n_envs) return;
+    const int env = S.env0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.env0 + S.env_count) return;
     // environments masked out by sdfc_sim_set_active keep their state untouched
     const bool on = n_steps > 0 && (S.active == nullptr || S.active[env] != 0);
     if (on) atomicAdd(S.n_unfinished, 1);
@@ -375,9 +380,10 @@ __device__ __forceinline__ void candidate(const SimDev& S, int env, int phase, d
     }
 }
 
+template <int kMaxR, int kMaxDyn, bool kFree>
 __global__ void __launch_bounds__(32) k_sim_pre(SimDev S, int poses_only) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= S.n_envs) return;
+    const int env = S.env0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.env0 + S.env_count) return;
     const int phase = poses_only ? PH_DERIV : S.phase[env];
     if (!poses_only) S.env_mode[env] = (phase == PH_DONE) ? 0 : (phase == PH_LS ? 1 : 2);
     if (phase == PH_DONE) return;
@@ -391,13 +397,14 @@ __global__ void __launch_bounds__(32) k_sim_pre(SimDev S, int poses_only) {
     SphKin sph;
     for (int b = 0; b < S.n_bodies; ++b) {
         const BodyDev& B = S.bodies[b];
-        joint_kin(B, xc + B.dof_off, qdc + B.dof_off, false, jk, sph);
+        joint_kin<kFree>(B, xc + B.dof_off, qdc + B.dof_off, false, jk, sph);
         body_pose(B, jk, qdc + B.dof_off, S.E + ((size_t)env * S.n_bodies + b) * 16,
                   S.phi + ((size_t)env * S.n_bodies + b) * 6, nullptr);
     }
 }
 
 // Solve A x = b (n <= kMaxR) by LU with partial pivoting (Simulation.cpp:1028 uses Eigen's PartialPivLU).
+template <int kMaxR>
 __device__ __noinline__ void lu_solve(double* A, double* b, int n) {
     for (int c = 0; c < n; ++c) {
         int piv = c;
@@ -443,9 +450,10 @@ __device__ __forceinline__ void mul66n(const double* A, const double* B, int n, 
         }
 }
 
+template <int kMaxR, int kMaxDyn, bool kFree>
 __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= S.n_envs) return;
+    const int env = S.env0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= S.env0 + S.env_count) return;
     const int mode = S.env_mode[env];
     if (mode == 0) return;
     const bool deriv = (mode == 2);
@@ -476,13 +484,13 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
             if (B.dyn < 0) continue;
             DynBody& D = dyn[B.dyn];
             D.n = B.ndof; D.off = B.dof_off; D.body = b;
-            D.has_dJ = deriv && (B.type == SDFC_JOINT_FREE3D_EXP);
-            joint_kin(B, xc + B.dof_off, qdc + B.dof_off, deriv, jk, sph);
+            D.has_dJ = kFree && deriv && (B.type == SDFC_JOINT_FREE3D_EXP);
+            joint_kin<kFree>(B, xc + B.dof_off, qdc + B.dof_off, deriv, jk, sph);
             double R[9], phi[6];
             body_pose(B, jk, qdc + B.dof_off, nullptr, phi, R);
             mul66n(B.Aij, jk.S, D.n, D.J);     // Robot.cpp:664-665
             mul66n(B.Aij, jk.Sd, D.n, D.Jd);
-            if (D.has_dJ)
+            if (kFree && D.has_dJ)
                 for (int i = 0; i < 3; ++i) { mul66n(B.Aij, jk.dS[i], D.n, D.dJ[i]); mul66n(B.Aij, jk.dSd[i], D.n, D.dJd[i]); }
             // Coriolis: ad(phi)^T (I phi)
             const double* w = phi; const double* v = phi + 3;
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
         for (int r = 0; r < 6; ++r)
             for (int k = 0; k < n; ++k) {
                 double s2 = 0;
-                if (D.has_dJ && k >= 3)
+                if (kFree && D.has_dJ && k >= 3)
                     for (int c = 0; c < n; ++c) s2 += D.dJ[k - 3][r * 6 + c] * qd[c];
                 dJq[s][r * 6 + k] = s2;
             }
@@ -615,7 +623,7 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
                 const double Dqvv = -JTMmJd[i * 6 + j] - t;
                 H[(off + i) * kMaxR + off + j] += M[i * 6 + j] - h * Dqvv;
             }
-        if (D.has_dJ) {
+        if (kFree && D.has_dJ) {
             for (int k = 3; k < n; ++k) {
                 const double* dJk = D.dJ[k - 3];
                 const double* dJdk = D.dJd[k - 3];
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
     if (deriv) {
         double rhs[kMaxR];
         for (int i = 0; i < nr; ++i) rhs[i] = -g[i];
-        lu_solve(H, rhs, nr);
+        lu_solve<kMaxR>(H, rhs, nr);
         for (int i = 0; i < nr; ++i) S.dx[o + i] = rhs[i];
         S.gnorm[env] = gn;
         S.alpha[env] = 1.0;
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(32) k_sim_post(SimDev S) {
             spherical_exp(r, rd, false, sph);
             double A3[kMaxR * kMaxR], b3[kMaxR];
             for (int i = 0; i < 3; ++i) { b3[i] = S0rd[i]; for (int j = 0; j < 3; ++j) A3[i * kMaxR + j] = sph.T[i * 3 + j]; }
-            lu_solve(A3, b3, 3);
+            lu_solve<kMaxR>(A3, b3, 3);
             for (int a = 0; a < 3; ++a) rd[a] = b3[a];
         }
     }
@@ -785,6 +793,13 @@ struct sdfc_sim {
     uint8_t *d_converged = nullptr, *d_touched = nullptr, *d_active = nullptr, *d_touched_ground = nullptr;
     int* d_ground_body = nullptr;
     int n_grounds = 0;
+    // lanes: disjoint environment ranges stepped on their own streams (see BatchDev::env0)
+    static constexpr int kMaxLanes = 4;
+    int n_lanes = 1;
+    cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_event[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_event = nullptr;
+    int variant = 2;  // kernel instantiation: 0 = (3,1,no free3d), 1 = (6,1,free3d), 2 = (12,2,free3d)
     bool use_active = false;
     double* d_fext = nullptr;
     int* d_unfinished = nullptr;
@@ -801,6 +816,19 @@ void colmajor_to_Rp(const double* E, double* R, double* p) {
         for (int c = 0; c < 3; ++c) R[r * 3 + c] = E[r + 4 * c];
         p[r] = E[r + 12];
     }
+}
+}  // namespace
+
+namespace {
+void launch_pre(sdfc_sim* s, const SimDev& D, int poses_only, int blocks, cudaStream_t st) {
+    if (s->variant == 0) k_sim_pre<3, 1, false><<<blocks, 32, 0, st>>>(D, poses_only);
+    else if (s->variant == 1) k_sim_pre<6, 1, true><<<blocks, 32, 0, st>>>(D, poses_only);
+    else k_sim_pre<kCapR, kCapDyn, true><<<blocks, 32, 0, st>>>(D, poses_only);
+}
+void launch_post(sdfc_sim* s, const SimDev& D, int blocks, cudaStream_t st) {
+    if (s->variant == 0) k_sim_post<3, 1, false><<<blocks, 32, 0, st>>>(D);
+    else if (s->variant == 1) k_sim_post<6, 1, true><<<blocks, 32, 0, st>>>(D);
+    else k_sim_post<kCapR, kCapDyn, true><<<blocks, 32, 0, st>>>(D);
 }
 }  // namespace
 
@@ -841,11 +869,16 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         for (int i = 0; i < 6; ++i) B.I6[i] = d.inertia[i];
         B.mass = d.mass;
     }
-    SDFC_REQUIRE(nr <= kMaxR && nd <= kMaxDyn, "sdfc_sim_create: at most 2 non-fixed bodies / 12 reduced dofs are supported");
+    SDFC_REQUIRE(nr <= kCapR && nd <= kCapDyn, "sdfc_sim_create: at most 2 non-fixed bodies / 12 reduced dofs are supported");
     SDFC_REQUIRE(nr > 0, "sdfc_sim_create: no degrees of freedom");
     SDFC_CUDA(cudaSetDevice(batch->ctx->device));
     sdfc_sim* s = new sdfc_sim();
     s->batch = batch; s->ctx = batch->ctx; s->n_envs = ne; s->n_bodies = nb; s->n_pairs = np; s->nr = nr;
+    {
+        bool any_free = false;
+        for (int b = 0; b < nb; ++b) any_free |= hb[b].type == SDFC_JOINT_FREE3D_EXP;
+        s->variant = (nd == 1 && nr <= 3 && !any_free) ? 0 : ((nd == 1 && nr <= 6) ? 1 : 2);
+    }
     sdfc_status st = SDFC_OK;
     auto A = [&](sdfc_status x) { if (st == SDFC_OK) st = x; };
     A(dev_alloc(&s->d_bodies, (size_t)nb));
@@ -862,10 +895,19 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     A(dev_alloc(&s->d_touched_ground, (size_t)ne * ng));
     A(dev_alloc(&s->d_ground_body, (size_t)ng));
     A(dev_alloc(&s->d_fext, (size_t)ne * nb * 6));
-    A(dev_alloc(&s->d_unfinished, (size_t)1));
+    A(dev_alloc(&s->d_unfinished, (size_t)sdfc_sim::kMaxLanes));
     A(dev_alloc(&s->d_counters, (size_t)4));
     if (st == SDFC_OK) {
-        cudaError_t e = cudaMallocHost((void**)&s->h_unfinished, sizeof(int));
+        // SDFC_SIM_LANES overrides the lane count (1 = everything on the context's stream)
+        const char* lanes_env = std::getenv("SDFC_SIM_LANES");
+        s->n_lanes = lanes_env ? std::max(1, std::min((int)sdfc_sim::kMaxLanes, std::atoi(lanes_env))) : (ne >= 512 ? 2 : 1);
+        s->n_lanes = std::min(s->n_lanes, std::max(1, ne / 32));
+        cudaError_t e = cudaMallocHost((void**)&s->h_unfinished, sizeof(int) * sdfc_sim::kMaxLanes);
+        for (int l = 0; l < s->n_lanes && e == cudaSuccess; ++l) {
+            e = cudaStreamCreateWithFlags(&s->lane_stream[l], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->lane_event[l], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_bodies, hb.data(), sizeof(BodyDev) * nb, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_pair_a, batch->body_a.data(), sizeof(int) * np, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_pair_b, batch->body_b.data(), sizeof(int) * np, cudaMemcpyHostToDevice);
@@ -901,6 +943,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     D.g_n_active = ng ? sdfc_host::ground_set_n_active(batch->gset) : nullptr;
     D.q_traj = nullptr; D.qdot_traj = nullptr;
     D.n_unfinished = s->d_unfinished; D.counters = s->d_counters;
+    D.env0 = 0; D.env_count = ne;
     *out = s;
     return SDFC_OK;
 }
@@ -912,6 +955,11 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     cudaFree(s->d_ints); cudaFree(s->d_converged); cudaFree(s->d_touched); cudaFree(s->d_active); cudaFree(s->d_touched_ground); cudaFree(s->d_ground_body); cudaFree(s->d_fext); cudaFree(s->d_unfinished);
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
+    for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) {
+        if (s->lane_stream[l]) cudaStreamDestroy(s->lane_stream[l]);
+        if (s->lane_event[l]) cudaEventDestroy(s->lane_event[l]);
+    }
+    if (s->fork_event) cudaEventDestroy(s->fork_event);
     delete s;
     return SDFC_OK;
 }
@@ -988,27 +1036,77 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     D.q_traj = q_traj_host ? s->d_traj_q : nullptr;
     D.qdot_traj = qdot_traj_host ? s->d_traj_qd : nullptr;
     D.active = s->use_active ? s->d_active : nullptr;
-    const int blocks = (s->n_envs + 31) / 32;
-    SDFC_CUDA(cudaMemsetAsync(s->d_unfinished, 0, sizeof(int), st));
-    k_sim_begin<<<blocks, 32, 0, st>>>(D, n_steps);
-    s->ctx->launches += 1;
+    // Lanes: each environment range advances through its own rounds on its own stream; the
+    // host feeds the lanes round-robin, so the 32-CTA assembly / solve kernels of one lane run
+    // under the contact kernels of another. Results do not depend on the lane count.
+    const int L = s->n_lanes;
+    cudaStream_t ctx_stream = s->ctx->stream;
+    SDFC_CUDA(cudaMemsetAsync(s->d_unfinished, 0, sizeof(int) * sdfc_sim::kMaxLanes, st));
+    SDFC_CUDA(cudaEventRecord(s->fork_event, st));
+    int lane_env0[sdfc_sim::kMaxLanes], lane_cnt[sdfc_sim::kMaxLanes];
+    bool lane_live[sdfc_sim::kMaxLanes];
+    for (int l = 0; l < L; ++l) {
+        lane_env0[l] = (int)((int64_t)s->n_envs * l / L);
+        lane_cnt[l] = (int)((int64_t)s->n_envs * (l + 1) / L) - lane_env0[l];
+        if (L == 2 && std::getenv("SDFC_SIM_LANE_SPLIT")) {  // debugging aid: first lane's size
+            const int c0 = std::max(0, std::min(s->n_envs, std::atoi(std::getenv("SDFC_SIM_LANE_SPLIT"))));
+            lane_env0[l] = l == 0 ? 0 : c0;
+            lane_cnt[l] = l == 0 ? c0 : s->n_envs - c0;
+        }
+        lane_live[l] = lane_cnt[l] > 0;
+        if (!lane_live[l]) continue;
+        cudaStream_t ls = (L == 1) ? st : s->lane_stream[l];
+        if (L > 1) SDFC_CUDA(cudaStreamWaitEvent(ls, s->fork_event, 0));
+        SimDev Dl = D;
+        Dl.env0 = lane_env0[l]; Dl.env_count = lane_cnt[l]; Dl.n_unfinished = s->d_unfinished + l;
+        k_sim_begin<<<(lane_cnt[l] + 31) / 32, 32, 0, ls>>>(Dl, n_steps);
+        s->ctx->launches += 1;
+    }
     // every step needs at least two rounds (one Newton evaluation, one line-search
     // trial), so the unfinished-counter is only polled every second round
-    int64_t guard = (int64_t)n_steps * (D.max_iter * (kMaxLS + 1) + 1);
-    for (int64_t round = 0; round < guard; ++round) {
-        k_sim_pre<<<blocks, 32, 0, st>>>(D, 0);
-        sdfc_status r = sdfc_host::batch_run(s->batch, D.E, D.phi, 0, D.env_mode, /*scatter=*/false, nullptr, nullptr,
-                                             nullptr, nullptr);
-        if (r != SDFC_OK) return r;
-        k_sim_post<<<blocks, 32, 0, st>>>(D);
-        s->ctx->launches += 2;
-        s->rounds += 1;
-        if (round & 1) {
-            SDFC_CUDA(cudaMemcpyAsync(s->h_unfinished, s->d_unfinished, sizeof(int), cudaMemcpyDeviceToHost, st));
-            SDFC_CUDA(cudaStreamSynchronize(st));
-            if (*s->h_unfinished <= 0) break;
+    const int64_t guard = (int64_t)n_steps * (D.max_iter * (kMaxLS + 1) + 1);
+    int64_t depth = 0;
+    sdfc_status rc = SDFC_OK;
+    for (int64_t round = 0; round < guard && rc == SDFC_OK; ++round) {
+        bool any = false;
+        for (int l = 0; l < L && rc == SDFC_OK; ++l) {
+            if (!lane_live[l]) continue;
+            any = true;
+            cudaStream_t ls = (L == 1) ? st : s->lane_stream[l];
+            SimDev Dl = D;
+            Dl.env0 = lane_env0[l]; Dl.env_count = lane_cnt[l]; Dl.n_unfinished = s->d_unfinished + l;
+            const int blocks = (lane_cnt[l] + 31) / 32;
+            s->ctx->stream = ls;  // the batch launches (and their timing events) go to the lane's stream
+            launch_pre(s, Dl, 0, blocks, ls);
+            rc = sdfc_host::batch_run(s->batch, D.E, D.phi, 0, D.env_mode, /*scatter=*/false, nullptr, nullptr, nullptr,
+                                      nullptr, lane_env0[l], lane_cnt[l]);
+            s->ctx->stream = ctx_stream;
+            if (rc != SDFC_OK) break;
+            launch_post(s, Dl, blocks, ls);
+            s->ctx->launches += 2;
+            if (std::getenv("SDFC_SIM_LANE_SYNC")) cudaDeviceSynchronize();  // debugging aid
+            if (round & 1) {
+                if (cudaMemcpyAsync(s->h_unfinished + l, s->d_unfinished + l, sizeof(int), cudaMemcpyDeviceToHost, ls) != cudaSuccess ||
+                    cudaEventRecord(s->lane_event[l], ls) != cudaSuccess)
+                    rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: poll failed");
+            }
         }
+        if (!any) break;
+        depth += 1;
+        if (round & 1)
+            for (int l = 0; l < L && rc == SDFC_OK; ++l) {
+                if (!lane_live[l]) continue;
+                if (cudaEventSynchronize(s->lane_event[l]) != cudaSuccess) rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: lane sync failed");
+                else if (s->h_unfinished[l] <= 0) lane_live[l] = false;
+            }
     }
+    s->rounds += depth;
+    if (rc != SDFC_OK) { cudaDeviceSynchronize(); return rc; }
+    if (L > 1)
+        for (int l = 0; l < L; ++l) {  // join: the context stream continues after every lane
+            SDFC_CUDA(cudaEventRecord(s->lane_event[l], s->lane_stream[l]));
+            SDFC_CUDA(cudaStreamWaitEvent(st, s->lane_event[l], 0));
+        }
     SDFC_CUDA(cudaGetLastError());
     if (q_traj_host) SDFC_CUDA(cudaMemcpyAsync(q_traj_host, s->d_traj_q, sizeof(double) * per_step * n_steps, cudaMemcpyDeviceToHost, st));
     if (qdot_traj_host) SDFC_CUDA(cudaMemcpyAsync(qdot_traj_host, s->d_traj_qd, sizeof(double) * per_step * n_steps, cudaMemcpyDeviceToHost, st));
@@ -1038,7 +1136,7 @@ sdfc_status sdfc_sim_get_ground_history(sdfc_sim* s, uint8_t* touched_ground) {
 sdfc_status sdfc_sim_get_poses(sdfc_sim* s, double* E_host) {
     SDFC_REQUIRE(s && E_host, "sdfc_sim_get_poses: NULL argument");
     SDFC_CUDA(cudaSetDevice(s->ctx->device));
-    k_sim_pre<<<(s->n_envs + 31) / 32, 32, 0, s->ctx->stream>>>(s->dev, 1);
+    launch_pre(s, s->dev, 1, (s->n_envs + 31) / 32, s->ctx->stream);
     s->ctx->launches += 1;
     SDFC_CUDA(cudaMemcpyAsync(E_host, s->dev.E, sizeof(double) * (size_t)s->n_envs * s->n_bodies * 16, cudaMemcpyDeviceToHost,
                               s->ctx->stream));

@@ -164,3 +164,40 @@ def test_rollouts_match_reference_forward(cuda_ctx, joint_type, n_envs):
         assert bool(conv[e]) == p.is_converged()
         assert bool(hist[e].any()) == (len(p.get_contact_bodies("part0")) > 0)
     sim.close()
+
+
+def test_lanes_and_mixed_mode_rounds_do_not_change_results(cuda_ctx):
+    """768 rollouts with different pushes drift apart in Newton / line-search phase, so most
+    rounds mix value-only and derivative environments. Stepping them on 1, 2 or 3 lanes
+    (environment ranges on their own streams, SDFC_SIM_LANES) must give bit-identical states:
+    guards the per-(env, pair, split) slot layout of the force partials (value and derivative
+    variants share the buffer inside one round) and the lane fork / join ordering."""
+    import os
+    from assemble_them_all_b200 import contact, scenes
+    rs = scenes.c2_planner_rollouts(n_envs=768, n_vertices=600, sdf_dx=0.1)
+    rs.q0[:, 2] = np.linspace(0.2, 1.5, 768)
+    outs, evals = [], []
+    old = os.environ.get("SDFC_SIM_LANES")
+    try:
+        for lanes in ("1", "2", "3"):
+            os.environ["SDFC_SIM_LANES"] = lanes
+            sim, *keep = rs.upload(cuda_ctx)
+            sim.reset(rs.q0, rs.qdot0)
+            for b in range(len(rs.bodies)):
+                sim.set_body_external_force(b, rs.f_ext[:, b])
+            s0 = sim.stats()
+            sim.forward(60)
+            s1 = sim.stats()
+            outs.append(sim.get_state())
+            evals.append((s1["deriv_env_evals"] - s0["deriv_env_evals"], s1["value_env_evals"] - s0["value_env_evals"]))
+            assert sim.get_contact_history().any()
+            sim.close()
+    finally:
+        if old is None:
+            os.environ.pop("SDFC_SIM_LANES", None)
+        else:
+            os.environ["SDFC_SIM_LANES"] = old
+    assert evals[0] == evals[1] == evals[2]
+    assert evals[0][0] > 768 * 60          # more than one Newton iteration per step somewhere: phases diverged
+    for q, qd in outs[1:]:
+        assert np.array_equal(q, outs[0][0]) and np.array_equal(qd, outs[0][1])
