@@ -1067,12 +1067,21 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     const int64_t guard = (int64_t)n_steps * (D.max_iter * (kMaxLS + 1) + 1);
     int64_t depth = 0;
     sdfc_status rc = SDFC_OK;
+    // The unfinished-counter of a lane is read back with a lag: the copy enqueued after round r
+    // is only waited for before round r + 2 is issued, so the device always has queued work while
+    // the host looks at an older answer (a finished lane runs at most two empty rounds).
+    bool lane_pending[sdfc_sim::kMaxLanes] = {false, false, false, false};
     for (int64_t round = 0; round < guard && rc == SDFC_OK; ++round) {
         bool any = false;
         for (int l = 0; l < L && rc == SDFC_OK; ++l) {
             if (!lane_live[l]) continue;
-            any = true;
             cudaStream_t ls = (L == 1) ? st : s->lane_stream[l];
+            if ((round & 1) && lane_pending[l]) {
+                if (cudaEventSynchronize(s->lane_event[l]) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: lane sync failed"); break; }
+                lane_pending[l] = false;
+                if (s->h_unfinished[l] <= 0) { lane_live[l] = false; continue; }
+            }
+            any = true;
             SimDev Dl = D;
             Dl.env0 = lane_env0[l]; Dl.env_count = lane_cnt[l]; Dl.n_unfinished = s->d_unfinished + l;
             const int blocks = (lane_cnt[l] + 31) / 32;
@@ -1089,16 +1098,11 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
                 if (cudaMemcpyAsync(s->h_unfinished + l, s->d_unfinished + l, sizeof(int), cudaMemcpyDeviceToHost, ls) != cudaSuccess ||
                     cudaEventRecord(s->lane_event[l], ls) != cudaSuccess)
                     rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: poll failed");
+                lane_pending[l] = true;
             }
         }
         if (!any) break;
         depth += 1;
-        if (round & 1)
-            for (int l = 0; l < L && rc == SDFC_OK; ++l) {
-                if (!lane_live[l]) continue;
-                if (cudaEventSynchronize(s->lane_event[l]) != cudaSuccess) rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: lane sync failed");
-                else if (s->h_unfinished[l] <= 0) lane_live[l] = false;
-            }
     }
     s->rounds += depth;
     if (rc != SDFC_OK) { cudaDeviceSynchronize(); return rc; }
