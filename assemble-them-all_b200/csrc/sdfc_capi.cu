@@ -73,21 +73,6 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
     if (env_count < 0) { env0 = 0; env_count = b->n_envs; }
-    if (const char* dbg = std::getenv("SDFC_DEBUG_SPLIT_EVAL")) {  // debugging aid: evaluate a full-range call as two ranges
-        const int c0 = std::atoi(dbg);
-        if (!scatter || env0 != 0 || env_count != b->n_envs || c0 <= 0 || c0 >= b->n_envs) goto no_split;
-        st = batch_run(b, E_dev, phi_dev, deriv, env_mode_dev, false, nullptr, nullptr, nullptr, nullptr, 0, c0);
-        if (st != SDFC_OK) return st;
-        st = batch_run(b, E_dev, phi_dev, deriv, env_mode_dev, false, nullptr, nullptr, nullptr, nullptr, c0, b->n_envs - c0);
-        if (st != SDFC_OK) return st;
-        BatchDev dv = b->dev;
-        launch_scatter_system(dv, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, b->ctx->stream);
-        if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
-            SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
-                                      cudaMemcpyDeviceToDevice, b->ctx->stream));
-        return SDFC_OK;
-    }
-no_split:
     cudaStream_t s = b->ctx->stream;
     const bool dm = b->any_fric || b->any_damp;
     sdfc_context* c = b->ctx;

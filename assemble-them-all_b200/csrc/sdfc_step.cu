@@ -1048,11 +1048,6 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     for (int l = 0; l < L; ++l) {
         lane_env0[l] = (int)((int64_t)s->n_envs * l / L);
         lane_cnt[l] = (int)((int64_t)s->n_envs * (l + 1) / L) - lane_env0[l];
-        if (L == 2 && std::getenv("SDFC_SIM_LANE_SPLIT")) {  // debugging aid: first lane's size
-            const int c0 = std::max(0, std::min(s->n_envs, std::atoi(std::getenv("SDFC_SIM_LANE_SPLIT"))));
-            lane_env0[l] = l == 0 ? 0 : c0;
-            lane_cnt[l] = l == 0 ? c0 : s->n_envs - c0;
-        }
         lane_live[l] = lane_cnt[l] > 0;
         if (!lane_live[l]) continue;
         cudaStream_t ls = (L == 1) ? st : s->lane_stream[l];
@@ -1093,7 +1088,6 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             if (rc != SDFC_OK) break;
             launch_post(s, Dl, blocks, ls);
             s->ctx->launches += 2;
-            if (std::getenv("SDFC_SIM_LANE_SYNC")) cudaDeviceSynchronize();  // debugging aid
             if (round & 1) {
                 if (cudaMemcpyAsync(s->h_unfinished + l, s->d_unfinished + l, sizeof(int), cudaMemcpyDeviceToHost, ls) != cudaSuccess ||
                     cudaEventRecord(s->lane_event[l], ls) != cudaSuccess)

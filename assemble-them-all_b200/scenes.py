@@ -180,6 +180,7 @@ class RolloutScene:
     damping: float = 0.0
     frame_skip: int = 100
     label: str = ""
+    grounds: list = field(default_factory=list)   # {"body", "E_g", "kn", "kt", "mu", "damping"} (ForceGroundContact)
 
     @property
     def n_envs(self):
@@ -197,7 +198,12 @@ class RolloutScene:
                                                 index_contact=6 * a, index_sdf=6 * b) for a, b in self.pairs]
         batch = contact.ContactBatch(ctx, self.n_envs, len(self.bodies), pairs, [a for a, _ in self.pairs],
                                      [b for _, b in self.pairs])
+        gforces = [contact.ForceGroundContact(ctx, pts[g["body"]], g["E_g"], g["kn"], g["kt"], g["mu"], g["damping"],
+                                              6 * g["body"]) for g in self.grounds]
+        if gforces:
+            batch.set_grounds(gforces, [g["body"] for g in self.grounds])
         sim = contact.BatchedSimulation(batch, [b.desc() for b in self.bodies], self.gravity, self.h)
+        sim._grounds = gforces
         return sim, batch, pairs, sdf, pts
 
 
@@ -225,6 +231,31 @@ def c2_planner_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sdf
     return RolloutScene(bodies, [(0, 1), (1, 0)], q0, np.zeros((n_envs, nr)), f, float(np.float32(1e-3)),
                         np.array([0.0, 0.0, 1e-12]),
                         label=f"C2 two-part BFS {joint_type}, {n_envs} rollouts x frame_skip 100, 2x~{n_vertices} contact pts, dx {sdf_dx}")
+
+
+def c1_freefall_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sdf_dx=0.05, col_th=0.01, steps=100):
+    """C1 batched: examples/test_joint_sim.py:24-63 (both parts free3d-exp, gravity 9.8, ground plane
+    z = -5 with kn 1e6 / kt 1e3 / mu 0.8 / damping 50, SDF contact kn 1e5) for n_envs drops that start
+    a few centimetres above the plane with seeded tilts and lateral velocities, so that the
+    window covers free flight, impact and frictional sliding."""
+    rng = np.random.default_rng(seed)
+    bodies = peg_hole_bodies(n_vertices, sdf_dx, col_th)
+    for b in bodies:
+        b.joint_type = "free3d-exp"
+    q0 = np.zeros((n_envs, 12))
+    qd0 = np.zeros((n_envs, 12))
+    q0[:, 2] = -2.0 + rng.uniform(-0.9, -0.6, n_envs)       # peg: inside the hole, lowest face 0.1 .. 0.4 above the plane
+    q0[:, 8] = -3.0 + rng.uniform(0.005, 0.05, n_envs)      # block: 0.5 .. 5 cm above the plane
+    q0[:, 3:6] = rng.normal(scale=0.01, size=(n_envs, 3))
+    q0[:, 9:12] = rng.normal(scale=0.005, size=(n_envs, 3))
+    qd0[:, 0:2] = rng.normal(scale=0.2, size=(n_envs, 2))
+    qd0[:, 6:8] = rng.normal(scale=0.2, size=(n_envs, 2))
+    E_g = np.eye(4)
+    E_g[2, 3] = -5.0
+    grounds = [{"body": b, "E_g": E_g, "kn": 1e6, "kt": 1e3, "mu": float(np.float32(0.8)), "damping": 5e1} for b in (0, 1)]
+    return RolloutScene(bodies, [(0, 1), (1, 0)], q0, qd0, np.zeros((n_envs, 2, 6)), float(np.float32(1e-3)),
+                        np.array([0.0, 0.0, -9.8]), kn=1e5, kt=1e3, mu=0.0, damping=0.0, frame_skip=steps, grounds=grounds,
+                        label=f"C1 free fall, {n_envs} drops x {steps} steps, 2x~{n_vertices} contact pts, ground + SDF contact, gravity 9.8")
 
 
 def sweep_scene(n_points, grid_n, active_frac=0.05, seed=synth.SWEEP_SEED):

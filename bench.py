@@ -300,6 +300,92 @@ def cpu_baseline_leg(scene, gpu_out, budget_s=20.0):
             "env_evals_per_sec": n_done / t_total}
 
 
+def c1_leg(ctx, args, torch, stream):
+    """env-steps/s of the batched stepper on the C1 configuration (two free parts, ground contact with
+    friction and damping + SDF contact, 12 reduced dofs): the general 12-dof kernels and k_ground."""
+    from assemble_them_all_b200 import scenes
+    n_envs = min(args.envs, 1024)
+    rs = scenes.c1_freefall_rollouts(n_envs=n_envs)
+    sim, *keep = rs.upload(ctx)
+    times = []
+    for rep in range(3):
+        sim.reset(rs.q0, rs.qdot0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        sim.forward(rs.frame_skip)
+        b.record(stream)
+        torch.cuda.synchronize()
+        if rep:
+            times.append(a.elapsed_time(b))
+    st = sim.stats()
+    out = {"value": n_envs * rs.frame_skip / (1e-3 * float(np.mean(times))), "unit": "env-steps/s", "workload": rs.label,
+           "ms_per_forward": float(np.mean(times)), "rounds_per_forward": st["rounds"] / 3.0,
+           "converged": int(sim.is_converged().sum()),
+           "ground_touched": int(sim.get_ground_history().any(axis=1).sum()),
+           "sdf_touched": int(sim.get_contact_history().any(axis=1).sum()),
+           "contact_evals_per_env_step": (st["deriv_env_evals"] + st["value_env_evals"]) / max(1, st["env_steps"]),
+           "cpu_reference_note": "full-size C1 on the reference: 88 env-steps/s on one core (profiles/r1h_configs_c1_c3.log)"}
+    sim.close()
+    return out
+
+
+def rot_leg(ctx, args, torch, stream):
+    """env-steps/s of the stepper on the rotational planner's rollouts (free3d-exp joint, 12 actions:
+    run_joint_plan.py:585-598) on the C2 geometry: the 6-dof kernels (exponential-map kinematics and
+    their derivatives)."""
+    from assemble_them_all_b200 import scenes
+    n_envs = min(args.envs, 1024)
+    rs = scenes.c2_planner_rollouts(n_envs=n_envs, n_vertices=10000, joint_type="free3d-exp")
+    sim, *keep = rs.upload(ctx)
+    times = []
+    for rep in range(3):
+        sim.reset(rs.q0, rs.qdot0)
+        for b in range(len(rs.bodies)):
+            sim.set_body_external_force(b, rs.f_ext[:, b])
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0 = sim.stats()
+        a.record(stream)
+        sim.forward(rs.frame_skip)
+        b2.record(stream)
+        torch.cuda.synchronize()
+        s1 = sim.stats()
+        if rep:
+            times.append(a.elapsed_time(b2))
+    out = {"value": n_envs * rs.frame_skip / (1e-3 * float(np.mean(times))), "unit": "env-steps/s", "workload": rs.label,
+           "ms_per_forward": float(np.mean(times)), "rounds_per_forward": s1["rounds"] - s0["rounds"],
+           "converged": int(sim.is_converged().sum()), "touched": int(sim.get_contact_history().any(axis=1).sum())}
+    sim.close()
+    return out
+
+
+def sdf_build_leg(ctx, cpu):
+    """SDF construction (sdfgen::make_level_set3 drop-in) for the two C2 parts: wall time of the host call
+    (upload, ~5 k wavefront launches, download); the CPU restatement timed on the larger part."""
+    from assemble_them_all_b200 import contact, synth
+    parts = synth.peg_in_hole(n_vertices=10000)
+    out = {"parts": []}
+    for pid in ("0", "1"):
+        V, F = parts[pid]
+        V = np.float64(np.float32(V))
+        contact.precompute_sdf(ctx, V, F, 0.05)   # warm-up
+        t0 = time.perf_counter()
+        g = contact.precompute_sdf(ctx, V, F, 0.05)
+        out["parts"].append({"cells": [g["ni"], g["nj"], g["nk"]], "triangles": int(len(F)), "gpu_ms": 1e3 * (time.perf_counter() - t0)})
+    if cpu:
+        from oracle import sdfgen_oracle as SG
+        V, F = parts["1"]
+        V = np.float64(np.float32(V))
+        lay = SG.grid_layout(V, 0.05)
+        sp = lay["spacing"].astype(np.float32)
+        t0 = time.perf_counter()
+        ref = SG.make_level_set3(F, V.astype(np.float32), lay["min_box"], sp[0], sp[1], sp[2], *(int(v) for v in lay["dims"]))
+        out["cpu_port_ms_part1"] = 1e3 * (time.perf_counter() - t0)
+        out["bit_identical_part1"] = bool(np.array_equal(ref, g["grid"].astype(np.float32)))
+    return out
+
+
 def env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream):
     """env-steps/s of the batched stepper on the planner rollouts (sdfc_sim_forward = Simulation::forward(frame_skip)
     for every rollout). `value`: state resident in HBM, nothing returned per step. `e2e`: reset + external force
@@ -398,6 +484,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from assemble_them_all_b200 import contact
@@ -516,6 +605,11 @@ def run_ours(args):
     contacts_per_step = int(n_active.sum().item())
 
     env_steps = None if args.skip_env_steps else env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream)
+    extras = {}
+    if rank == 0 and not args.skip_env_steps:
+        extras["c1_freefall"] = c1_leg(ctx, args, torch, stream)
+        extras["rotational_rollouts"] = rot_leg(ctx, args, torch, stream)
+        extras["sdf_build"] = sdf_build_leg(ctx, cpu=(world == 1 and not args.no_cpu_baseline))
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -546,6 +640,7 @@ def run_ours(args):
                            "step": ms_step},
             "env_evals_per_sec": world * scene.n_envs / (ms_max * 1e-3),
             "env_steps": env_steps,
+            **extras,
         }
         if world == 1 and not args.no_cpu_baseline:
             fm_h, Km_h, Dm_h, _ = out
