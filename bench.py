@@ -300,6 +300,14 @@ def cpu_baseline_leg(scene, gpu_out, budget_s=20.0):
             "env_evals_per_sec": n_done / t_total}
 
 
+def ncu_traffic(key):
+    """dram bytes per launch measured by ncu --set full (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def c1_leg(ctx, args, torch, stream):
     """env-steps/s of the batched stepper on the C1 configuration (two free parts, ground contact with
     friction and damping + SDF contact, 12 reduced dofs): the general 12-dof kernels and k_ground."""
@@ -357,6 +365,61 @@ def rot_leg(ctx, args, torch, stream):
            "ms_per_forward": float(np.mean(times)), "rounds_per_forward": s1["rounds"] - s0["rounds"],
            "converged": int(sim.is_converged().sum()), "touched": int(sim.get_contact_history().any(axis=1).sum())}
     sim.close()
+    return out
+
+
+def hbm_regime_leg(ctx, torch, stream, dev, peak, n_points=30_000_000, grid_n=512):
+    """The same detection kernel where it IS HBM-bound (C5 of BASELINE.json): n_points uniform random points
+    against a 512^3 grid (4.3 GB of fp32 cell records, 34x the L2), one environment. The headline entry uses
+    the library's default point order (the one-time Morton sort of sdfc_points_create); the same points in
+    file order (every gather a fresh DRAM sector group) are reported next to it.
+    Algorithmic bytes: 96 B per query; compulsory DRAM bytes of the layout: 24 B point +
+    32 B cell record + 1 bit. Timed with CUDA events on the launching stream, L2 flushed between launches."""
+    from assemble_them_all_b200 import contact, scenes, synth
+    spec, pts = scenes.sweep_scene(n_points, grid_n)
+    sdf = contact.SdfGrid.from_spec(ctx, spec)
+    R = synth.axis_angle_rotation([0.3, -0.2, 0.9], 0.01)
+    E = np.stack([synth.make_E(R, [0.01, -0.02, 0.015]), np.eye(4)])[None]
+    dE = torch.from_numpy(np.ascontiguousarray(np.swapaxes(E, -1, -2))).to(dev)
+    dna = torch.zeros((1, 1), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    secs = {}
+    for order, sort in (("file order", False), ("Morton-sorted at upload", True)):
+        cp = contact.ContactPoints(ctx, pts, morton_sort=sort)
+        pair = contact.ForceGeneralSDFContact(ctx, cp, sdf, 1e6, 1e3)
+        batch = contact.ContactBatch(ctx, 1, 2, [pair], [0], [1])
+        for _ in range(3):
+            batch.detect_device(dE.data_ptr(), dna.data_ptr())
+        ms = []
+        for _ in range(7):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            batch.detect_device(dE.data_ptr(), dna.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        secs[order] = float(np.median(ms)) * 1e-3
+        batch.close(); pair.close(); cp.close()
+    t = secs["Morton-sorted at upload"]
+    achieved = n_points * BYTES_PER_QUERY / t / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_detect_mask@C5_1e8x512"]
+        traffic = tr["dram_bytes_per_launch"] * (n_points / 1e8)   # per-launch traffic scales with the point count
+    except Exception:
+        pass
+    out = {"kernel": "k_detect_mask", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": None, "workload": f"C5: {n_points:.0e} uniform points (Morton-sorted at upload) vs {grid_n}^3 grid, 1 environment",
+           "file_order": {"avg_launch_ms": secs["file order"] * 1e3, "frac": n_points * BYTES_PER_QUERY / secs["file order"] / 1e9 / peak,
+                          "traffic": traffic, "traffic_note": "ncu dram bytes of the 1e8-point file-order capture scaled by the point count"},
+           "avg_launch_ms": t * 1e3, "queries_per_sec": n_points / t, "algorithmic_bytes_per_launch": n_points * BYTES_PER_QUERY,
+           "compulsory_dram_GBs": n_points * (24 + 32 + 0.125) / t / 1e9,
+           "compulsory_frac": n_points * (24 + 32 + 0.125) / t / 1e9 / peak,
+           "active_fraction": float(dna.item()) / n_points}
+    sdf.close()
+    del flush
+    torch.cuda.empty_cache()
     return out
 
 
@@ -610,6 +673,7 @@ def run_ours(args):
         extras["c1_freefall"] = c1_leg(ctx, args, torch, stream)
         extras["rotational_rollouts"] = rot_leg(ctx, args, torch, stream)
         extras["sdf_build"] = sdf_build_leg(ctx, cpu=(world == 1 and not args.no_cpu_baseline))
+        extras["roofline_hbm_regime"] = hbm_regime_leg(ctx, torch, stream, dev, measured_hbm_peak()[0])
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -633,7 +697,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * float(np.mean(e2e_times))},
             "gpu_launches": gpu_launches,
             "roofline": {"kernel": "k_detect_mask", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic("k_detect_mask@C2"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": q_rank * BYTES_PER_QUERY, "avg_launch_ms": det_ms,
                          "share_of_step": det_ms / ms_step},
             "kernels_ms": {"k_detect_mask": det_ms, "k_force": frc_ms, "k_reduce_splits+k_scatter_system": red_ms,

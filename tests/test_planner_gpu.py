@@ -131,3 +131,27 @@ def test_sequence_plan_matches_reference(cuda_ctx):
     assert (r.status, r.sequence, r.trials) == (st, seq, count)
     assert [(m, d, s) for m, d, _, s in r.log] == trace
     assert st == "Success" and seq == ["2", "0"]
+
+
+def test_planner_wall_time_report(cuda_ctx):
+    """One whole planning problem at a realistic mesh size (L-channel, ~13 k contact points on the
+    block, dx 0.05): sequential reference loop on the CPU vs the batched planner on the GPU. Same
+    plan required; wall times are printed (kept under profiles/ by the profiling script)."""
+    import time
+    p, hulls, sim = _setup(cuda_ctx, synth.l_channel(h=0.1), "translational", 0.05, 36)
+    npts = [len(np.array(p.get_body_vertices(n)).T) for n in ("part0", "part1")]
+    seq = SP.SequentialBFSPlanner(p, "part0", hulls)
+    t0 = time.perf_counter()
+    st, path, acts, stages = seq.plan(PL.TRANS_ACTIONS, max_depth=8)
+    t_cpu = time.perf_counter() - t0
+    bp = PL.BatchedBFSPlanner(sim, 0, hulls)
+    bp.plan(max_depth=8)                                    # warm-up (first-use allocations)
+    t0 = time.perf_counter()
+    r = bp.plan(max_depth=8)
+    t_gpu = time.perf_counter() - t0
+    print(f"\nPLANNER: contact points {npts}; plan {acts} ({st}); reference loop: {seq.rollouts} rollouts, {seq.env_steps} env-steps, "
+          f"{t_cpu:.2f} s on one core; batched planner: {r.rollouts_run} rollouts run ({r.rollouts} consumed), {r.env_steps} env-steps, "
+          f"{r.forward_calls} forward calls, {t_gpu:.3f} s -> {t_cpu / t_gpu:.1f}x")
+    assert (r.status, r.actions, r.stages, r.rollouts) == (st, acts, stages, seq.rollouts)
+    assert r.path.shape == path.shape and rel_err(path, r.path) <= 1e-9
+    sim.close()
