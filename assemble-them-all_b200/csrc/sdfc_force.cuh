@@ -114,9 +114,12 @@ struct ColSink {
         for (int j = 0; j < kNfCols; ++j) acc[j] = 0.0;
     }
     __device__ __forceinline__ void emit(int j, const double* c12) {
+        // lanes beyond the last contact evaluate a duplicate with kn = 0 (force_rounds_nf): every
+        // output of contact_eval_nf is proportional to kn, so they contribute exact zeros without
+        // 24 selects per column here
         double v[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = valid ? c12[i] : 0.0;
+        for (int i = 0; i < 12; ++i) v[i] = c12[i];
         TransposeReduce<12, 16>::run(v, lane);
         acc[j] += v[0];
     }
@@ -162,7 +165,7 @@ __device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total,
         sink.valid = c < total;
         const int id = S.ids[sink.valid ? c : base];
         const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
-        contact_eval_nf<F32>(S.pd.grid, S.nf, S.pd.prm.kn, xi1, sink);
+        contact_eval_nf<F32>(S.pd.grid, S.nf, sink.valid ? S.pd.prm.kn : 0.0, xi1, sink);
     }
 }
 
