@@ -12,13 +12,16 @@
 //   * fast sweeping (.cpp:99-124,212-222): 2 x 8 Gauss-Seidel sweeps, each cell reading
 //     the closest triangles of its 7 upwind neighbours already updated in the same sweep.
 //     Upwind neighbours lie on earlier anti-diagonal planes i'+j'+k' = s of the sweep's own
-//     index order, so one kernel per plane reproduces the sequential result.
+//     index order, so processing plane after plane reproduces the sequential result; the planes
+//     are separated by grid-wide barriers inside one persistent cooperative kernel.
 //   * parity signs (.cpp:193-208,223-225): integer intersection counts (atomicAdd) and a
 //     prefix parity along x.
 // Arithmetic: fp32 distances, fp64 grid coordinates / barycentrics, in the reference's
 // evaluation order; this translation unit is compiled with -fmad=false (the reference's
 // x86-64 build has no FMA) and nvcc's default IEEE division and square root.
 #include "sdfc_host.h"
+
+#include <cooperative_groups.h>
 
 #include <cfloat>
 #include <cmath>
@@ -182,17 +185,15 @@ __global__ void k_ls_decode(LevelSetDev L, size_t n) {
     L.closest[c] = hit ? (int)(unsigned)(key & 0xFFFFFFFFull) : -1;
 }
 
-// One anti-diagonal plane of one sweep (makelevelset3.cpp:99-124): threads over (j', k'),
-// i' = s - j' - k'; primed indices count along the sweep direction starting at 0.
-__global__ void __launch_bounds__(128) k_ls_sweep(LevelSetDev L, int s, int di, int dj, int dk) {
-    const int jp = 1 + blockIdx.x * blockDim.x + threadIdx.x, kp = 1 + blockIdx.y;
-    if (jp > L.nj - 1 || kp > L.nk - 1) return;
-    const int ip = s - jp - kp;
-    if (ip < 1 || ip > L.ni - 1) return;
+// One cell of one sweep (makelevelset3.cpp:86-97,112-123). Primed indices count along the
+// sweep direction starting at 0; the 7 upwind neighbours lie on earlier planes i'+j'+k'.
+__device__ __forceinline__ void sweep_cell(const LevelSetDev& L, int ip, int jp, int kp, int di, int dj, int dk) {
     const int i = di > 0 ? ip : L.ni - 1 - ip, j = dj > 0 ? jp : L.nj - 1 - jp, k = dk > 0 ? kp : L.nk - 1 - kp;
     const size_t c0 = cell(L, i, j, k);
-    float best = L.phi[c0];
-    int best_t = L.closest[c0];
+    // phi / closest are rewritten plane after plane by other CTAs of the same (persistent) kernel:
+    // read them through L2 (ld.global.cg), never from a possibly stale L1 line
+    float best = __ldcg(L.phi + c0);
+    int best_t = __ldcg(L.closest + c0);
     const F3 gx = grid_point(L, i, j, k);
     const int ni[7] = {i - di, i, i - di, i, i - di, i, i - di};
     const int nj[7] = {j, j - dj, j - dj, j, j, j - dj, j - dj};
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(128) k_ls_sweep(LevelSetDev L, int s, int di, 
     float last_d = 0.f;
 #pragma unroll
     for (int n = 0; n < 7; ++n) {
-        const int t = L.closest[cell(L, ni[n], nj[n], nk[n])];
+        const int t = __ldcg(L.closest + cell(L, ni[n], nj[n], nk[n]));
         if (t < 0) continue;
         float d;
         if (t == last_t) d = last_d;  // same triangle, same arithmetic: identical value
@@ -213,6 +214,40 @@ __global__ void __launch_bounds__(128) k_ls_sweep(LevelSetDev L, int s, int di, 
     }
     L.phi[c0] = best;
     L.closest[c0] = best_t;
+}
+
+// One anti-diagonal plane of one sweep: threads over (j', k'), i' = s - j' - k'. Fallback path
+// (one launch per plane) when a cooperative launch is not available.
+__global__ void __launch_bounds__(128) k_ls_sweep(LevelSetDev L, int s, int di, int dj, int dk) {
+    const int jp = 1 + blockIdx.x * blockDim.x + threadIdx.x, kp = 1 + blockIdx.y;
+    if (jp > L.nj - 1 || kp > L.nk - 1) return;
+    const int ip = s - jp - kp;
+    if (ip < 1 || ip > L.ni - 1) return;
+    sweep_cell(L, ip, jp, kp, di, dj, dk);
+}
+
+// All 2 x 8 sweeps in ONE persistent cooperative kernel: the planes of a sweep are separated by
+// grid-wide barriers instead of kernel boundaries (~4.7 k planes for a 100^3 grid).
+__global__ void __launch_bounds__(256) k_ls_sweep_all(LevelSetDev L) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int dirs[8][3] = {{1, 1, 1}, {-1, -1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {-1, 1, 1}};
+    const int wj = L.nj - 1, wk = L.nk - 1;
+    const int s_max = (L.ni - 1) + wj + wk;
+    const long long gsize = (long long)gridDim.x * blockDim.x, gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int d = 0; d < 8; ++d)
+            for (int s = 3; s <= s_max; ++s) {
+                // (j', k') pairs of this plane: k' in [max(1, s - (ni-1) - wj), min(wk, s - 2)]
+                const int k_lo = max(1, s - (L.ni - 1) - wj), k_hi = min(wk, s - 2);
+                const long long span = (long long)(k_hi - k_lo + 1) * wj;
+                for (long long idx = gtid; idx < span; idx += gsize) {
+                    const int jp = 1 + (int)(idx % wj), kp = k_lo + (int)(idx / wj);
+                    const int ip = s - jp - kp;
+                    if (ip >= 1 && ip <= L.ni - 1) sweep_cell(L, ip, jp, kp, dirs[d][0], dirs[d][1], dirs[d][2]);
+                }
+                grid.sync();
+            }
 }
 
 __global__ void k_ls_sign(LevelSetDev L) {
@@ -268,15 +303,36 @@ sdfc_status sdfc_make_level_set3(sdfc_context* ctx, int n_tri, const uint32_t* t
         k_ls_band<<<n_tri, 128, 0, st>>>(L);
         k_ls_decode<<<nb, 256, 0, st>>>(L, n);
         ctx->launches += 3;
-        const dim3 sg((nj - 1 + 127) / 128, nk - 1);
-        static const int dirs[8][3] = {{1, 1, 1}, {-1, -1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {-1, 1, 1}};
-        const int s_max = (ni - 1) + (nj - 1) + (nk - 1);
-        for (int pass = 0; pass < 2; ++pass)
-            for (int d = 0; d < 8; ++d)
-                for (int s = 3; s <= s_max; ++s) {
-                    k_ls_sweep<<<sg, 128, 0, st>>>(L, s, dirs[d][0], dirs[d][1], dirs[d][2]);
-                    ctx->launches += 1;
-                }
+        // sweeps: one persistent cooperative kernel (grid-wide barrier per plane) when the device
+        // supports it, else one launch per plane
+        int coop = 0, per_sm = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ls_sweep_all, 256, 0);
+        bool done = false;
+        if (coop && per_sm > 0 && std::getenv("SDFC_SDFGEN_NO_COOP") == nullptr) {
+            // enough CTAs for the widest plane, never more than can be co-resident
+            const long long widest = (long long)(nj - 1) * (nk - 1);
+            const int want = (int)std::min<long long>((widest + 255) / 256, (long long)sms * std::min(per_sm, 2));
+            void* args[] = {(void*)&L};
+            if (cudaLaunchCooperativeKernel((void*)k_ls_sweep_all, dim3(std::max(want, 1)), dim3(256), args, 0, st) == cudaSuccess) {
+                done = true;
+                ctx->launches += 1;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (!done) {
+            const dim3 sg((nj - 1 + 127) / 128, nk - 1);
+            static const int dirs[8][3] = {{1, 1, 1}, {-1, -1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, -1}, {1, -1, -1}, {-1, 1, 1}};
+            const int s_max = (ni - 1) + (nj - 1) + (nk - 1);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int d = 0; d < 8; ++d)
+                    for (int s = 3; s <= s_max; ++s) {
+                        k_ls_sweep<<<sg, 128, 0, st>>>(L, s, dirs[d][0], dirs[d][1], dirs[d][2]);
+                        ctx->launches += 1;
+                    }
+        }
         k_ls_sign<<<dim3((nj + 127) / 128, nk), 128, 0, st>>>(L);
         ctx->launches += 1;
         e = cudaGetLastError();

@@ -111,7 +111,8 @@ def freefall(redmax, synth, tmp, args):
     mesh = redmax.SDFMesh(np.ascontiguousarray(V.T), np.ascontiguousarray(F.T.astype(np.int32)), args.dx)
     X = np.random.default_rng(5).uniform(-3.2, 3.2, size=(3, 4000))
     dist = np.asarray(mesh.distance(X))
-    np.savez(args.out, Q=Q, QD=QD, converged=conv, touched=np.array(touched), E_final=np.asarray(sim.get_body_E0i("part0")),
+    min_dist = float(mesh.min_distance(np.ascontiguousarray(X[:, :500])))
+    np.savez(args.out, sdfmesh_min_distance=min_dist, Q=Q, QD=QD, converged=conv, touched=np.array(touched), E_final=np.asarray(sim.get_body_E0i("part0")),
              t_forward=t_fwd, t_build=t_build, n_env_steps=args.steps, sdfmesh_distance=dist)
     print(f"{os.path.basename(os.path.abspath(args.module_dir))}: freefall {args.steps} steps in {t_fwd:.3f} s, build {t_build:.2f} s")
 

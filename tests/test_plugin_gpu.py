@@ -63,7 +63,9 @@ def test_reference_freefall_with_b200_ground_sdf_contact_and_sdfgen_matches_stoc
     b200, msg_b = _run(os.path.join(REF, "b200"), str(tmp_path / "b200.npz"), "free3d-exp", steps=300, scene="freefall")
     print(msg_s)
     print(msg_b)
-    assert np.array_equal(stock["sdfmesh_distance"], b200["sdfmesh_distance"])
+    assert np.array_equal(stock["sdfmesh_distance"], b200["sdfmesh_distance"])   # GPU sdfgen grid + GPU sampling (sdfc_sdf_distance)
+    assert float(stock["sdfmesh_min_distance"]) == float(b200["sdfmesh_min_distance"])
+    assert (stock["sdfmesh_distance"] < 1e30).any() and (stock["sdfmesh_distance"] > 1e30).any()  # inside and outside the box
     h = float(np.float32(1e-3))
     for s in range(stock["Q"].shape[1]):
         assert_state_close(stock["Q"][0, s], stock["QD"][0, s], b200["Q"][0, s], b200["QD"][0, s], h, f"step {s}")
