@@ -93,6 +93,7 @@ SIGNATURES = {
     "sdfc_sim_forward": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "sdfc_sim_get_status": (C.c_int, [C.c_void_p, c_uint8_p, c_uint8_p]),
     "sdfc_sim_get_poses": (C.c_int, [C.c_void_p, c_double_p]),
+    "sdfc_batch_get_skin_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "sdfc_sim_get_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
 

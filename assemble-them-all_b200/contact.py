@@ -420,6 +420,12 @@ class ContactBatch:
         check(self._lib.sdfc_batch_set_grounds(self._h, len(grounds), arr, b.ctypes.data_as(_lib.c_int32_p)))
         self.n_grounds = len(grounds)
 
+    def skin_stats(self):
+        """{words_culled, margins_used_up, rebuilds} of the stepper's detection culling (zeros when off)."""
+        s = (C.c_int64 * 3)()
+        check(self._lib.sdfc_batch_get_skin_stats(self._h, s))
+        return {"words_culled": int(s[0]), "margins_used_up": int(s[1]), "rebuilds": int(s[2])}
+
     def ground_active(self):
         """(n_envs, n_grounds) contact counts of the last evaluation."""
         n = np.empty((self.n_envs, self.n_grounds), dtype=np.int32)

@@ -60,6 +60,8 @@ sdfc_status batch_refresh(sdfc_batch* b) {
         b->seen_sdf_version[i] = b->pairs[i]->sdf->version;
     }
     SDFC_CUDA(cudaMemcpyAsync(b->d_pairs, host.data(), sizeof(PairDev) * b->n_pairs, cudaMemcpyHostToDevice, b->ctx->stream));
+    if (b->skin_on)   // margins were measured with the old grids / thresholds
+        SDFC_CUDA(cudaMemsetAsync(b->dev.skin_valid, 0, sizeof(int) * (size_t)b->n_envs * b->n_pairs, b->ctx->stream));
     SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));  // `host` goes out of scope
     return SDFC_OK;
 }
@@ -79,7 +81,10 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     BatchDev dev = b->dev;
     dev.env_mode = env_mode_dev;
     dev.env0 = env0; dev.env_count = env_count;
-    c->begin(0); launch_detect_mask(dev, E_dev, s); c->end();
+    c->begin(0);
+    if (b->skin_on) { launch_skin_decide(dev, E_dev, s); c->launches += 1; }
+    launch_detect_mask(dev, E_dev, s);
+    c->end();
     c->begin(1);
     if (env_mode_dev != nullptr) {
         launch_force(dev, E_dev, phi_dev, false, b->any_fric, b->any_damp, s);
@@ -109,6 +114,25 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
                                   cudaMemcpyDeviceToDevice, s));
     SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+sdfc_status batch_enable_skin(sdfc_batch* b) {
+    if (b->skin_on) return SDFC_OK;
+    const size_t ep = (size_t)b->n_envs * b->n_pairs;
+    sdfc_status st = dev_alloc(&b->d_skin_margin, (size_t)b->n_envs * b->dev.words_per_env);
+    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_pose, ep * 24);
+    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_int, ep * 4);
+    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_stats, (size_t)3);
+    if (st != SDFC_OK) return st;
+    SDFC_CUDA(cudaMemset(b->d_skin_int, 0, sizeof(int) * ep * 4));
+    SDFC_CUDA(cudaMemset(b->d_skin_stats, 0, sizeof(unsigned long long) * 3));
+    b->dev.skin_stats = b->d_skin_stats;
+    b->dev.skin_margin = b->d_skin_margin;
+    b->dev.skin_ref = b->d_skin_pose; b->dev.skin_cur = b->d_skin_pose + ep * 12;
+    b->dev.skin_mode = b->d_skin_int; b->dev.skin_valid = b->d_skin_int + ep;
+    b->dev.skin_fail = b->d_skin_int + 2 * ep; b->dev.skin_elig = b->d_skin_int + 3 * ep;
+    b->skin_on = true;
     return SDFC_OK;
 }
 }  // namespace sdfc_host
@@ -260,6 +284,29 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
     for (int a = 0; a < 3; ++a) { s->dev.mn[a] = min_box[a]; s->dev.mx[a] = max_box[a]; }
     s->dev.dx = dx; s->dev.dy = dy; s->dev.dz = dz; s->dev.col_th = col_th;
     s->dev.rdx = 1.0 / dx; s->dev.rdy = 1.0 / dy; s->dev.rdz = 1.0 / dz;  // IEEE division: correctly rounded
+    {   // Lipschitz bound of the trilinear interpolant (GridDev::lip), one pass over the grid on the device
+        unsigned long long* d_l2 = nullptr;
+        unsigned long long bits[2] = {0ull, ~0ull};
+        e = cudaMalloc((void**)&d_l2, sizeof(bits));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_l2, bits, sizeof(bits), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            launch_grid_lipschitz(s->d_g64, ni, nj, nk, dx, dy, dz, d_l2, ctx->stream);
+            ctx->launches += 1;
+            e = cudaMemcpyAsync(bits, d_l2, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_l2);
+        if (e != cudaSuccess) {
+            cudaFree(s->d_g64); cudaFree(s->d_c32); delete s;
+            return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_create: Lipschitz pass failed: ") + cudaGetErrorString(e));
+        }
+        double l2, bmin;
+        std::memcpy(&l2, &bits[0], sizeof(l2));
+        const unsigned long long kb = (bits[1] >> 63) ? (bits[1] & 0x7fffffffffffffffull) : ~bits[1];   // inverse of ordered_key
+        std::memcpy(&bmin, &kb, sizeof(bmin));
+        s->dev.lip = std::sqrt(l2);
+        s->dev.bmin = bmin;
+    }
     *out = s;
     return SDFC_OK;
 }
@@ -647,6 +694,7 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     cudaFree(b->d_pairs); cudaFree(b->d_tile_pair); cudaFree(b->d_tile_word0); cudaFree(b->d_mask);
     cudaFree(b->d_n_active); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
     cudaFree(b->d_E); cudaFree(b->d_phi); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
+    cudaFree(b->d_skin_margin); cudaFree(b->d_skin_pose); cudaFree(b->d_skin_int); cudaFree(b->d_skin_stats);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_nact) cudaFreeHost(b->h_nact);
@@ -662,6 +710,18 @@ sdfc_status sdfc_batch_set_grounds(sdfc_batch* b, int n_grounds, sdfc_ground* co
         SDFC_REQUIRE(grounds[i] && body[i] >= 0 && body[i] < b->n_bodies, "sdfc_batch_set_grounds: NULL ground or body out of range");
     SDFC_CUDA(cudaSetDevice(b->ctx->device));
     return sdfc_host::ground_set_create(b->ctx, b->n_envs, b->n_bodies, n_grounds, grounds, body, &b->gset);
+}
+
+sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* b, int64_t stats[3]) {
+    SDFC_REQUIRE(b && stats, "sdfc_batch_get_skin_stats: NULL argument");
+    stats[0] = stats[1] = stats[2] = 0;
+    if (!b->skin_on) return SDFC_OK;
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    unsigned long long c[3] = {0, 0, 0};
+    SDFC_CUDA(cudaMemcpyAsync(c, b->d_skin_stats, sizeof(c), cudaMemcpyDeviceToHost, b->ctx->stream));
+    SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    for (int i = 0; i < 3; ++i) stats[i] = (int64_t)c[i];
+    return SDFC_OK;
 }
 
 sdfc_status sdfc_batch_get_ground_active(sdfc_batch* b, int32_t* n_active_out) {

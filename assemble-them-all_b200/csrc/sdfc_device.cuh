@@ -42,6 +42,14 @@ struct GridDev {
     double dx, dy, dz;
     double rdx, rdy, rdz;  // RN(1/dx), RN(1/dy), RN(1/dz), computed on the host with an IEEE division
     double col_th;
+    // Lipschitz constant of the trilinear interpolant over the grid box: sqrt(Lx^2 + Ly^2 + Lz^2),
+    // L_axis = max |difference of axis-adjacent grid values| / spacing (host, at upload). Used by
+    // the stepper's conservative "skin" culling (sdfc_kernels.cu), never by the sampled values.
+    double lip;
+    // Smallest node value in the two outermost node layers: a lower bound of the interpolant on the
+    // faces of [mn, mx] (they lie inside those layers). A point outside the box has d = FLT_MAX; to
+    // become active it must first cross a face, so bmin + col_th is its margin.
+    double bmin;
 };
 
 // a / b, correctly rounded, given rb = RN(1/b). Markstein's sequence: a first

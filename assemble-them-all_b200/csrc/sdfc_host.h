@@ -116,6 +116,10 @@ struct sdfc_batch {
     double* h_in = nullptr;   // pinned: E then phi
     double* h_out = nullptr;  // pinned: fm, Km, Dm
     int32_t* h_nact = nullptr;
+    // optional temporal-coherence culling of the detection kernel (BatchDev::skin_*), switched on by the stepper
+    bool skin_on = false;
+    float* d_skin_margin = nullptr; double* d_skin_pose = nullptr; int* d_skin_int = nullptr;
+    unsigned long long* d_skin_stats = nullptr;
 };
 
 
@@ -128,6 +132,8 @@ namespace sdfc_host {
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
                       bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev,
                       int env0 = 0, int env_count = -1);
+// Allocates the skin state of a batch and switches the culling on (idempotent).
+sdfc_status batch_enable_skin(sdfc_batch* b);
 }  // namespace sdfc_host
 
 namespace sdfc_host {

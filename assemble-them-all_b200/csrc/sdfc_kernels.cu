@@ -47,10 +47,56 @@ __device__ __forceinline__ double detect_point(const GridDev& G, const double* R
     return __dadd_rn(query_sdf<F32>(G, x[0], x[1], x[2], false, nullptr), G.col_th);  // BodySDFObj.cpp:212
 }
 
+// Skin state of this CTA's (env, pair): displacement of the relative pose since the reference.
+struct SkinCta {
+    bool on, rebuild;
+    unsigned long long* stats;
+    float out_margin;   // bmin + col_th rounded down, or -1 when that is not positive
+    double dR[9], dp[3], fro, lip;
+    float* margin;   // this pair's words of this environment
+    int* fail;       // counters of (env, pair)
+    int* elig;
+};
+
+// One thread per (env, pair): relative pose now, decide whether the margins are rebuilt.
+__global__ void k_skin_decide(BatchDev B, const double* __restrict__ E) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B.env_count * B.n_pairs) return;
+    const int env = B.env0 + idx / B.n_pairs, pair = idx % B.n_pairs;
+    if (B.env_mode != nullptr && B.env_mode[env] == 0) return;
+    const size_t ep = (size_t)env * B.n_pairs + pair;
+    const PairDev& pd = B.pairs[pair];
+    const double* E1 = E + ((size_t)env * B.n_bodies + pd.body_a) * 16;
+    const double* E2 = E + ((size_t)env * B.n_bodies + pd.body_b) * 16;
+    double cur[12];
+    for (int r = 0; r < 3; ++r) {          // R_rel = R2^T R1, p_rel = R2^T (p1 - p2); column-major poses
+        for (int c = 0; c < 3; ++c)
+            cur[3 * r + c] = E2[4 * r] * E1[4 * c] + E2[4 * r + 1] * E1[4 * c + 1] + E2[4 * r + 2] * E1[4 * c + 2];
+        cur[9 + r] = E2[4 * r] * (E1[12] - E2[12]) + E2[4 * r + 1] * (E1[13] - E2[13]) + E2[4 * r + 2] * (E1[14] - E2[14]);
+    }
+    int mode = 0;
+    if (!B.skin_valid[ep]) mode = 1;
+    else if (4 * B.skin_fail[ep] > B.skin_elig[ep]) mode = 1;   // > 25 % of the margins are used up
+    B.skin_fail[ep] = 0;
+    for (int i = 0; i < 12; ++i) B.skin_cur[ep * 12 + i] = cur[i];
+    if (mode) {
+        for (int i = 0; i < 12; ++i) B.skin_ref[ep * 12 + i] = cur[i];
+        B.skin_valid[ep] = 1;
+        B.skin_elig[ep] = 0;
+        atomicAdd(B.skin_stats + 2, 1ull);
+    }
+    B.skin_mode[ep] = mode;
+}
+
+void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream) {
+    const int n = B.env_count * B.n_pairs;
+    k_skin_decide<<<(n + 127) / 128, 128, 0, stream>>>(B, E);
+}
+
 template <bool F32>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
-                                            int* s_count) {
+                                            int* s_count, const SkinCta& sk) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifndef SDFC_DETECT_U
 #define SDFC_DETECT_U 1
@@ -65,7 +111,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     // warps of a CTA finish together even when the contact region covers a few words only.
     if (threadIdx.x < kDetectTileWords) {
         const int w = word0 + threadIdx.x;
-        bool keep = false;
+        bool keep = false, culled = false, used_up = false, elig_out = false;
         if (w < pd.n_words) {
             const double* sp = pd.wsphere + 4 * (size_t)w;
             double cw[3], cl[3];
@@ -75,7 +121,37 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
             keep = cl[0] >= pd.grid.mn[0] - r && cl[0] <= pd.grid.mx[0] + r &&
                    cl[1] >= pd.grid.mn[1] - r && cl[1] <= pd.grid.mx[1] + r &&
                    cl[2] >= pd.grid.mn[2] - r && cl[2] <= pd.grid.mx[2] + r;
+            if (sk.on) {
+                if (sk.rebuild) {
+                    // every point outside the box at the reference pose: they all carry the outside margin
+                    if (!keep) { sk.margin[w] = sk.out_margin; elig_out = sk.out_margin >= 0.f; }
+                } else if (keep) {
+                    const float m = sk.margin[w];
+                    if (m >= 0.f) {
+                        // displacement bound of every point of the word since the reference pose:
+                        // centre moved by |dR c + dp|, the rest of the sphere by at most |dR|_F r
+                        const double cx = __ldg(sp), cy = __ldg(sp + 1), cz = __ldg(sp + 2);
+                        const double ux = sk.dR[0] * cx + sk.dR[1] * cy + sk.dR[2] * cz + sk.dp[0];
+                        const double uy = sk.dR[3] * cx + sk.dR[4] * cy + sk.dR[5] * cz + sk.dp[1];
+                        const double uz = sk.dR[6] * cx + sk.dR[7] * cy + sk.dR[8] * cz + sk.dp[2];
+                        const double delta = sqrt(ux * ux + uy * uy + uz * uz) + sk.fro * __ldg(sp + 3);
+                        if ((double)m - sk.lip * delta * (1.0 + 1e-9) > 1e-9) { keep = false; culled = true; }  // provably no contact
+                        else used_up = true;
+                    }
+                }
+            }
             if (!keep) mask_row[pd.word_offset + w] = 0u;  // culled words: empty mask
+        }
+        if (sk.on && sk.rebuild) {
+            const unsigned eb = __ballot_sync(0xffffffffu, elig_out);
+            if (lane == 0 && eb) atomicAdd(sk.elig, __popc(eb));
+        }
+        if (sk.on && !sk.rebuild) {   // warp-uniform
+            const unsigned cb = __ballot_sync(0xffffffffu, culled), ub = __ballot_sync(0xffffffffu, used_up);
+            if (lane == 0) {
+                if (cb) atomicAdd(sk.stats, (unsigned long long)__popc(cb));
+                if (ub) { atomicAdd(sk.fail, __popc(ub)); atomicAdd(sk.stats + 1, (unsigned long long)__popc(ub)); }
+            }
         }
         const unsigned live = __ballot_sync(0xffffffffu, keep);
         // kDetectTileWords == 64: warps 0 and 1 hold the two ballots
@@ -109,10 +185,24 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (ws[u] < 0) continue;  // warp-uniform
-            bool act = false;
-            if (inr[u]) act = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]) < 0.;
+            double d = 1e300;
+            if (inr[u]) d = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]);
+            const bool act = inr[u] && d < 0.;
             const unsigned m = __ballot_sync(0xffffffffu, act);
             if (lane == 0) { mask_row[pd.word_offset + ws[u]] = m; cnt += __popc(m); }
+            if (sk.on && sk.rebuild) {
+                // margin of the word at the reference pose: smallest d of its points; a point outside the
+                // box (d = FLT_MAX + col_th) carries the outside margin: before it can be active it has to
+                // cross a face of the box, where the interpolant is >= GridDev::bmin
+                double dm = inr[u] ? (d > 1e37 ? (double)sk.out_margin : d) : 1e300;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+                if (lane == 0) {
+                    const bool ok = dm > 0.0;
+                    sk.margin[ws[u]] = ok ? __double2float_rd(dm) : -1.f;
+                    if (ok) atomicAdd(sk.elig, 1);
+                }
+            }
         }
     }
     if (lane == 0 && cnt) atomicAdd(s_count, cnt);
@@ -138,12 +228,33 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
         if (threadIdx.x == 0) s_count = 0;
     }
     __syncthreads();
+    __shared__ SkinCta sk;
     if (threadIdx.x < 12) stage_pose(E, B.n_bodies, env, pd.body_a, R1, p1, threadIdx.x);
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
+    else if (threadIdx.x == 64) {
+        sk.on = B.skin_margin != nullptr;
+        if (sk.on) {
+            const size_t ep = (size_t)env * B.n_pairs + pair;
+            sk.rebuild = B.skin_mode[ep] != 0;
+            double f2 = 0.0;
+            for (int i = 0; i < 12; ++i) {
+                const double dlt = B.skin_cur[ep * 12 + i] - B.skin_ref[ep * 12 + i];
+                if (i < 9) { sk.dR[i] = dlt; f2 += dlt * dlt; } else sk.dp[i - 9] = dlt;
+            }
+            sk.fro = sqrt(f2);
+            sk.lip = pd.grid.lip;
+            const double om = pd.grid.bmin + pd.grid.col_th;
+            sk.out_margin = om > 0.0 ? __double2float_rd(fmin(om, 1e30)) : -1.f;
+            sk.margin = B.skin_margin + (size_t)env * B.words_per_env + pd.word_offset;
+            sk.stats = B.skin_stats;
+            sk.fail = B.skin_fail + ep;
+            sk.elig = B.skin_elig + ep;
+        }
+    }
     __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
-    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count);
-    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count);
+    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
+    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
 }
@@ -363,6 +474,58 @@ void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, c
     const size_t n = (size_t)ni * nj * nk;
     const int blocks = (int)max((size_t)1, min((n + 255) / 256, (size_t)148 * 16));
     k_build_cells<<<blocks, 256, 0, stream>>>(g32, ni, nj, nk, out);
+}
+
+// Squared Lipschitz bound of the trilinear interpolant (GridDev::lip): inside a cell each gradient
+// component is a convex combination of the cell's four edge differences along that axis, so
+// |grad|^2 <= sum_axis (largest |edge difference| / spacing)^2; the grid-wide bound is the
+// maximum over cells. Upper neighbours are clamped like the sampler's (BodySDFObj.cpp:137-140).
+// Non-negative doubles order like their bit patterns, hence the integer atomicMax (out[0]).
+// out[1]: smallest node value in the two outermost node layers (GridDev::bmin) as an order-preserving
+// key (ordered_key); the faces of [min_box, max_box] lie inside those layers (BodySDFObj.cpp:66-70).
+__device__ __forceinline__ unsigned long long ordered_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void k_grid_lipschitz(const double* __restrict__ g, int ni, int nj, int nk, double rdx, double rdy, double rdz,
+                                 unsigned long long* __restrict__ out) {
+    const size_t n = (size_t)ni * nj * nk, stride = (size_t)gridDim.x * blockDim.x;
+    double best = 0.0, bmin = 1e300;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const int i = (int)(c % ni), j = (int)((c / ni) % nj), k = (int)(c / ((size_t)ni * nj));
+        const int i1 = min(i + 1, ni - 1), j1 = min(j + 1, nj - 1), k1 = min(k + 1, nk - 1);
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            v[q] = g[(size_t)((q & 1) ? i1 : i) + (size_t)ni * ((size_t)((q & 2) ? j1 : j) + (size_t)nj * ((q & 4) ? k1 : k))];
+        const double ex = fmax(fmax(fabs(v[1] - v[0]), fabs(v[3] - v[2])), fmax(fabs(v[5] - v[4]), fabs(v[7] - v[6]))) * rdx;
+        const double ey = fmax(fmax(fabs(v[2] - v[0]), fabs(v[3] - v[1])), fmax(fabs(v[6] - v[4]), fabs(v[7] - v[5]))) * rdy;
+        const double ez = fmax(fmax(fabs(v[4] - v[0]), fabs(v[5] - v[1])), fmax(fabs(v[6] - v[2]), fabs(v[7] - v[3]))) * rdz;
+        double l2 = ex * ex + ey * ey + ez * ez;
+        bool finite = true;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) finite = finite && isfinite(v[q]);
+        if (!finite || !isfinite(l2)) l2 = 1e300;   // NaN / inf grids: never cull
+        best = fmax(best, l2);
+        if (i <= 1 || i >= ni - 2 || j <= 1 || j >= nj - 2 || k <= 1 || k >= nk - 2) bmin = finite ? fmin(bmin, v[0]) : -1e300;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+        bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (best > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(best));
+        atomicMin(out + 1, ordered_key(bmin));
+    }
+}
+
+void launch_grid_lipschitz(const double* g64, int ni, int nj, int nk, double dx, double dy, double dz,
+                           unsigned long long* out, cudaStream_t stream) {
+    const size_t n = (size_t)ni * nj * nk;
+    const int blocks = (int)max((size_t)1, min((n + 255) / 256, (size_t)148 * 16));
+    k_grid_lipschitz<<<blocks, 256, 0, stream>>>(g64, ni, nj, nk, 1.0 / dx, 1.0 / dy, 1.0 / dz, out);
 }
 
 // Self-test of exact_div(): n pseudo-random numerators (full 52-bit mantissas,

@@ -70,10 +70,26 @@ struct BatchDev {
     // disjoint ranges ("lanes") on separate streams so that one lane's latency-bound
     // assembly / solve kernels overlap another lane's contact kernels.
     int env0, env_count;
+    // Optional temporal-coherence state of the stepper ("skin", nullptr = off). For every
+    // (env, pair) a reference relative pose of the contact body in the SDF frame, and for every
+    // 32-point word the smallest d = sdf + col_th its points had at that pose (or -1 when a point
+    // was outside the grid box). While L * (largest displacement of the word since the
+    // reference) stays below that margin no point of the word can have d < 0, so the word is
+    // skipped with an empty mask - exactly what a full evaluation would produce.
+    float* skin_margin;   // [n_envs][words_per_env]
+    double* skin_ref;     // [n_envs][n_pairs][12]  R_rel (row-major) | p_rel at the last rebuild
+    double* skin_cur;     // [n_envs][n_pairs][12]  same for the current evaluation
+    int* skin_mode;       // [n_envs][n_pairs]      1 = rebuild margins in this evaluation
+    int* skin_valid;      // [n_envs][n_pairs]      reference pose and margins exist
+    int* skin_fail;       // [n_envs][n_pairs]      eligible words that had to be evaluated last time
+    int* skin_elig;       // [n_envs][n_pairs]      words with a margin
+    unsigned long long* skin_stats;   // [3] running totals: words culled, words whose margin was used up, rebuilds
 };
 
 // launches (all asynchronous on `stream`)
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream);
+// skin bookkeeping of one evaluation (before launch_detect_mask when B.skin_margin != nullptr)
+void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream);
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
                   cudaStream_t stream);
 // Sums the split partials in fixed order into per-pair blocks (overwrite):
@@ -93,6 +109,9 @@ void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const dou
                          cudaStream_t stream);
 void launch_min_reduce(const double* v, int64_t n, double* out_scalar, double* scratch, cudaStream_t stream);
 void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, cudaStream_t stream);
+// *out (zeroed by the caller) = bit pattern of the squared Lipschitz bound of the interpolant (GridDev::lip)
+void launch_grid_lipschitz(const double* g64, int ni, int nj, int nk, double dx, double dy, double dz,
+                           unsigned long long* out, cudaStream_t stream);
 void launch_selftest_exact_div(int64_t n, uint64_t seed, double b, unsigned long long* mismatches, cudaStream_t stream);
 void launch_aos_to_soa(const double* aos, int64_t n, double* x, double* y, double* z, cudaStream_t stream);
 

@@ -25,6 +25,10 @@
 #include <cmath>
 #include <cstring>
 
+#ifndef SDFC_SKIN_DEFAULT
+#define SDFC_SKIN_DEFAULT 1
+#endif
+
 namespace sdfc {
 
 constexpr int kCapR = 12;    // reduced dofs per environment (largest instantiation)
@@ -897,6 +901,10 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     A(dev_alloc(&s->d_fext, (size_t)ne * nb * 6));
     A(dev_alloc(&s->d_unfinished, (size_t)sdfc_sim::kMaxLanes));
     A(dev_alloc(&s->d_counters, (size_t)4));
+    {   // SDFC_SKIN=0/1: temporal-coherence culling of the detection kernel (BatchDev::skin_*); results are identical
+        const char* skin_env = std::getenv("SDFC_SKIN");
+        if (skin_env ? std::atoi(skin_env) != 0 : (SDFC_SKIN_DEFAULT != 0)) A(sdfc_host::batch_enable_skin(batch));
+    }
     if (st == SDFC_OK) {
         // SDFC_SIM_LANES overrides the lane count (1 = everything on the context's stream)
         const char* lanes_env = std::getenv("SDFC_SIM_LANES");

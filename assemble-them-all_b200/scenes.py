@@ -190,10 +190,17 @@ class RolloutScene:
     def queries_per_eval(self):
         return self.n_envs * sum(len(self.bodies[a].points) for a, _ in self.pairs)
 
-    def upload(self, ctx):
+    def upload(self, ctx, shared=None):
+        """shared: optional {body name: (SdfGrid, ContactPoints)} of this context, filled on demand, so that
+        several scenes over the same parts (C4 candidates) keep one device copy of every grid / point set."""
         from . import contact
-        sdf = [contact.SdfGrid.from_spec(ctx, b.grid) for b in self.bodies]
-        pts = [contact.ContactPoints(ctx, b.points) for b in self.bodies]
+        if shared is None:
+            shared = {}
+        for b in self.bodies:
+            if b.name not in shared:
+                shared[b.name] = (contact.SdfGrid.from_spec(ctx, b.grid), contact.ContactPoints(ctx, b.points))
+        sdf = [shared[b.name][0] for b in self.bodies]
+        pts = [shared[b.name][1] for b in self.bodies]
         pairs = [contact.ForceGeneralSDFContact(ctx, pts[a], sdf[b], self.kn, self.kt, self.mu, self.damping,
                                                 index_contact=6 * a, index_sdf=6 * b) for a, b in self.pairs]
         batch = contact.ContactBatch(ctx, self.n_envs, len(self.bodies), pairs, [a for a, _ in self.pairs],
@@ -256,6 +263,67 @@ def c1_freefall_rollouts(n_envs=1024, n_vertices=10000, seed=synth.MESH_SEED, sd
     return RolloutScene(bodies, [(0, 1), (1, 0)], q0, qd0, np.zeros((n_envs, 2, 6)), float(np.float32(1e-3)),
                         np.array([0.0, 0.0, -9.8]), kn=1e5, kt=1e3, mu=0.0, damping=0.0, frame_skip=steps, grounds=grounds,
                         label=f"C1 free fall, {n_envs} drops x {steps} steps, 2x~{n_vertices} contact pts, ground + SDF contact, gravity 9.8")
+
+
+def c4_bodies(nx=4, ny=5, n_parts=20, n_vertices=10000, sdf_dx=0.05, col_th=0.01):
+    """The C4 assembly (synth.peg_array): a perforated plate (part 0) and n_parts - 1 pegs seated in its
+    square through-holes. Body frames are the axis-aligned frames at the centres of mass (all parts are
+    symmetric about them, so the products of inertia vanish); grids are analytic box / plate distances
+    laid out and rounded to fp32 as BodySDFObj::precompute_SDF does (BodySDFObj.cpp:59-83)."""
+    parts = synth.peg_array(nx=nx, ny=ny, n_vertices=n_vertices, n_parts=n_parts)
+    col_th = float(np.float32(col_th))
+    sdf_dx = float(np.float32(sdf_dx))
+    pitch, hole, peg = 2.0, 1.1, 1.0
+    plate = np.array([pitch * nx + 1.0, pitch * ny + 1.0, 2.0])
+    s = 10.0 / plate.max()
+    centers = np.array([((i - (nx - 1) / 2) * pitch, (j - (ny - 1) / 2) * pitch) for j in range(ny) for i in range(nx)]) * s
+    half_plate, half_hole, half_peg = 0.5 * plate * s, 0.5 * hole * s * np.ones(2), 0.5 * s * np.array([peg, peg, 4.0])
+
+    def sd_plate(p):
+        holes = np.min(np.stack([_box_sdf(p[:, :2] - c, half_hole) for c in centers]), axis=0)
+        return np.maximum(_box_sdf(p, half_plate), -holes)
+
+    def sd_peg(p):
+        return _box_sdf(p, half_peg)
+
+    m_pl, I_pl = _box_inertia(2 * half_plate)
+    m_h, I_h = _box_inertia((hole * s, hole * s, plate[2] * s))
+    for cx, cy in centers:   # parallel-axis theorem, hole by hole
+        I_pl = I_pl - (I_h + m_h * np.array([cy * cy, cx * cx, cx * cx + cy * cy]))
+        m_pl -= m_h
+    m_pg, I_pg = _box_inertia(2 * half_peg)
+    out = []
+    for pid in sorted(parts, key=int):
+        V, _ = parts[pid]
+        c = 0.5 * (V.min(0) + V.max(0))
+        Vb = V - c
+        fn, m, I3 = (sd_plate, m_pl, I_pl) if pid == "0" else (sd_peg, m_pg, I_pg)
+        grid = analytic_grid(fn, Vb.min(0), Vb.max(0), sdf_dx, col_th)
+        out.append(SceneBody(f"part{pid}", np.ascontiguousarray(Vb), grid, synth.make_E(np.eye(3), c), float(m),
+                             np.concatenate([I3, [m, m, m]])))
+    return out
+
+
+def c4_candidate_rollouts(bodies, move, force_mag=100.0, joint_type="translational"):
+    """C4: the six axis-direction rollouts of ONE candidate removal (run_multi_plan.py:84-126 tries every
+    remaining part with a BFS plan whose first stage is these actions). Body 0 of the returned scene is the
+    candidate `move` (index into `bodies`), the others stay fixed in id order; 2 contact forces per still
+    part in the planner XML's order (run_joint_plan.py:169-173)."""
+    order = [move] + [i for i in range(len(bodies)) if i != move]
+    bs = []
+    for k, i in enumerate(order):
+        b = bodies[i]
+        bs.append(SceneBody(b.name, b.points, b.grid, b.rest_E, b.mass, b.inertia, joint_type if k == 0 else "fixed"))
+    pairs = []
+    for k in range(1, len(bs)):
+        pairs += [(0, k), (k, 0)]
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64)
+    nr = 3 if joint_type == "translational" else 6
+    f = np.zeros((6, len(bs), 6))
+    f[:, 0, 3:] = dirs * force_mag
+    return RolloutScene(bs, pairs, np.zeros((6, nr)), np.zeros((6, nr)), f, float(np.float32(1e-3)),
+                        np.array([0.0, 0.0, 1e-12]),
+                        label=f"C4 {len(bs)}-part plate + pegs, candidate {bodies[move].name}, 6 axis rollouts x frame_skip 100")
 
 
 def sweep_scene(n_points, grid_n, active_frac=0.05, seed=synth.SWEEP_SEED):

@@ -368,6 +368,87 @@ def rot_leg(ctx, args, torch, stream):
     return out
 
 
+def c4_leg(args, torch, local, cpu):
+    """env-steps/s on C4 (BASELINE.json configs[3]): every candidate removal of the 20-part assembly
+    (each part x 6 axis directions = 120 rollouts x frame_skip 100; run_multi_plan.py:84-126). A candidate
+    has its own joint layout and 38 contact forces, so it is its own batched simulation; the 20 simulations
+    are driven concurrently by a few host threads, each with its own library context (stream) and one device
+    copy of the 20 grids / point sets. Timed by wall clock between two device synchronisations."""
+    import threading
+    from assemble_them_all_b200 import contact, scenes
+    bodies = scenes.c4_bodies()
+    n_workers = 4
+    ctxs = [contact.Context(local) for _ in range(n_workers)]
+    shared = [dict() for _ in range(n_workers)]
+    sims = []
+    for m in range(len(bodies)):
+        w = m % n_workers
+        rs = scenes.c4_candidate_rollouts(bodies, m)
+        sim, *keep = rs.upload(ctxs[w], shared[w])
+        sims.append((w, rs, sim, keep))
+
+    def prepare():
+        for _, rs, sim, _ in sims:
+            sim.reset(rs.q0, rs.qdot0)
+            sim.set_body_external_force(0, rs.f_ext[:, 0])
+
+    def drive(w):
+        for ww, rs, sim, _ in sims:
+            if ww == w:
+                sim.forward(rs.frame_skip)
+
+    times = []
+    for rep in range(3):
+        prepare()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=drive, args=(w,)) for w in range(n_workers)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        if rep:
+            times.append(time.perf_counter() - t0)
+    n_roll = sum(rs.n_envs for _, rs, _, _ in sims)
+    n = sims[0][1].frame_skip
+    st = [sim.stats() for _, _, sim, _ in sims]
+    evals = sum(x["deriv_env_evals"] + x["value_env_evals"] for x in st) / max(1, sum(x["env_steps"] for x in st))
+    q_env = sims[1][1].queries_per_eval // sims[1][1].n_envs
+    # a removal "succeeds" in this leg when the part has moved its own height out along the action
+    moved = [float(np.max(np.abs(sim.get_q()), axis=1).max()) for _, _, sim, _ in sims]
+    out = {"value": n_roll * n / float(np.mean(times)), "unit": "env-steps/s",
+           "workload": f"C4 {len(bodies)}-part plate + pegs (~10000 contact pts each), {len(sims)} candidate removals x 6 "
+                       f"axis rollouts x frame_skip {n}, 38 contact forces per rollout",
+           "rollouts": n_roll, "ms_per_forward": 1e3 * float(np.mean(times)), "host_threads": n_workers,
+           "queries_per_env_eval": int(q_env), "contact_evals_per_env_step": evals,
+           "converged": int(sum(int(sim.is_converged().sum()) for _, _, sim, _ in sims)),
+           "touched": int(sum(int(sim.get_contact_history().any(axis=1).sum()) for _, _, sim, _ in sims)),
+           "largest_displacement_per_candidate": [round(x, 3) for x in moved],
+           "timing": "wall clock between device synchronisations (20 simulations on 4 streams)"}
+    if cpu and have_ref():
+        # the reference's Simulation::forward on the same candidate (inputs injected), one rollout, 40 steps (contact from step ~27)
+        from oracle import ref_scene
+        m, e, k = 7, 0, 40
+        w, rs, sim, _ = sims[m]
+        sim.reset(rs.q0, rs.qdot0)
+        sim.set_body_external_force(0, rs.f_ext[:, 0])
+        Q, _ = sim.forward(k, trajectory=True)
+        p = ref_scene.make_probe(rs.bodies, rs.kn, rs.kt, rs.mu, rs.damping, inject_frames=True)
+        t_ref, q_ref, _ = ref_scene.rollout(p, rs.q0[e], rs.qdot0[e], rs.f_ext[e, 0], k)
+        err = float(np.max(np.abs(q_ref - Q[-1, e])) / max(1e-300, np.max(np.abs(q_ref))))
+        if err > 1e-9:
+            raise SystemExit(f"PARITY FAILURE: C4 candidate {m} rollout {e}: q after {k} steps differs from the reference by {err:.3e}")
+        out["cpu_baseline"] = {"value": k / t_ref, "unit": "env-steps/s", "cores": 1, "kind": "reference",
+                               "sample": f"candidate part{m}, rollout +x, {k} steps on one core ({t_ref:.1f} s); GPU q after "
+                                         f"{k} steps: rel err {err:.1e}"}
+    for _, _, sim, _ in sims:
+        sim.close()
+    for c in ctxs:
+        c.close()
+    return out
+
+
 def hbm_regime_leg(ctx, torch, stream, dev, peak, n_points=30_000_000, grid_n=512):
     """The same detection kernel where it IS HBM-bound (C5 of BASELINE.json): n_points uniform random points
     against a 512^3 grid (4.3 GB of fp32 cell records, 34x the L2), one environment. The headline entry uses
@@ -502,6 +583,7 @@ def env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream):
         "queries_per_sec_while_stepping": world * (d["deriv_env_evals"] + d["value_env_evals"]) *
         (rs.queries_per_eval // rs.n_envs) / t_dev,
         "gpu_launches_per_forward": launches / reps,
+        "detection_culling": batch.skin_stats(),
     }
     # the planner's only exchange: one all_gather of per-rollout outcome records (NCCL), in rollout order
     from assemble_them_all_b200 import sharding
@@ -672,6 +754,7 @@ def run_ours(args):
     if rank == 0 and not args.skip_env_steps:
         extras["c1_freefall"] = c1_leg(ctx, args, torch, stream)
         extras["rotational_rollouts"] = rot_leg(ctx, args, torch, stream)
+        extras["c4_candidate_removals"] = c4_leg(args, torch, local, cpu=(world == 1 and not args.no_cpu_baseline))
         extras["sdf_build"] = sdf_build_leg(ctx, cpu=(world == 1 and not args.no_cpu_baseline))
         extras["roofline_hbm_regime"] = hbm_regime_leg(ctx, torch, stream, dev, measured_hbm_peak()[0])
 

@@ -104,3 +104,42 @@ def test_c3_rotational_rollouts_100k_points(cuda_ctx):
     assert worst <= 1e-9
     assert int(hist.sum()) == touched and touched >= 2
     sim.close()
+
+
+def test_c4_twenty_part_candidate_removals(cuda_ctx):
+    """C4 (BASELINE.json configs[3]) at full size: plate + 19 pegs, ~10 000 contact points per part,
+    38 contact forces per rollout (~3.9e5 detection queries per evaluation). Candidates: an interior
+    peg (all six axis actions) and the plate itself (+x, +z); per-step q of every rollout against the
+    reference's Simulation::forward on the same injected inputs, contact-history flags equal."""
+    from assemble_them_all_b200 import scenes
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    bodies = scenes.c4_bodies()
+    assert len(bodies) == 20 and all(9000 <= len(b.points) <= 12000 for b in bodies)
+    steps = 45                                              # contact starts around step 27 (clearance 0.045, col_th 0.01)
+    shared = {}
+    report = []
+    for move, envs in ((7, range(6)), (0, (0, 4))):
+        rs = scenes.c4_candidate_rollouts(bodies, move)
+        assert len(rs.pairs) == 38
+        sim, *keep = rs.upload(cuda_ctx, shared)
+        sim.reset(rs.q0, rs.qdot0)
+        sim.set_body_external_force(0, rs.f_ext[:, 0])
+        q, _ = sim.forward(steps, trajectory=True)
+        hist = sim.get_contact_history()
+        p = ref_scene.make_probe(rs.bodies, rs.kn, rs.kt, rs.mu, rs.damping, inject_frames=True)
+        worst, t_ref, touched = 0.0, 0.0, 0
+        for e in envs:
+            t, qf, qdf, Q, QD = ref_scene.rollout(p, rs.q0[e], rs.qdot0[e], rs.f_ext[e, 0], steps, trajectory=True)
+            t_ref += t
+            worst = max(worst, rel_err(Q, q[:, e]))
+            ref_touch = len(p.get_contact_bodies("part0")) > 0
+            assert bool(hist[e].any()) == ref_touch
+            touched += ref_touch
+        report.append(f"candidate {bodies[move].name}: {len(list(envs))} rollouts x {steps} steps, reference {t_ref:.1f} s "
+                      f"({len(list(envs)) * steps / t_ref:.1f} env-steps/s, 1 core), max rel err of q {worst:.2e}, touched {touched}")
+        assert worst <= 1e-9
+        assert touched >= 1
+        sim.close()
+    print("\nC4: " + "; ".join(report))

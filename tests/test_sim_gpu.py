@@ -201,3 +201,46 @@ def test_lanes_and_mixed_mode_rounds_do_not_change_results(cuda_ctx):
     assert evals[0][0] > 768 * 60          # more than one Newton iteration per step somewhere: phases diverged
     for q, qd in outs[1:]:
         assert np.array_equal(q, outs[0][0]) and np.array_equal(qd, outs[0][1])
+
+
+@pytest.mark.parametrize("joint_type,frame_skip", [("translational", 100), ("free3d-exp", 80)])
+def test_skin_culling_does_not_change_results(cuda_ctx, joint_type, frame_skip):
+    """SDFC_SKIN=1 lets the detection kernel skip a 32-point word while Lipschitz x (displacement of the
+    word since the margins were measured) stays below the word's smallest d (BatchDev::skin_*). The cull
+    is conservative, so masks, contact counts and therefore every state must be BIT-identical to the
+    full evaluation (SDFC_SKIN=0), for rollouts that slide freely, hit the wall and stay in contact."""
+    import os
+    from assemble_them_all_b200 import scenes
+    rs = scenes.c2_planner_rollouts(n_envs=192, n_vertices=1500, sdf_dx=0.1, joint_type=joint_type)
+    rs.q0[:, 2] = np.linspace(0.0, 2.5, 192)
+    old = os.environ.get("SDFC_SKIN")
+    outs = []
+    try:
+        for skin in ("0", "1"):
+            os.environ["SDFC_SKIN"] = skin
+            sim, batch, *keep = rs.upload(cuda_ctx)
+            sim.reset(rs.q0, rs.qdot0)
+            for b in range(len(rs.bodies)):
+                sim.set_body_external_force(b, rs.f_ext[:, b])
+            Q, QD = sim.forward(frame_skip, trajectory=True)
+            st = sim.stats()
+            hist = sim.get_contact_history()
+            # a second forward from a reset: margins measured at the END of the first one are still valid state
+            sim.reset(rs.q0, rs.qdot0)
+            Q2, _ = sim.forward(20, trajectory=True)
+            outs.append((Q, QD, Q2, hist, sim.is_converged(),
+                         (st["deriv_env_evals"], st["value_env_evals"], st["rounds"]), batch.skin_stats()))
+            sim.close()
+    finally:
+        if old is None:
+            os.environ.pop("SDFC_SKIN", None)
+        else:
+            os.environ["SDFC_SKIN"] = old
+    a, b = outs
+    assert a[3].any() and not a[3].all()
+    assert a[5] == b[5]
+    assert a[6] == {"words_culled": 0, "margins_used_up": 0, "rebuilds": 0}
+    print("\nskin:", b[6], "of", (a[5][0] + a[5][1]) * sum(-(-len(rs.bodies[p].points) // 32) for p, _ in rs.pairs), "word visits")
+    assert b[6]["words_culled"] > 0 and b[6]["rebuilds"] >= 192 * 2
+    for x, y in zip(a[:5], b[:5]):
+        assert np.array_equal(x, y)

@@ -41,3 +41,28 @@ def test_planner_xml_mentions_both_directions():
     xml = synth.planner_xml("/tmp/x", "0", ["1", "2"])
     assert xml.count("<general_SDF_contact general_body=") == 4
     assert 'timestep="1e-3"' in xml and 'col_th="0.01"' in xml
+
+
+def test_c4_scene_bodies_and_candidate_layout():
+    """C4 scene (scenes.c4_bodies / c4_candidate_rollouts): analytic grids agree with the meshes
+    (every vertex lies on the zero level set up to the grid's interpolation error), mass properties
+    follow from the volumes, and a candidate's contact forces come in the planner XML's order."""
+    from assemble_them_all_b200 import scenes
+    from oracle import sdfc_oracle as O
+    O.build()
+    bodies = scenes.c4_bodies(nx=2, ny=2, n_parts=5, n_vertices=500, sdf_dx=0.1)
+    assert [b.name for b in bodies] == [f"part{i}" for i in range(5)]
+    for b in bodies:
+        g = O.Grid.from_dict({"ni": b.grid.ni, "nj": b.grid.nj, "nk": b.grid.nk, "min_box": b.grid.min_box,
+                              "max_box": b.grid.max_box, "dx": b.grid.dx, "dy": b.grid.dy, "dz": b.grid.dz,
+                              "col_th": 0.0, "grid": b.grid.grid})
+        assert np.abs(O.query_sdf(g, b.points)).max() < 0.1
+        assert np.array_equal(b.grid.grid.astype(np.float32).astype(np.float64), b.grid.grid)
+    s = 10.0 / 5.0
+    assert np.isclose(bodies[1].mass, (1.0 * 1.0 * 4.0) * s ** 3)
+    assert np.isclose(bodies[0].mass, (5.0 * 5.0 * 2.0 - 4 * 1.1 * 1.1 * 2.0) * s ** 3)
+    rs = scenes.c4_candidate_rollouts(bodies, 2)
+    assert [b.name for b in rs.bodies] == ["part2", "part0", "part1", "part3", "part4"]
+    assert [b.joint_type for b in rs.bodies] == ["translational"] + ["fixed"] * 4
+    assert rs.pairs == [(0, 1), (1, 0), (0, 2), (2, 0), (0, 3), (3, 0), (0, 4), (4, 0)]
+    assert rs.n_envs == 6 and np.array_equal(rs.f_ext[4, 0], [0, 0, 0, 0, 0, 100.0]) and not rs.f_ext[:, 1:].any()
