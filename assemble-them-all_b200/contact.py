@@ -421,10 +421,10 @@ class ContactBatch:
         self.n_grounds = len(grounds)
 
     def skin_stats(self):
-        """{words_culled, margins_used_up, rebuilds} of the stepper's detection culling (zeros when off)."""
-        s = (C.c_int64 * 3)()
+        """{words_culled, margins_used_up, rebuilds, pairs_skipped} of the stepper's detection culling (zeros when off)."""
+        s = (C.c_int64 * 4)()
         check(self._lib.sdfc_batch_get_skin_stats(self._h, s))
-        return {"words_culled": int(s[0]), "margins_used_up": int(s[1]), "rebuilds": int(s[2])}
+        return {"words_culled": int(s[0]), "margins_used_up": int(s[1]), "rebuilds": int(s[2]), "pairs_skipped": int(s[3])}
 
     def ground_active(self):
         """(n_envs, n_grounds) contact counts of the last evaluation."""

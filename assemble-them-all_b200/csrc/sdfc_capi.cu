@@ -31,6 +31,7 @@ void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, 
     out->sx = pts->d_s; out->sy = pts->d_s + pts->n; out->sz = pts->d_s + 2 * (size_t)pts->n;
     out->ox = pts->d_o; out->oy = pts->d_o + pts->n; out->oz = pts->d_o + 2 * (size_t)pts->n;
     out->wsphere = pts->d_wsphere;
+    for (int a = 0; a < 4; ++a) out->bsphere[a] = pts->bsphere[a];
     out->n = pts->n;
     out->n_words = (pts->n + 31) / 32;
     out->word_offset = word_offset;
@@ -122,16 +123,17 @@ sdfc_status batch_enable_skin(sdfc_batch* b) {
     const size_t ep = (size_t)b->n_envs * b->n_pairs;
     sdfc_status st = dev_alloc(&b->d_skin_margin, (size_t)b->n_envs * b->dev.words_per_env);
     if (st == SDFC_OK) st = dev_alloc(&b->d_skin_pose, ep * 24);
-    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_int, ep * 4);
-    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_stats, (size_t)3);
+    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_int, ep * 5);
+    if (st == SDFC_OK) st = dev_alloc(&b->d_skin_stats, (size_t)4);
     if (st != SDFC_OK) return st;
-    SDFC_CUDA(cudaMemset(b->d_skin_int, 0, sizeof(int) * ep * 4));
-    SDFC_CUDA(cudaMemset(b->d_skin_stats, 0, sizeof(unsigned long long) * 3));
+    SDFC_CUDA(cudaMemset(b->d_skin_int, 0, sizeof(int) * ep * 5));
+    SDFC_CUDA(cudaMemset(b->d_skin_stats, 0, sizeof(unsigned long long) * 4));
     b->dev.skin_stats = b->d_skin_stats;
     b->dev.skin_margin = b->d_skin_margin;
     b->dev.skin_ref = b->d_skin_pose; b->dev.skin_cur = b->d_skin_pose + ep * 12;
     b->dev.skin_mode = b->d_skin_int; b->dev.skin_valid = b->d_skin_int + ep;
     b->dev.skin_fail = b->d_skin_int + 2 * ep; b->dev.skin_elig = b->d_skin_int + 3 * ep;
+    b->dev.skin_pair_margin = b->d_skin_int + 4 * ep;
     b->skin_on = true;
     return SDFC_OK;
 }
@@ -447,6 +449,18 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
         }
         st = dev_alloc(&p->d_wsphere, sph.size());
         if (st == SDFC_OK) e = cudaMemcpy(p->d_wsphere, sph.data(), sizeof(double) * sph.size(), cudaMemcpyHostToDevice);
+        {   // bounding sphere of the whole set (pair-level displacement bound of the stepper's culling)
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, r2 = 0;
+            for (int i = 0; i < n; ++i)
+                for (int a = 0; a < 3; ++a) { const double v = src[(size_t)a * n + i]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+            for (int a = 0; a < 3; ++a) p->bsphere[a] = 0.5 * (lo[a] + hi[a]);
+            for (int i = 0; i < n; ++i) {
+                double d2 = 0;
+                for (int a = 0; a < 3; ++a) { const double t = src[(size_t)a * n + i] - p->bsphere[a]; d2 += t * t; }
+                r2 = std::max(r2, d2);
+            }
+            p->bsphere[3] = std::sqrt(r2) * (1.0 + 1e-12);
+        }
     }
     if (e != cudaSuccess || st != SDFC_OK) {
         if (p->d_s != p->d_o) cudaFree(p->d_s);
@@ -712,15 +726,15 @@ sdfc_status sdfc_batch_set_grounds(sdfc_batch* b, int n_grounds, sdfc_ground* co
     return sdfc_host::ground_set_create(b->ctx, b->n_envs, b->n_bodies, n_grounds, grounds, body, &b->gset);
 }
 
-sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* b, int64_t stats[3]) {
+sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* b, int64_t stats[4]) {
     SDFC_REQUIRE(b && stats, "sdfc_batch_get_skin_stats: NULL argument");
-    stats[0] = stats[1] = stats[2] = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (!b->skin_on) return SDFC_OK;
     SDFC_CUDA(cudaSetDevice(b->ctx->device));
-    unsigned long long c[3] = {0, 0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     SDFC_CUDA(cudaMemcpyAsync(c, b->d_skin_stats, sizeof(c), cudaMemcpyDeviceToHost, b->ctx->stream));
     SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
-    for (int i = 0; i < 3; ++i) stats[i] = (int64_t)c[i];
+    for (int i = 0; i < 4; ++i) stats[i] = (int64_t)c[i];
     return SDFC_OK;
 }
 

@@ -80,6 +80,7 @@ struct sdfc_points {
     double* d_o = nullptr;  // original order SoA: x[n] y[n] z[n]
     double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
     double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
+    double bsphere[4] = {0, 0, 0, 0};  // (cx, cy, cz, r) of the whole set
     bool sorted = false;
 };
 

@@ -56,6 +56,7 @@ struct SkinCta {
     float* margin;   // this pair's words of this environment
     int* fail;       // counters of (env, pair)
     int* elig;
+    int* pair_margin;
 };
 
 // One thread per (env, pair): relative pose now, decide whether the margins are rebuilt.
@@ -77,12 +78,28 @@ __global__ void k_skin_decide(BatchDev B, const double* __restrict__ E) {
     int mode = 0;
     if (!B.skin_valid[ep]) mode = 1;
     else if (4 * B.skin_fail[ep] > B.skin_elig[ep]) mode = 1;   // > 25 % of the margins are used up
+    else {
+        // whole pair: every word has a margin and the smallest one outlasts the largest displacement of the set
+        const float pm = __int_as_float(B.skin_pair_margin[ep]);
+        if (pm >= 0.f) {
+            const double* ref = B.skin_ref + ep * 12;
+            double d[12], f2 = 0.0;
+            for (int i = 0; i < 12; ++i) { d[i] = cur[i] - ref[i]; if (i < 9) f2 += d[i] * d[i]; }
+            const double cx = pd.bsphere[0], cy = pd.bsphere[1], cz = pd.bsphere[2];
+            const double ux = d[0] * cx + d[1] * cy + d[2] * cz + d[9];
+            const double uy = d[3] * cx + d[4] * cy + d[5] * cz + d[10];
+            const double uz = d[6] * cx + d[7] * cy + d[8] * cz + d[11];
+            const double delta = sqrt(ux * ux + uy * uy + uz * uz) + sqrt(f2) * pd.bsphere[3];
+            if ((double)pm - pd.grid.lip * delta * (1.0 + 1e-9) > 1e-9) { mode = 2; atomicAdd(B.skin_stats + 3, 1ull); }
+        }
+    }
     B.skin_fail[ep] = 0;
     for (int i = 0; i < 12; ++i) B.skin_cur[ep * 12 + i] = cur[i];
-    if (mode) {
+    if (mode == 1) {
         for (int i = 0; i < 12; ++i) B.skin_ref[ep * 12 + i] = cur[i];
         B.skin_valid[ep] = 1;
         B.skin_elig[ep] = 0;
+        B.skin_pair_margin[ep] = __float_as_int(3e38f);
         atomicAdd(B.skin_stats + 2, 1ull);
     }
     B.skin_mode[ep] = mode;
@@ -144,7 +161,10 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
         }
         if (sk.on && sk.rebuild) {
             const unsigned eb = __ballot_sync(0xffffffffu, elig_out);
+            const unsigned ob = __ballot_sync(0xffffffffu, w < pd.n_words && !keep);
             if (lane == 0 && eb) atomicAdd(sk.elig, __popc(eb));
+            // signed-int order == float order on {-1} u [0, inf): one word without a margin makes the pair's -1
+            if (lane == 0 && ob) atomicMin(sk.pair_margin, __float_as_int(sk.out_margin));
         }
         if (sk.on && !sk.rebuild) {   // warp-uniform
             const unsigned cb = __ballot_sync(0xffffffffu, culled), ub = __ballot_sync(0xffffffffu, used_up);
@@ -199,7 +219,9 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
                 for (int o = 16; o > 0; o >>= 1) dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, o));
                 if (lane == 0) {
                     const bool ok = dm > 0.0;
-                    sk.margin[ws[u]] = ok ? __double2float_rd(dm) : -1.f;
+                    const float mw = ok ? __double2float_rd(dm) : -1.f;
+                    sk.margin[ws[u]] = mw;
+                    atomicMin(sk.pair_margin, __float_as_int(mw));
                     if (ok) atomicAdd(sk.elig, 1);
                 }
             }
@@ -221,6 +243,8 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     const int tile = blockIdx.x, env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;  // CTA-uniform
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
+    // whole pair provably contact-free (k_skin_decide): n_active stays 0, so nothing reads this pair's mask words
+    if (B.skin_mode != nullptr && B.skin_mode[(size_t)env * B.n_pairs + pair] == 2) return;  // CTA-uniform
     {
         const int* src = reinterpret_cast<const int*>(B.pairs + pair);
         int* dst = reinterpret_cast<int*>(&pd);
@@ -249,6 +273,7 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
             sk.stats = B.skin_stats;
             sk.fail = B.skin_fail + ep;
             sk.elig = B.skin_elig + ep;
+            sk.pair_margin = B.skin_pair_margin + ep;
         }
     }
     __syncthreads();

@@ -17,6 +17,7 @@ struct PairDev {
     // in the contact body's frame: lets detection skip whole words that cannot
     // reach the SDF's box (they would all return FLT_MAX, BodySDFObj.cpp:170)
     const double* wsphere;
+    double bsphere[4];   // bounding sphere of the whole point set (pair-level culling of the stepper)
     int n;            // number of contact points
     int n_words;      // ceil(n / 32) mask words
     int word_offset;  // first mask word of this pair inside an environment's mask row
@@ -79,11 +80,12 @@ struct BatchDev {
     float* skin_margin;   // [n_envs][words_per_env]
     double* skin_ref;     // [n_envs][n_pairs][12]  R_rel (row-major) | p_rel at the last rebuild
     double* skin_cur;     // [n_envs][n_pairs][12]  same for the current evaluation
-    int* skin_mode;       // [n_envs][n_pairs]      1 = rebuild margins in this evaluation
+    int* skin_mode;       // [n_envs][n_pairs]      1 = rebuild margins in this evaluation, 2 = whole pair skipped
+    int* skin_pair_margin;   // [n_envs][n_pairs]   float bits: smallest word margin (-1 as soon as one word has none)
     int* skin_valid;      // [n_envs][n_pairs]      reference pose and margins exist
     int* skin_fail;       // [n_envs][n_pairs]      eligible words that had to be evaluated last time
     int* skin_elig;       // [n_envs][n_pairs]      words with a margin
-    unsigned long long* skin_stats;   // [3] running totals: words culled, words whose margin was used up, rebuilds
+    unsigned long long* skin_stats;   // [4] running totals: words culled, words whose margin was used up, rebuilds, pairs skipped
 };
 
 // launches (all asynchronous on `stream`)

@@ -221,9 +221,11 @@ SDFC_API sdfc_status sdfc_batch_set_grounds(sdfc_batch* batch, int n_grounds, sd
 /* Running totals of the stepper's temporal-coherence culling in the detection kernel (all 0 when
  * it is off; SDFC_SKIN=0/1 at sdfc_sim_create): stats[0] = 32-point words skipped because
  * Lipschitz x displacement stayed below their measured margin, stats[1] = words whose margin was
- * used up (evaluated in full), stats[2] = (environment, pair) margin rebuilds. The cull never changes
- * a result: a skipped word has no point with d < 0 (CollisionDetection.cpp:137-138). */
-SDFC_API sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* batch, int64_t stats[3]);
+ * used up (evaluated in full), stats[2] = (environment, pair) margin rebuilds, stats[3] = (environment,
+ * pair) evaluations skipped as a whole (smallest margin of the pair against the displacement bound of
+ * the whole point set). The cull never changes a result: a skipped word has no point with d < 0
+ * (CollisionDetection.cpp:137-138). */
+SDFC_API sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* batch, int64_t stats[4]);
 /* Ground contact counts of the last evaluation: [n_envs][n_grounds], host. */
 SDFC_API sdfc_status sdfc_batch_get_ground_active(sdfc_batch* batch, int32_t* n_active_out);
 

@@ -239,8 +239,8 @@ def test_skin_culling_does_not_change_results(cuda_ctx, joint_type, frame_skip):
     a, b = outs
     assert a[3].any() and not a[3].all()
     assert a[5] == b[5]
-    assert a[6] == {"words_culled": 0, "margins_used_up": 0, "rebuilds": 0}
+    assert not any(a[6].values())
     print("\nskin:", b[6], "of", (a[5][0] + a[5][1]) * sum(-(-len(rs.bodies[p].points) // 32) for p, _ in rs.pairs), "word visits")
-    assert b[6]["words_culled"] > 0 and b[6]["rebuilds"] >= 192 * 2
+    assert b[6]["words_culled"] > 0 and b[6]["rebuilds"] >= 192 * 2 and b[6]["pairs_skipped"] > 0
     for x, y in zip(a[:5], b[:5]):
         assert np.array_equal(x, y)
