@@ -128,6 +128,7 @@ sdfc_status batch_enable_skin(sdfc_batch* b) {
     if (st != SDFC_OK) return st;
     SDFC_CUDA(cudaMemset(b->d_skin_int, 0, sizeof(int) * ep * 5));
     SDFC_CUDA(cudaMemset(b->d_skin_stats, 0, sizeof(unsigned long long) * 4));
+    SDFC_CUDA(cudaDeviceSynchronize());
     b->dev.skin_stats = b->d_skin_stats;
     b->dev.skin_margin = b->d_skin_margin;
     b->dev.skin_ref = b->d_skin_pose; b->dev.skin_cur = b->d_skin_pose + ep * 12;
@@ -259,13 +260,18 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
     }
     sdfc_status st = dev_alloc(&s->d_g64, s->count);
     if (st != SDFC_OK) { delete s; return st; }
+    // The context stream is cudaStreamNonBlocking: it is NOT ordered after null-stream copies / memsets, and a
+    // pageable cudaMemcpy may return before its DMA has landed. Every creation path therefore ends its
+    // null-stream work with a device synchronisation before anything is launched on the context stream.
     cudaError_t e = cudaMemcpy(s->d_g64, grid_host, s->count * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess && lossless) {
         float* d_g32 = nullptr;
         // cell records need 8x the plain fp32 grid; if that does not fit, stay on the fp64 path
         if (cudaMalloc((void**)&d_g32, s->count * sizeof(float)) == cudaSuccess &&
             cudaMalloc((void**)&s->d_c32, s->count * 2 * sizeof(float4)) == cudaSuccess) {
             e = cudaMemcpy(d_g32, g32.data(), s->count * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e == cudaSuccess) {
                 launch_build_cells(d_g32, ni, nj, nk, s->d_c32, ctx->stream);
                 ctx->launches += 1;
@@ -461,6 +467,7 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
             }
             p->bsphere[3] = std::sqrt(r2) * (1.0 + 1e-12);
         }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // pageable uploads have landed before the context stream reads them
     }
     if (e != cudaSuccess || st != SDFC_OK) {
         if (p->d_s != p->d_o) cudaFree(p->d_s);
@@ -687,6 +694,7 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
         if (e == cudaSuccess && !tile_pair.empty()) e = cudaMemcpy(b->d_tile_word0, tile_word0.data(), sizeof(int) * tile_word0.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(b->d_mask, 0, sizeof(uint32_t) * (size_t)n_envs * std::max(words, 1));
         if (e == cudaSuccess) e = cudaMemset(b->d_Dm_sub, 0, sizeof(double) * ep * 144);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // null-stream work done before the context stream uses it
         if (e != cudaSuccess) st = fail(SDFC_ERR_CUDA, std::string("sdfc_batch_create: ") + cudaGetErrorString(e));
     }
     if (st != SDFC_OK) { sdfc_batch_destroy(b); return st; }

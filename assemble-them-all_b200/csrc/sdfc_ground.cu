@@ -359,7 +359,8 @@ sdfc_status ground_set_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     A(dev_alloc(&s->d_out, eg * kGroundOut));
     A(dev_alloc(&s->d_n_active, eg));
     A(dev_alloc(&s->d_ticket, eg));
-    if (st == SDFC_OK && cudaMemset(s->d_ticket, 0, sizeof(unsigned) * eg) != cudaSuccess)
+    // null-stream memset: synchronise before the (non-blocking) context stream launches anything that reads it
+    if (st == SDFC_OK && (cudaMemset(s->d_ticket, 0, sizeof(unsigned) * eg) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess))
         st = fail(SDFC_ERR_CUDA, "ground_set_create: cudaMemset failed");
     if (st != SDFC_OK) { ground_set_destroy(s); return st; }
     GroundBatchDev& D = s->dev;

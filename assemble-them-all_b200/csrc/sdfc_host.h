@@ -4,6 +4,7 @@
 #include "../../include/sdfcontact_b200.h"
 #include "sdfc_kernels.cuh"
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,11 @@ sdfc_status dev_alloc(T** p, size_t count) {
     *p = nullptr;
     if (count == 0) return SDFC_OK;
     SDFC_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    // SDFC_POISON=1 (debugging aid): every fresh allocation is filled with 0xFF bytes (NaN doubles / floats,
+    // -1 ints), so that a read of memory the library never wrote shows up as NaN or a wild index instead
+    // of depending on what the previous owner of the pages left there
+    static const bool poison = [] { const char* e = std::getenv("SDFC_POISON"); return e && std::atoi(e) != 0; }();
+    if (poison) { SDFC_CUDA(cudaMemset((void*)*p, 0xFF, count * sizeof(T))); SDFC_CUDA(cudaDeviceSynchronize()); }
     return SDFC_OK;
 }
 }  // namespace sdfc_host

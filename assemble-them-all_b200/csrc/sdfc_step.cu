@@ -928,6 +928,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         if (e == cudaSuccess && ng) e = cudaMemcpy(s->d_ground_body, sdfc_host::ground_set_bodies(batch->gset), sizeof(int) * ng, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(s->d_fext, 0, sizeof(double) * ne * nb * 6);
         if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * 4);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();  // null-stream work done before the lane / context streams use it
         if (e != cudaSuccess) st = fail(SDFC_ERR_CUDA, std::string("sdfc_sim_create: ") + cudaGetErrorString(e));
     }
     if (st != SDFC_OK) { sdfc_sim_destroy(s); return st; }

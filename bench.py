@@ -377,7 +377,7 @@ def c4_leg(args, torch, local, cpu):
     import threading
     from assemble_them_all_b200 import contact, scenes
     bodies = scenes.c4_bodies()
-    n_workers = 4
+    n_workers = max(1, min(len(bodies), int(os.environ.get("SDFC_C4_WORKERS", "10"))))
     ctxs = [contact.Context(local) for _ in range(n_workers)]
     shared = [dict() for _ in range(n_workers)]
     sims = []
@@ -425,7 +425,7 @@ def c4_leg(args, torch, local, cpu):
            "converged": int(sum(int(sim.is_converged().sum()) for _, _, sim, _ in sims)),
            "touched": int(sum(int(sim.get_contact_history().any(axis=1).sum()) for _, _, sim, _ in sims)),
            "largest_displacement_per_candidate": [round(x, 3) for x in moved],
-           "timing": "wall clock between device synchronisations (20 simulations on 4 streams)"}
+           "timing": f"wall clock between device synchronisations ({len(sims)} simulations on {n_workers} streams)"}
     if cpu and have_ref():
         # the reference's Simulation::forward on the same candidate (inputs injected), one rollout, 40 steps (contact from step ~27)
         from oracle import ref_scene

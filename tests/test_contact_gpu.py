@@ -238,3 +238,22 @@ def test_edge_cases(cuda_ctx, scene, golden_contact):
         contact.ForceGeneralSDFContact(cuda_ctx, cp, object())
     with pytest.raises(contact.SdfContactError):
         contact.SdfGrid(cuda_ctx, 4, 4, 4, [0, 0, 0], [1, 1, 1], 0.3, 0.3, 0.3, 0.0, np.zeros(10))
+
+
+def test_results_do_not_depend_on_stale_device_memory():
+    """SDFC_POISON=1 fills every fresh device allocation of the library with 0xFF bytes (NaN / -1). A batch
+    evaluation (both variants), planner rollouts of both joint types and a free-fall batch must give the
+    same bytes with and without it: nothing is read before the library wrote it, and creation-time
+    null-stream uploads are ordered before the first launch on the (non-blocking) context stream - the
+    r1i plug-in flakiness was exactly that race."""
+    import os
+    import subprocess
+    import sys
+    driver = os.path.join(os.path.dirname(os.path.abspath(__file__)), "drivers", "poison_probe.py")
+    digests = []
+    for poison in ("0", "1", "1"):
+        r = subprocess.run([sys.executable, driver], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, SDFC_POISON=poison))
+        assert r.returncode == 0, r.stdout + r.stderr
+        digests.append([ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1] == digests[2]
