@@ -49,7 +49,7 @@ __device__ __forceinline__ double detect_point(const GridDev& G, const double* R
 
 // Skin state of this CTA's (env, pair): displacement of the relative pose since the reference.
 struct SkinCta {
-    bool on, rebuild;
+    bool rebuild;
     unsigned long long* stats;
     float out_margin;   // bmin + col_th rounded down, or -1 when that is not positive
     double dR[9], dp[3], fro, lip;
@@ -110,7 +110,7 @@ void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream)
     k_skin_decide<<<(n + 127) / 128, 128, 0, stream>>>(B, E);
 }
 
-template <bool F32>
+template <bool F32, bool SKIN>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
                                             int* s_count, const SkinCta& sk) {
@@ -138,7 +138,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
             keep = cl[0] >= pd.grid.mn[0] - r && cl[0] <= pd.grid.mx[0] + r &&
                    cl[1] >= pd.grid.mn[1] - r && cl[1] <= pd.grid.mx[1] + r &&
                    cl[2] >= pd.grid.mn[2] - r && cl[2] <= pd.grid.mx[2] + r;
-            if (sk.on) {
+            if constexpr (SKIN) {
                 if (sk.rebuild) {
                     // every point outside the box at the reference pose: they all carry the outside margin
                     if (!keep) { sk.margin[w] = sk.out_margin; elig_out = sk.out_margin >= 0.f; }
@@ -159,14 +159,14 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
             }
             if (!keep) mask_row[pd.word_offset + w] = 0u;  // culled words: empty mask
         }
-        if (sk.on && sk.rebuild) {
+        if (SKIN && sk.rebuild) {
             const unsigned eb = __ballot_sync(0xffffffffu, elig_out);
             const unsigned ob = __ballot_sync(0xffffffffu, w < pd.n_words && !keep);
             if (lane == 0 && eb) atomicAdd(sk.elig, __popc(eb));
             // signed-int order == float order on {-1} u [0, inf): one word without a margin makes the pair's -1
             if (lane == 0 && ob) atomicMin(sk.pair_margin, __float_as_int(sk.out_margin));
         }
-        if (sk.on && !sk.rebuild) {   // warp-uniform
+        if (SKIN && !sk.rebuild) {   // warp-uniform
             const unsigned cb = __ballot_sync(0xffffffffu, culled), ub = __ballot_sync(0xffffffffu, used_up);
             if (lane == 0) {
                 if (cb) atomicAdd(sk.stats, (unsigned long long)__popc(cb));
@@ -210,7 +210,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
             const bool act = inr[u] && d < 0.;
             const unsigned m = __ballot_sync(0xffffffffu, act);
             if (lane == 0) { mask_row[pd.word_offset + ws[u]] = m; cnt += __popc(m); }
-            if (sk.on && sk.rebuild) {
+            if (SKIN && sk.rebuild) {
                 // margin of the word at the reference pose: smallest d of its points; a point outside the
                 // box (d = FLT_MAX + col_th) carries the outside margin: before it can be active it has to
                 // cross a face of the box, where the interpolant is >= GridDev::bmin
@@ -233,6 +233,9 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
 #ifndef SDFC_DETECT_MIN_BLOCKS
 #define SDFC_DETECT_MIN_BLOCKS 6  // 40 registers: the kernel is latency-bound on the cell gathers, occupancy wins
 #endif
+// SKIN = false is the plain kernel (every batch evaluation outside the stepper); SKIN = true adds the
+// stepper's margin test / margin rebuild, compiled out of the plain instantiation.
+template <bool SKIN>
 __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_detect_mask(BatchDev B, const double* __restrict__ E) {
     __shared__ PairDev pd;
     __shared__ double R1[9], p1[3], R2[9], p2[3];
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;  // CTA-uniform
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
     // whole pair provably contact-free (k_skin_decide): n_active stays 0, so nothing reads this pair's mask words
-    if (B.skin_mode != nullptr && B.skin_mode[(size_t)env * B.n_pairs + pair] == 2) return;  // CTA-uniform
+    if (SKIN && B.skin_mode[(size_t)env * B.n_pairs + pair] == 2) return;  // CTA-uniform
     {
         const int* src = reinterpret_cast<const int*>(B.pairs + pair);
         int* dst = reinterpret_cast<int*>(&pd);
@@ -255,9 +258,8 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     __shared__ SkinCta sk;
     if (threadIdx.x < 12) stage_pose(E, B.n_bodies, env, pd.body_a, R1, p1, threadIdx.x);
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
-    else if (threadIdx.x == 64) {
-        sk.on = B.skin_margin != nullptr;
-        if (sk.on) {
+    else if (SKIN && threadIdx.x == 64) {
+        {
             const size_t ep = (size_t)env * B.n_pairs + pair;
             sk.rebuild = B.skin_mode[ep] != 0;
             double f2 = 0.0;
@@ -278,8 +280,8 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     }
     __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
-    if (pd.grid.c32 != nullptr) detect_tile<true>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
-    else detect_tile<false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
+    if (pd.grid.c32 != nullptr) detect_tile<true, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
+    else detect_tile<false, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
 }
@@ -287,7 +289,8 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream) {
     cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
     dim3 grid(B.n_tiles, B.env_count);
-    k_detect_mask<<<grid, kDetectThreads, 0, stream>>>(B, E);
+    if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreads, 0, stream>>>(B, E);
+    else k_detect_mask<false><<<grid, kDetectThreads, 0, stream>>>(B, E);
 }
 
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
