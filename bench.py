@@ -624,14 +624,21 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    # nothing a library prints (NCCL's version banner comes from C code) can land in front of the line
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the contact path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (NCCL_DEBUG >= VERSION, WARN included) to stdout; stdout carries ONE JSON
+        # line, so the banner level is dropped and whatever NCCL still logs goes to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from assemble_them_all_b200 import contact
@@ -792,7 +799,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             fm_h, Km_h, Dm_h, _ = out
             line["cpu_baseline"] = cpu_baseline_leg(scene, (fm_h, Km_h, Dm_h))
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
