@@ -1,3 +1,5 @@
+# Regression recipe for the r1i creation-path race ("Stream ordering rule"): the test-file sequence that
+# exposed it three times in a row, the SDFC_POISON=1 suite, then the full GPU suite twice. GPU box only.
 for i in 1 2 3; do
   python -m pytest tests/test_multipart.py tests/test_plugin_gpu.py -m gpu -q -s 2>&1 | grep "MISMATCH\|passed\|failed\|FAILED"
 done
