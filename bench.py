@@ -561,6 +561,8 @@ def env_steps_leg(ctx, args, rank, world, local, torch, dist, dev, stream):
         dev_ms.append(a.elapsed_time(b))
     st1 = sim.stats()
     launches = ctx.launch_count - l0
+    prepare()
+    sim.forward(n, trajectory=True)   # warm-up of the trajectory path (first call allocates the device trajectory buffers)
     for _ in range(reps):
         t0 = time.perf_counter()
         prepare()
