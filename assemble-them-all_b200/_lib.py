@@ -35,9 +35,11 @@ SIGNATURES = {
                                   C.c_double, C.c_double, c_double_p, c_void_pp]),
     "sdfc_sdf_set_col_th": (C.c_int, [C.c_void_p, C.c_double]),
     "sdfc_sdf_is_fp32": (C.c_int, [C.c_void_p]),
+    "sdfc_sdf_layout_kind": (C.c_int, [C.c_void_p]),
     "sdfc_sdf_destroy": (C.c_int, [C.c_void_p]),
     "sdfc_sdf_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
     "sdfc_sdf_min_distance": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p]),
+    "sdfc_sdf_stencil": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "sdfc_sdf_distance_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdfc_make_level_set3": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                        C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -70,6 +72,7 @@ SIGNATURES = {
     "sdfc_batch_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "sdfc_batch_detect_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdfc_batch_get_active": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_uint8_p]),
     "sdfc_batch_queries_per_eval": (C.c_int64, [C.c_void_p]),
     "sdfc_ground_create": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_double, C.c_double, c_void_pp]),
     "sdfc_ground_set_transform": (C.c_int, [C.c_void_p, c_double_p]),

@@ -66,19 +66,29 @@ def build(force=False, verbose=False):
              list(extra_all) + PER_SOURCE_FLAGS.get(os.path.basename(s), [])) for s in srcs]
     jobs += [(os.path.join(CSRC, FORCE_INST), os.path.join(objdir, f"sdfc_force_v{v}.o"),
               [f"-DSDFC_FORCE_VARIANT={v}", *extra_all]) for v in range(8)]
+    hdr_deps = [os.path.join(CSRC, h) for h in HEADERS if h != FORCE_INST] + [os.path.abspath(__file__)]
+    flag_stamp = os.path.join(objdir, ".flags")
+    flags_now = " ".join(NVCC_FLAGS + extra_all)
+    flags_same = os.path.exists(flag_stamp) and open(flag_stamp).read() == flags_now
     for s, o, extra in jobs:
+        objs.append(o)
+        # per-object staleness: a .cu-only edit does not recompile the 8 force variants
+        if not force and flags_same and os.path.exists(o) and all(
+                os.path.getmtime(d) <= os.path.getmtime(o) for d in [s, *hdr_deps] if os.path.exists(d)):
+            continue
         cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(o)
     for s, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
+    with open(flag_stamp, "w") as f:
+        f.write(flags_now)
     cmd = [_nvcc(), "-shared", "-o", OUT, *objs, "--compiler-bindir", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     return OUT

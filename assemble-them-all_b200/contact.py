@@ -135,6 +135,11 @@ class SdfGrid:
     def is_fp32(self):
         return bool(self._lib.sdfc_sdf_is_fp32(self._h))
 
+    @property
+    def layout(self):
+        """Device storage: "fp64", "records" (fp32 cell records) or "bricks" (fp32 4x4x4 bricks, TMA-staged)."""
+        return ("fp64", "records", "bricks")[int(self._lib.sdfc_sdf_layout_kind(self._h))]
+
     def set_col_th(self, col_th):
         self.col_th = float(col_th)
         check(self._lib.sdfc_sdf_set_col_th(self._h, self.col_th))
@@ -155,6 +160,18 @@ class SdfGrid:
         out = C.c_double()
         check(self._lib.sdfc_sdf_min_distance(self._h, len(X), _dp(X), C.byref(out)))
         return float(out.value)
+
+    def stencil(self, X, fast=True):
+        """BodySDFObj::query_SDF(x, true), query_dSDF, query_ddSDF (BodySDFObj.cpp:123-205) at X (n,3) in
+        the grid's frame -> (sdf (n,), grad (n,3), hess (n,3,3)). fast selects the planner kernel's
+        shared-stencil path, else the general kernel's sample-by-sample path; same bits either way."""
+        X = _f64(X)
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise SdfContactError("[Error] stencil expects an (n,3) array")
+        n = len(X)
+        acc, g, H = np.empty(n), np.empty((n, 3)), np.empty((n, 3, 3))
+        check(self._lib.sdfc_sdf_stencil(self._h, n, _dp(X), int(bool(fast)), _dp(acc), _dp(g), _dp(H)))
+        return acc, g, H
 
     def distance_device(self, n, dx_ptr, dy_ptr, dz_ptr, dout_ptr):
         check(self._lib.sdfc_sdf_distance_device(self._h, int(n), dx_ptr, dy_ptr, dz_ptr, dout_ptr))
@@ -224,7 +241,10 @@ def load_sdf_text(path, col_th=0.0):
 
 
 class ContactPoints:
+    SORT_MODES = {False: 0, True: 1, None: 0, "none": 0, "morton": 1, "kd": 2, 0: 0, 1: 1, 2: 2}
+
     def __init__(self, ctx, xyz, morton_sort=True):
+        """morton_sort: False / True (30-bit Morton order) / "kd" (k-d order with box-shaped detection tiles)."""
         self.ctx = ctx
         self._lib = ctx._lib
         X = _f64(xyz)
@@ -232,7 +252,7 @@ class ContactPoints:
             raise SdfContactError("[Error] contact points must be an (n,3) array")
         self.n = len(X)
         self._h = C.c_void_p()
-        check(self._lib.sdfc_points_create(ctx._h, self.n, _dp(X), int(bool(morton_sort)), C.byref(self._h)))
+        check(self._lib.sdfc_points_create(ctx._h, self.n, _dp(X), self.SORT_MODES[morton_sort], C.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -461,6 +481,14 @@ class ContactBatch:
     def eval_device(self, E_ptr, phi_ptr, deriv, fm_ptr, Km_ptr, Dm_ptr, nact_ptr):
         """Raw device pointers (ints). E is column-major per pose. Asynchronous."""
         check(self._lib.sdfc_batch_eval_device(self._h, E_ptr, phi_ptr, int(bool(deriv)), fm_ptr, Km_ptr, Dm_ptr, nact_ptr))
+
+    def active_mask(self, env, pair):
+        """(n,) uint8 in ORIGINAL point order: the 1-bit active mask the last batched detection wrote for
+        (env, pair) - collision_detection_general_SDF's d < 0 test (CollisionDetection.cpp:137-138)."""
+        n = self.pairs[pair].contact_points.n
+        out = np.empty(n, dtype=np.uint8)
+        check(self._lib.sdfc_batch_get_active(self._h, int(env), int(pair), out.ctypes.data_as(_lib.c_uint8_p)))
+        return out
 
     def detect_device(self, E_ptr, nact_ptr):
         check(self._lib.sdfc_batch_detect_device(self._h, E_ptr, nact_ptr))

@@ -3,7 +3,10 @@
 // of sdfc_kernels.cu. No CPU compute path: every entry needs a CUDA device.
 #include "sdfc_host.h"
 
+#include <cuda.h>   // CUtensorMap, cuTensorMapEncodeTiled (resolved through cudaGetDriverEntryPoint: no libcuda link)
+
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +34,7 @@ void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, 
     out->sx = pts->d_s; out->sy = pts->d_s + pts->n; out->sz = pts->d_s + 2 * (size_t)pts->n;
     out->ox = pts->d_o; out->oy = pts->d_o + pts->n; out->oz = pts->d_o + 2 * (size_t)pts->n;
     out->wsphere = pts->d_wsphere;
+    out->tile_box = pts->d_tile_box;
     for (int a = 0; a < 4; ++a) out->bsphere[a] = pts->bsphere[a];
     out->n = pts->n;
     out->n_words = (pts->n + 31) / 32;
@@ -52,11 +56,13 @@ sdfc_status batch_refresh(sdfc_batch* b) {
     std::vector<PairDev> host(b->n_pairs);
     int word_offset = 0;
     b->any_fric = b->any_damp = false;
+    b->dev.any_bricks = 0;
     for (int i = 0; i < b->n_pairs; ++i) {
         fill_pair_dev(b->pairs[i], b->body_a[i], b->body_b[i], word_offset, &host[i]);
         word_offset += host[i].n_words;
         if (host[i].prm.mu > kEps) b->any_fric = true;
         if (host[i].prm.damping != 0.0) b->any_damp = true;
+        if (host[i].grid.b32 != nullptr) b->dev.any_bricks = 1;
         b->seen_pair_version[i] = b->pairs[i]->version;
         b->seen_sdf_version[i] = b->pairs[i]->sdf->version;
     }
@@ -150,6 +156,43 @@ uint32_t expand10(uint32_t v) {
     v = (v | (v << 4)) & 0x030C30C3u;
     v = (v | (v << 2)) & 0x09249249u;
     return v;
+}
+
+// k-d ordering of a point set: the index range is split at the median of its longest axis, at a position
+// that is a whole number of detection tiles (2048 points) while the range holds more than one tile, then a
+// whole number of 32-point words. Every tile, every 256-point group and every word of the sorted copy is
+// therefore a compact box: tight word spheres for the broad phase and a small voxel brick per tile for the
+// TMA-staged detection (Morton ranges of a fixed point count straddle octree cells and have loose boxes).
+struct KdPoint { double x[3]; int32_t idx; };
+void kd_split(KdPoint* pts, int lo, int hi, int depth) {
+    const int cnt = hi - lo;
+    if (cnt <= 32) return;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = lo; i < hi; ++i)
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], pts[i].x[a]); mx[a] = std::max(mx[a], pts[i].x[a]); }
+    int ax = 0;
+    for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+    const int tile = kDetectTileWords * 32;
+    const int unit = cnt > tile ? tile : 32;
+    const int units = (cnt + unit - 1) / unit;
+    const int mid = lo + ((units + 1) / 2) * unit;
+    std::nth_element(pts + lo, pts + mid, pts + hi, [ax](const KdPoint& a, const KdPoint& b) {
+        return a.x[ax] < b.x[ax] || (a.x[ax] == b.x[ax] && a.idx < b.idx);   // total order: deterministic
+    });
+    if (depth < 4 && cnt > (1 << 18)) {   // large sets: the two halves in parallel (up to 16 threads)
+        std::thread t(kd_split, pts, lo, mid, depth + 1);
+        kd_split(pts, mid, hi, depth + 1);
+        t.join();
+    } else {
+        kd_split(pts, lo, mid, depth + 1);
+        kd_split(pts, mid, hi, depth + 1);
+    }
+}
+void kd_order(const double* xyz, int n, std::vector<int32_t>& order) {
+    std::vector<KdPoint> pts(n);
+    for (int i = 0; i < n; ++i) { pts[i].x[0] = xyz[3 * i]; pts[i].x[1] = xyz[3 * i + 1]; pts[i].x[2] = xyz[3 * i + 2]; pts[i].idx = i; }
+    kd_split(pts.data(), 0, n, 0);
+    for (int i = 0; i < n; ++i) order[i] = pts[i].idx;
 }
 }  // namespace
 
@@ -265,7 +308,61 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
     // null-stream work with a device synchronisation before anything is launched on the context stream.
     cudaError_t e = cudaMemcpy(s->d_g64, grid_host, s->count * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e == cudaSuccess && lossless) {
+    // fp32-lossless grids: cell records (32 B per cell, one sector per query) while they stay cache-resident,
+    // bricks (4 B per node, staged per tile with TMA) for grids whose records would be several times the L2.
+    // SDFC_GRID_LAYOUT = records | bricks overrides the size rule.
+    bool want_bricks = s->count * 32 > ((size_t)96 << 20);
+    if (const char* lay = std::getenv("SDFC_GRID_LAYOUT")) {
+        if (std::string(lay) == "bricks") want_bricks = true;
+        else if (std::string(lay) == "records") want_bricks = false;
+    }
+    const int nbx = (ni + 1 + 3) / 4, nby = (nj + 1 + 3) / 4, nbz = (nk + 1 + 3) / 4;   // + 1: replicated node layer
+    if (e == cudaSuccess && lossless && want_bricks) {
+        float* d_g32 = nullptr;
+        const size_t nbricks = (size_t)nbx * nby * nbz;
+        std::vector<CUtensorMap> maps((size_t)kBrickMaxXY * kBrickMaxXY);
+        if (cudaMalloc((void**)&d_g32, s->count * sizeof(float)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_b32, nbricks * 256) == cudaSuccess &&
+            cudaMalloc(&s->d_tmaps, maps.size() * sizeof(CUtensorMap)) == cudaSuccess) {
+            e = cudaMemcpy(d_g32, g32.data(), s->count * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e == cudaSuccess) {
+                launch_build_bricks(d_g32, ni, nj, nk, nbx, nby, nbz, s->d_b32, ctx->stream);
+                ctx->launches += 1;
+                e = cudaStreamSynchronize(ctx->stream);
+            }
+            // descriptor table: the bricked grid as a 4-D tensor (64 floats, nbx, nby, nbz); entry (bx - 1, by - 1)
+            // moves a box of 64 x bx x by x 1, i.e. one layer of a tile's brick region per cp.async.bulk.tensor
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (e == cudaSuccess) e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+            if (e == cudaSuccess && (fn == nullptr || qres != cudaDriverEntryPointSuccess)) e = cudaErrorNotSupported;
+            if (e == cudaSuccess) {
+                const cuuint64_t gdim[4] = {64, (cuuint64_t)nbx, (cuuint64_t)nby, (cuuint64_t)nbz};
+                const cuuint64_t gstr[3] = {256, (cuuint64_t)256 * nbx, (cuuint64_t)256 * nbx * nby};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                for (int bx = 1; bx <= kBrickMaxXY && e == cudaSuccess; ++bx)
+                    for (int by = 1; by <= kBrickMaxXY; ++by) {
+                        const cuuint32_t box[4] = {64, (cuuint32_t)std::min(bx, nbx), (cuuint32_t)std::min(by, nby), 1};
+                        const CUresult r = ((EncodeFn)fn)(&maps[(size_t)(bx - 1) * kBrickMaxXY + (by - 1)], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                                          s->d_b32, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        if (r != CUDA_SUCCESS) { e = cudaErrorInvalidValue; break; }
+                    }
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(s->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        } else {
+            cudaGetLastError();
+            cudaFree(s->d_b32); s->d_b32 = nullptr;
+            cudaFree(s->d_tmaps); s->d_tmaps = nullptr;
+        }
+        cudaFree(d_g32);
+    } else if (e == cudaSuccess && lossless) {
         float* d_g32 = nullptr;
         // cell records need 8x the plain fp32 grid; if that does not fit, stay on the fp64 path
         if (cudaMalloc((void**)&d_g32, s->count * sizeof(float)) == cudaSuccess &&
@@ -284,10 +381,12 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
         cudaFree(d_g32);
     }
     if (e != cudaSuccess || st != SDFC_OK) {
-        cudaFree(s->d_g64); cudaFree(s->d_c32); delete s;
+        cudaFree(s->d_g64); cudaFree(s->d_c32); cudaFree(s->d_b32); cudaFree(s->d_tmaps); delete s;
         return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_create: upload failed: ") + cudaGetErrorString(e));
     }
     s->dev.g64 = s->d_g64; s->dev.c32 = s->d_c32;
+    s->dev.b32 = s->d_b32; s->dev.tmaps = s->d_tmaps;
+    s->dev.nbx = nbx; s->dev.nby = nby; s->dev.nbz = nbz;
     s->dev.ni = ni; s->dev.nj = nj; s->dev.nk = nk;
     for (int a = 0; a < 3; ++a) { s->dev.mn[a] = min_box[a]; s->dev.mx[a] = max_box[a]; }
     s->dev.dx = dx; s->dev.dy = dy; s->dev.dz = dz; s->dev.col_th = col_th;
@@ -305,7 +404,7 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         cudaFree(d_l2);
         if (e != cudaSuccess) {
-            cudaFree(s->d_g64); cudaFree(s->d_c32); delete s;
+            cudaFree(s->d_g64); cudaFree(s->d_c32); cudaFree(s->d_b32); cudaFree(s->d_tmaps); delete s;
             return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_create: Lipschitz pass failed: ") + cudaGetErrorString(e));
         }
         double l2, bmin;
@@ -314,6 +413,13 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
         std::memcpy(&bmin, &kb, sizeof(bmin));
         s->dev.lip = std::sqrt(l2);
         s->dev.bmin = bmin;
+        // bmin bounds the interpolant on the faces of [min_box, max_box] only if those faces lie in the two
+        // outermost node layers, as BodySDFObj::precompute_SDF lays grids out (BodySDFObj.cpp:66-70). For a
+        // caller-supplied box that ends deeper inside the grid there is no outside margin: never cull such words.
+        const int nn[3] = {ni, nj, nk};
+        const double dd[3] = {dx, dy, dz};
+        for (int a = 0; a < 3; ++a)
+            if (!(std::fabs(max_box[a] - (min_box[a] + (nn[a] - 1) * dd[a])) <= dd[a])) s->dev.bmin = -1e300;
     }
     *out = s;
     return SDFC_OK;
@@ -324,11 +430,12 @@ sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th) {
     sdf->version++;
     return SDFC_OK;
 }
-int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && sdf->d_c32) ? 1 : 0; }
+int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && (sdf->d_c32 || sdf->d_b32)) ? 1 : 0; }
+int sdfc_sdf_layout_kind(const sdfc_sdf* sdf) { return !sdf ? -1 : (sdf->d_b32 ? 2 : (sdf->d_c32 ? 1 : 0)); }
 sdfc_status sdfc_sdf_destroy(sdfc_sdf* s) {
     if (!s) return SDFC_OK;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_g64); cudaFree(s->d_c32); cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
+    cudaFree(s->d_g64); cudaFree(s->d_c32); cudaFree(s->d_b32); cudaFree(s->d_tmaps); cudaFree(s->d_aos); cudaFree(s->d_soa); cudaFree(s->d_out); cudaFree(s->d_red);
     delete s;
     return SDFC_OK;
 }
@@ -392,6 +499,33 @@ sdfc_status sdfc_sdf_min_distance(sdfc_sdf* sdf, int64_t n, const double* X_host
     return SDFC_OK;
 }
 
+sdfc_status sdfc_sdf_stencil(sdfc_sdf* sdf, int64_t n, const double* X_host, int fast, double* sdf_acc_out,
+                             double* grad_out, double* hess_out) {
+    SDFC_REQUIRE(sdf && (n == 0 || X_host), "sdfc_sdf_stencil: NULL argument");
+    SDFC_REQUIRE(n >= 0, "sdfc_sdf_stencil: negative n");
+    if (n == 0) return SDFC_OK;
+    SDFC_CUDA(cudaSetDevice(sdf->ctx->device));
+    sdfc_status st = sdf_scratch(sdf, n);
+    if (st != SDFC_OK) return st;
+    double* d_gh = nullptr;   // grad 3n | hess 9n
+    if ((st = dev_alloc(&d_gh, (size_t)12 * n)) != SDFC_OK) return st;
+    cudaStream_t s = sdf->ctx->stream;
+    cudaError_t e = cudaMemcpyAsync(sdf->d_aos, X_host, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        launch_aos_to_soa(sdf->d_aos, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, s);
+        launch_sdf_stencil(sdf->dev, n, sdf->d_soa, sdf->d_soa + n, sdf->d_soa + 2 * n, fast, sdf->d_out, d_gh, d_gh + 3 * n, s);
+        sdf->ctx->launches += 2;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && sdf_acc_out) e = cudaMemcpyAsync(sdf_acc_out, sdf->d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && grad_out) e = cudaMemcpyAsync(grad_out, d_gh, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && hess_out) e = cudaMemcpyAsync(hess_out, d_gh + 3 * n, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_gh);
+    if (e != cudaSuccess) return fail(SDFC_ERR_CUDA, std::string("sdfc_sdf_stencil: ") + cudaGetErrorString(e));
+    return SDFC_OK;
+}
+
 // ----------------------------------------------------------------- points
 sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host, int morton_sort, sdfc_points** out) {
     SDFC_REQUIRE(ctx && out && (n == 0 || xyz_host), "sdfc_points_create: NULL argument");
@@ -409,28 +543,35 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
     p->d_s = p->d_o;
     std::vector<double> soa_sorted;
     if (e == cudaSuccess && morton_sort) {
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        for (int i = 0; i < n; ++i)
-            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], xyz_host[3 * i + a]); hi[a] = std::max(hi[a], xyz_host[3 * i + a]); }
-        std::vector<std::pair<uint32_t, int>> keys(n);
-        for (int i = 0; i < n; ++i) {
-            uint32_t q[3];
-            for (int a = 0; a < 3; ++a) {
-                const double ext = hi[a] - lo[a];
-                const double t = ext > 0 ? (xyz_host[3 * i + a] - lo[a]) / ext : 0.0;
-                q[a] = (uint32_t)std::min(1023.0, std::max(0.0, std::floor(t * 1024.0)));
+        std::vector<int32_t> order(n);
+        if (morton_sort == 2) {
+            kd_order(xyz_host, n, order);
+        } else {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int i = 0; i < n; ++i)
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], xyz_host[3 * i + a]); hi[a] = std::max(hi[a], xyz_host[3 * i + a]); }
+            std::vector<std::pair<uint32_t, int>> keys(n);
+            for (int i = 0; i < n; ++i) {
+                uint32_t q[3];
+                for (int a = 0; a < 3; ++a) {
+                    const double ext = hi[a] - lo[a];
+                    const double t = ext > 0 ? (xyz_host[3 * i + a] - lo[a]) / ext : 0.0;
+                    q[a] = (uint32_t)std::min(1023.0, std::max(0.0, std::floor(t * 1024.0)));
+                }
+                keys[i] = {expand10(q[0]) | (expand10(q[1]) << 1) | (expand10(q[2]) << 2), i};
             }
-            keys[i] = {expand10(q[0]) | (expand10(q[1]) << 1) | (expand10(q[2]) << 2), i};
+            std::stable_sort(keys.begin(), keys.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
+            for (int i = 0; i < n; ++i) order[i] = keys[i].second;
         }
-        std::stable_sort(keys.begin(), keys.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
         std::vector<double> srt((size_t)3 * n);
         for (int i = 0; i < n; ++i) {
-            const int o = keys[i].second;
+            const int o = order[i];
             srt[i] = soa[o]; srt[(size_t)n + i] = soa[(size_t)n + o]; srt[2 * (size_t)n + i] = soa[2 * (size_t)n + o];
         }
         st = dev_alloc(&p->d_s, (size_t)3 * n);
         if (st == SDFC_OK) e = cudaMemcpy(p->d_s, srt.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice);
         p->sorted = true;
+        p->perm.swap(order);
         soa_sorted.swap(srt);
     }
     if (e == cudaSuccess && st == SDFC_OK) {
@@ -455,6 +596,19 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
         }
         st = dev_alloc(&p->d_wsphere, sph.size());
         if (st == SDFC_OK) e = cudaMemcpy(p->d_wsphere, sph.data(), sizeof(double) * sph.size(), cudaMemcpyHostToDevice);
+        {   // box of every detection tile (PairDev::tile_box)
+            const int per = kDetectTileWords * 32, nt = (n + per - 1) / per;
+            std::vector<double> box((size_t)6 * nt);
+            for (int t = 0; t < nt; ++t) {
+                const int i0 = t * per, i1 = std::min(n, i0 + per);
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                for (int i = i0; i < i1; ++i)
+                    for (int a = 0; a < 3; ++a) { const double v = src[(size_t)a * n + i]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+                for (int a = 0; a < 3; ++a) { box[6 * (size_t)t + a] = lo[a]; box[6 * (size_t)t + 3 + a] = hi[a]; }
+            }
+            if (st == SDFC_OK) st = dev_alloc(&p->d_tile_box, box.size());
+            if (st == SDFC_OK && e == cudaSuccess) e = cudaMemcpy(p->d_tile_box, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice);
+        }
         {   // bounding sphere of the whole set (pair-level displacement bound of the stepper's culling)
             double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, r2 = 0;
             for (int i = 0; i < n; ++i)
@@ -471,7 +625,7 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
     }
     if (e != cudaSuccess || st != SDFC_OK) {
         if (p->d_s != p->d_o) cudaFree(p->d_s);
-        cudaFree(p->d_o); cudaFree(p->d_wsphere); delete p;
+        cudaFree(p->d_o); cudaFree(p->d_wsphere); cudaFree(p->d_tile_box); delete p;
         return fail(SDFC_ERR_CUDA, std::string("sdfc_points_create: upload failed: ") + cudaGetErrorString(e));
     }
     *out = p;
@@ -482,7 +636,7 @@ sdfc_status sdfc_points_destroy(sdfc_points* p) {
     if (!p) return SDFC_OK;
     cudaSetDevice(p->ctx->device);
     if (p->d_s != p->d_o) cudaFree(p->d_s);
-    cudaFree(p->d_o); cudaFree(p->d_wsphere);
+    cudaFree(p->d_o); cudaFree(p->d_wsphere); cudaFree(p->d_tile_box);
     delete p;
     return SDFC_OK;
 }
@@ -639,6 +793,8 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
                               const int32_t* body_a, const int32_t* body_b, sdfc_batch** out) {
     SDFC_REQUIRE(ctx && pairs && body_a && body_b && out, "sdfc_batch_create: NULL argument");
     SDFC_REQUIRE(n_envs > 0 && n_bodies > 0 && n_pairs > 0, "sdfc_batch_create: sizes must be positive");
+    // environments are gridDim.y / gridDim.z of the contact kernels
+    SDFC_REQUIRE(n_envs <= 65535, "sdfc_batch_create: at most 65535 environments per batch (split larger batches)");
     *out = nullptr;
     for (int i = 0; i < n_pairs; ++i) {
         SDFC_REQUIRE(pairs[i] && pairs[i]->ctx == ctx, "sdfc_batch_create: pair is NULL or from another context");
@@ -770,12 +926,36 @@ sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t
     SDFC_CUDA(cudaSetDevice(b->ctx->device));
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
-    b->ctx->begin(0); launch_detect_mask(b->dev, E_dev, b->ctx->stream); b->ctx->end();
+    // Stand-alone detection never uses the stepper's temporal-coherence culling: the margins, modes and
+    // displacement bounds on the device belong to the stepper's last evaluation at another pose (only
+    // batch_run runs k_skin_decide before the SKIN kernel). The plain kernel leaves that state untouched.
+    BatchDev dev = b->dev;
+    dev.skin_margin = nullptr;
+    b->ctx->begin(0); launch_detect_mask(dev, E_dev, b->ctx->stream); b->ctx->end();
     b->ctx->launches += 1;
     if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,
                                   cudaMemcpyDeviceToDevice, b->ctx->stream));
     SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_get_active(sdfc_batch* b, int env, int pair, uint8_t* active_out) {
+    SDFC_REQUIRE(b && active_out, "sdfc_batch_get_active: NULL argument");
+    SDFC_REQUIRE(env >= 0 && env < b->n_envs && pair >= 0 && pair < b->n_pairs, "sdfc_batch_get_active: index out of range");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    const sdfc_points* pts = b->pairs[pair]->pts;
+    const int n = pts->n, nw = (n + 31) / 32;
+    int word_offset = 0;
+    for (int i = 0; i < pair; ++i) word_offset += (b->pairs[i]->pts->n + 31) / 32;
+    std::vector<uint32_t> words((size_t)std::max(nw, 1));
+    SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (nw) SDFC_CUDA(cudaMemcpy(words.data(), b->d_mask + (size_t)env * b->dev.words_per_env + word_offset, sizeof(uint32_t) * nw,
+                                 cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const uint8_t bit = (words[i >> 5] >> (i & 31)) & 1u;
+        active_out[pts->perm.empty() ? i : pts->perm[i]] = bit;
+    }
     return SDFC_OK;
 }
 

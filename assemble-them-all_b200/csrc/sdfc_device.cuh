@@ -37,6 +37,16 @@ struct GridDev {
     // instead of four scattered row segments; 8x the footprint of the plain fp32
     // grid, which HBM capacity (180 GB) makes a non-issue.
     const float4* c32;
+    // fp32-lossless BRICKED grid or nullptr (large grids, where cell records would not stay in L2):
+    // the plain fp32 node values in 4 x 4 x 4 bricks of 256 contiguous bytes, brick (bx, by, bz) at
+    // bx + nbx * (by + nby * bz), node (i, j, k) at (i & 3) + 4 * (j & 3) + 16 * (k & 3) inside its brick.
+    // One padded node layer past n - 1 on every axis replicates the last layer, so the reference's
+    // upper clamp (BodySDFObj.cpp:137-140) is a plain + 1. 4 B per node instead of 32 B per cell; a
+    // detection tile stages the bricks under its bounding box in shared memory with TMA (sdfc_brick.cu),
+    // every other kernel gathers the 8 corners from global memory (load_cell).
+    const float* b32;
+    const void* tmaps;     // device array of 16 x 16 CUtensorMap: box = 64 floats x nbx x nby x 1 bricks
+    int nbx, nby, nbz;
     int ni, nj, nk;
     double mn[3], mx[3];
     double dx, dy, dz;
@@ -50,6 +60,7 @@ struct GridDev {
     // faces of [mn, mx] (they lie inside those layers). A point outside the box has d = FLT_MAX; to
     // become active it must first cross a face, so bmin + col_th is its margin.
     double bmin;
+    __host__ __device__ bool f32() const { return c32 != nullptr || b32 != nullptr; }
 };
 
 // a / b, correctly rounded, given rb = RN(1/b). Markstein's sequence: a first
@@ -73,9 +84,22 @@ __device__ __forceinline__ double grid_at64(const GridDev& G, int i, int j, int 
 
 // The 8 corners of cell (i,j,k) with the reference's upper clamp
 // (BodySDFObj.cpp:137-140). Index clamps to [0,n-1] only guard memory.
+// F32 = the grid is stored fp32-lossless, as cell records (c32) or as bricks (b32).
 template <bool F32>
 __device__ __forceinline__ void load_cell(const GridDev& G, int i, int j, int k, double v[8]) {
     i = max(0, min(i, G.ni - 1)); j = max(0, min(j, G.nj - 1)); k = max(0, min(k, G.nk - 1));
+    if (F32 && G.c32 == nullptr) {   // bricked layout (uniform branch): node + 1 always exists (padded layer)
+        const int i1 = i + 1, j1 = j + 1, k1 = k + 1;
+        const size_t ox0 = (size_t)(i >> 2) * 64 + (i & 3), ox1 = (size_t)(i1 >> 2) * 64 + (i1 & 3);
+        const size_t oy0 = (size_t)(j >> 2) * G.nbx * 64 + (j & 3) * 4, oy1 = (size_t)(j1 >> 2) * G.nbx * 64 + (j1 & 3) * 4;
+        const size_t sz = (size_t)G.nbx * G.nby * 64;
+        const size_t oz0 = (size_t)(k >> 2) * sz + (k & 3) * 16, oz1 = (size_t)(k1 >> 2) * sz + (k1 & 3) * 16;
+        v[0] = (double)__ldg(G.b32 + ox0 + oy0 + oz0); v[1] = (double)__ldg(G.b32 + ox1 + oy0 + oz0);
+        v[2] = (double)__ldg(G.b32 + ox0 + oy1 + oz0); v[3] = (double)__ldg(G.b32 + ox1 + oy1 + oz0);
+        v[4] = (double)__ldg(G.b32 + ox0 + oy0 + oz1); v[5] = (double)__ldg(G.b32 + ox1 + oy0 + oz1);
+        v[6] = (double)__ldg(G.b32 + ox0 + oy1 + oz1); v[7] = (double)__ldg(G.b32 + ox1 + oy1 + oz1);
+        return;
+    }
     if (F32) {
         const size_t idx = (size_t)i + (size_t)G.ni * ((size_t)j + (size_t)G.nj * (size_t)k);
         // one 256-bit read-only load of the 32-byte cell record (LDG.E.256 on sm_100a):

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
     const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
     const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
     const uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
-    const bool f32 = S.pd.grid.c32 != nullptr;
+    const bool f32 = S.pd.grid.f32();
     const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
     const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
 

@@ -73,6 +73,8 @@ struct sdfc_sdf {
     sdfc::GridDev dev{};
     double* d_g64 = nullptr;
     float4* d_c32 = nullptr;  // fp32 cell records (2 float4 per cell) when the grid is fp32-lossless
+    float* d_b32 = nullptr;   // or the bricked fp32 grid (large grids), with its TMA descriptor table
+    void* d_tmaps = nullptr;
     size_t count = 0;
     uint64_t version = 1;
     // grow-only scratch for the host-buffer sampling entry
@@ -87,6 +89,8 @@ struct sdfc_points {
     double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
     double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
     double bsphere[4] = {0, 0, 0, 0};  // (cx, cy, cz, r) of the whole set
+    double* d_tile_box = nullptr;  // (lo[3], hi[3]) per detection tile of the sorted copy
+    std::vector<int32_t> perm;     // sorted position -> original index (empty: identity)
     bool sorted = false;
 };
 

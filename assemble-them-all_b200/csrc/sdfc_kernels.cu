@@ -110,10 +110,20 @@ void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream)
     k_skin_decide<<<(n + 127) / 128, 128, 0, stream>>>(B, E);
 }
 
-template <bool F32, bool SKIN>
+// Where the 8 corner values of a query come from. GlobalSampler: gathered through L1 / L2 (cell records,
+// global bricks or the fp64 grid). BrickSampler (below): the tile's voxel brick staged in shared memory.
+template <bool F32>
+struct GlobalSampler {
+    __device__ __forceinline__ double eval(const GridDev& G, const double* R1, const double* p1, const double* R2,
+                                           const double* p2, double x0, double x1, double x2) {
+        return detect_point<F32>(G, R1, p1, R2, p2, x0, x1, x2);
+    }
+};
+
+template <bool F32, bool SKIN, class Sampler>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
-                                            int* s_count, const SkinCta& sk) {
+                                            int* s_count, const SkinCta& sk, Sampler& smp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifndef SDFC_DETECT_U
 #define SDFC_DETECT_U 1
@@ -206,7 +216,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
         for (int u = 0; u < U; ++u) {
             if (ws[u] < 0) continue;  // warp-uniform
             double d = 1e300;
-            if (inr[u]) d = detect_point<F32>(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]);
+            if (inr[u]) d = smp.eval(pd.grid, R1, p1, R2, p2, px[u], py[u], pz[u]);
             const bool act = inr[u] && d < 0.;
             const unsigned m = __ballot_sync(0xffffffffu, act);
             if (lane == 0) { mask_row[pd.word_offset + ws[u]] = m; cnt += __popc(m); }
@@ -280,15 +290,189 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     }
     __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
-    if (pd.grid.c32 != nullptr) detect_tile<true, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
-    else detect_tile<false, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk);
+    if (pd.grid.f32()) { GlobalSampler<true> smp; detect_tile<true, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk, smp); }
+    else { GlobalSampler<false> smp; detect_tile<false, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk, smp); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+}
+
+// --------------------------------------------------------------------------
+// detection with the tile's voxel brick staged in shared memory by TMA
+// --------------------------------------------------------------------------
+// For grids that do not stay in L2 (GridDev::b32, 4 B per node) a gather per query costs a full DRAM
+// line per corner group. Instead the CTA of a tile (2048 spatially sorted points) maps the tile's box
+// (PairDev::tile_box, contact-body frame) into the SDF frame, takes the bricks under it, and pulls them
+// into shared memory with cp.async.bulk.tensor (one 4-D box of 64 x nbx x nby x 1 per brick layer,
+// completion on an mbarrier) while the broad phase and the point transforms run. Every query then reads
+// its 8 corners from shared memory: same values, same lerp sequence, same bits as BodySDFObj.cpp:132-153.
+// A tile whose brick does not fit (or a pair without bricks) gathers from global memory as before.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_bricks(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct BrickSampler {
+    const float* sb;     // staged bricks [nbz][nby][nbx][64] or nullptr (global gathers)
+    uint64_t* bar;
+    int bx0, by0, bz0, nbx, nby, nbz;
+    bool waited;
+    __device__ __forceinline__ double eval(const GridDev& G, const double* R1, const double* p1, const double* R2,
+                                           const double* p2, double x0, double x1, double x2) {
+        double xw[3], x[3];
+        to_world(R1, p1, x0, x1, x2, xw);
+        to_local(R2, p2, xw, x);
+        if (!in_box(G, x[0], x[1], x[2])) return __dadd_rn((double)FLT_MAX, G.col_th);   // BodySDFObj.cpp:170,212
+        double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
+        double cj = exact_div(__dsub_rn(x[1], G.mn[1]), G.dy, G.rdy);
+        double ck = exact_div(__dsub_rn(x[2], G.mn[2]), G.dz, G.rdz);
+        int i = (int)floor(ci), j = (int)floor(cj), k = (int)floor(ck);
+        ci = __dsub_rn(ci, (double)i); cj = __dsub_rn(cj, (double)j); ck = __dsub_rn(ck, (double)k);
+        i = max(0, min(i, G.ni - 1)); j = max(0, min(j, G.nj - 1)); k = max(0, min(k, G.nk - 1));   // memory guard, as load_cell
+        double v[8];
+        const int i1 = i + 1, j1 = j + 1, k1 = k + 1;   // the padded layer replicates the clamp of BodySDFObj.cpp:137-140
+        const int rx0 = (i >> 2) - bx0, rx1 = (i1 >> 2) - bx0, ry0 = (j >> 2) - by0, ry1 = (j1 >> 2) - by0;
+        const int rz0 = (k >> 2) - bz0, rz1 = (k1 >> 2) - bz0;
+        // the brick covers the image of the tile's box, so this always holds for a staged tile; checked anyway
+        const bool staged = sb != nullptr && rx0 >= 0 && rx1 < nbx && ry0 >= 0 && ry1 < nby && rz0 >= 0 && rz1 < nbz;
+        if (staged) {
+            if (!waited) { mbar_wait(bar, 0); waited = true; }
+            const int sy = nbx * 64, sz = sy * nby;
+            const int ox0 = rx0 * 64 + (i & 3), ox1 = rx1 * 64 + (i1 & 3);
+            const int oy0 = ry0 * sy + (j & 3) * 4, oy1 = ry1 * sy + (j1 & 3) * 4;
+            const int oz0 = rz0 * sz + (k & 3) * 16, oz1 = rz1 * sz + (k1 & 3) * 16;
+            v[0] = (double)sb[ox0 + oy0 + oz0]; v[1] = (double)sb[ox1 + oy0 + oz0];
+            v[2] = (double)sb[ox0 + oy1 + oz0]; v[3] = (double)sb[ox1 + oy1 + oz0];
+            v[4] = (double)sb[ox0 + oy0 + oz1]; v[5] = (double)sb[ox1 + oy0 + oz1];
+            v[6] = (double)sb[ox0 + oy1 + oz1]; v[7] = (double)sb[ox1 + oy1 + oz1];
+        } else {
+            load_cell<true>(G, i, j, k, v);
+        }
+        return __dadd_rn(lerp8(v, ci, cj, ck), G.col_th);
+    }
+};
+
+__global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, const double* __restrict__ E) {
+    extern __shared__ __align__(128) unsigned char brick_raw[];
+    __shared__ PairDev pd;
+    __shared__ double R1[9], p1[3], R2[9], p2[3];
+    __shared__ int s_count;
+    __shared__ int s_live[2 * kDetectTileWords];
+    __shared__ int s_nlive[kDetectThreads / 32];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_brick[7];   // bx0, by0, bz0, nbx, nby, nbz, staged
+    const int tile = blockIdx.x, env = blockIdx.y + B.env0;
+    if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;
+    const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
+    {
+        const int* src = reinterpret_cast<const int*>(B.pairs + pair);
+        int* dst = reinterpret_cast<int*>(&pd);
+        for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) { s_count = 0; s_brick[6] = 0; mbar_init(&s_bar, 1); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) stage_pose(E, B.n_bodies, env, pd.body_a, R1, p1, threadIdx.x);
+    else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E, B.n_bodies, env, pd.body_b, R2, p2, threadIdx.x - 32);
+    __syncthreads();
+    float* sb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(brick_raw) + 127) & ~(uintptr_t)127);
+    const bool bricks = pd.grid.b32 != nullptr && pd.grid.tmaps != nullptr && pd.tile_box != nullptr;
+    if (bricks && threadIdx.x < 32) {
+        // image of the tile's box in the SDF frame: min / max over its 8 corners (lanes 0..7)
+        const double* tb = pd.tile_box + 6 * (size_t)(word0 / kDetectTileWords);
+        const int c = threadIdx.x & 7;
+        double cw[3], cl[3];
+        to_world(R1, p1, __ldg(tb + ((c & 1) ? 3 : 0)), __ldg(tb + ((c & 2) ? 4 : 1)), __ldg(tb + ((c & 4) ? 5 : 2)), cw);
+        to_local(R2, p2, cw, cl);
+        double lo[3] = {cl[0], cl[1], cl[2]}, hi[3] = {cl[0], cl[1], cl[2]};
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        if (threadIdx.x == 0) {
+            // only points inside [mn, mx] sample the grid; 1e-7 covers the rounding of the transforms (as the broad phase)
+            const GridDev& G = pd.grid;
+            const double dd[3] = {G.dx, G.dy, G.dz}, rd[3] = {G.rdx, G.rdy, G.rdz};
+            const int nn[3] = {G.ni, G.nj, G.nk}, nbr[3] = {G.nbx, G.nby, G.nbz};
+            int b0[3], nb[3];
+            bool any = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double l = fmax(lo[a] - 1e-7, G.mn[a]), h = fmin(hi[a] + 1e-7, G.mx[a]);
+                any = any && (l <= h);
+                // cell index is monotonic in the coordinate (correctly rounded quotient, then floor)
+                int c0 = (int)floor(exact_div(__dsub_rn(l, G.mn[a]), dd[a], rd[a]));
+                int c1 = (int)floor(exact_div(__dsub_rn(h, G.mn[a]), dd[a], rd[a]));
+                c0 = max(0, min(c0, nn[a] - 1)); c1 = max(0, min(c1, nn[a] - 1));
+                b0[a] = c0 >> 2;
+                nb[a] = min(((c1 + 1) >> 2), nbr[a] - 1) - b0[a] + 1;   // + 1: upper neighbour node
+            }
+            const bool fits = any && nb[0] <= kBrickMaxXY && nb[1] <= kBrickMaxXY &&
+                              (size_t)nb[0] * nb[1] * nb[2] * 256 <= (size_t)kBrickSmemBytes;
+            s_brick[0] = b0[0]; s_brick[1] = b0[1]; s_brick[2] = b0[2];
+            s_brick[3] = nb[0]; s_brick[4] = nb[1]; s_brick[5] = nb[2];
+            s_brick[6] = fits ? 1 : 0;
+            if (fits) {
+                const uint32_t slice = (uint32_t)nb[0] * nb[1] * 256;
+                mbar_arrive_expect_tx(&s_bar, slice * nb[2]);
+                const unsigned char* tm = static_cast<const unsigned char*>(G.tmaps) +
+                                          (size_t)((nb[0] - 1) * kBrickMaxXY + (nb[1] - 1)) * 128;
+                for (int z = 0; z < nb[2]; ++z)
+                    tma_load_bricks(tm, &s_bar, reinterpret_cast<unsigned char*>(sb) + (size_t)z * slice, 0, b0[0], b0[1], b0[2] + z);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
+    SkinCta sk_unused;
+    const bool staged = s_brick[6] != 0;
+    if (pd.grid.b32 != nullptr) {
+        BrickSampler smp{staged ? sb : nullptr, &s_bar, s_brick[0], s_brick[1], s_brick[2], s_brick[3], s_brick[4], s_brick[5], false};
+        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+        if (staged && !smp.waited) mbar_wait(&s_bar, 0);   // the CTA must not retire under an in-flight bulk copy
+    } else if (pd.grid.f32()) {
+        GlobalSampler<true> smp;
+        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+    } else {
+        GlobalSampler<false> smp;
+        detect_tile<false, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+    }
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
 }
 
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream) {
     cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
+    if (B.n_tiles == 0 || B.env_count == 0) return;   // every pair has an empty point set: all counts stay 0
     dim3 grid(B.n_tiles, B.env_count);
+    if (B.any_bricks && B.skin_margin == nullptr) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_detect_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrickSmemBytes + 128);
+            configured = true;
+        }
+        k_detect_brick<<<grid, kDetectThreads, kBrickSmemBytes + 128, stream>>>(B, E);
+        return;
+    }
     if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreads, 0, stream>>>(B, E);
     else k_detect_mask<false><<<grid, kDetectThreads, 0, stream>>>(B, E);
 }
@@ -444,7 +628,7 @@ __global__ void __launch_bounds__(256) k_query_points(PairDev pd, const double* 
     else if (threadIdx.x >= 32 && threadIdx.x < 44) stage_pose(E2, 1, 0, 0, R2, p2, threadIdx.x - 32);
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    if (pd.grid.c32 != nullptr) query_points_body<true>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
+    if (pd.grid.f32()) query_points_body<true>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
     else query_points_body<false>(pd, R1, p1, R2, p2, d_out, cell_out, active_out, &s_count);
     __syncthreads();
     if (threadIdx.x == 0 && s_count) atomicAdd(n_active, s_count);
@@ -470,8 +654,43 @@ void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const dou
                          cudaStream_t stream) {
     if (n <= 0) return;
     const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)148 * 16));
-    if (G.c32 != nullptr) k_sdf_distance<true><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
+    if (G.f32()) k_sdf_distance<true><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
     else k_sdf_distance<false><<<blocks, 256, 0, stream>>>(G, n, x, y, z, out);
+}
+
+// query_SDF(x, true), query_dSDF and query_ddSDF at arbitrary points of the grid's frame
+// (BodySDFObj.cpp:123-205): the raw FD gradient / Hessian the contact kernels consume, exposed
+// so that rows a6 / a7 of the scope table can be compared with the reference bit for bit.
+// fast != 0 runs the shared-stencil path of the planner kernel (sdf_stencil), else the
+// sample-by-sample path of the general kernel (sdf_stencil_generic).
+template <bool F32>
+__global__ void __launch_bounds__(128) k_sdf_stencil(GridDev G, int64_t n, const double* __restrict__ x,
+                                                     const double* __restrict__ y, const double* __restrict__ z, int fast,
+                                                     double* __restrict__ acc, double* __restrict__ grad,
+                                                     double* __restrict__ hess) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_pad = (n + 31) / 32 * 32;   // sdf_stencil votes across the warp: whole warps iterate together
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        const int64_t j = i < n ? i : n - 1;
+        const double p[3] = {__ldg(x + j), __ldg(y + j), __ldg(z + j)};
+        double d, g[3], H[9];
+        if (fast) sdf_stencil<F32>(G, p, d, g, H);
+        else sdf_stencil_generic<F32>(G, p, d, g, H);
+        if (i >= n) continue;
+        if (acc) acc[i] = query_sdf<F32>(G, p[0], p[1], p[2], true, nullptr);
+        if (grad) { grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2]; }
+        if (hess)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) hess[9 * i + q] = H[q];
+    }
+}
+
+void launch_sdf_stencil(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, int fast,
+                        double* acc, double* grad, double* hess, cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = (int)max((int64_t)1, min((n + 127) / 128, (int64_t)148 * 8));
+    if (G.f32()) k_sdf_stencil<true><<<blocks, 128, 0, stream>>>(G, n, x, y, z, fast, acc, grad, hess);
+    else k_sdf_stencil<false><<<blocks, 128, 0, stream>>>(G, n, x, y, z, fast, acc, grad, hess);
 }
 
 __global__ void k_aos_to_soa(const double* __restrict__ aos, int64_t n, double* __restrict__ x, double* __restrict__ y,
@@ -502,6 +721,25 @@ void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, c
     const size_t n = (size_t)ni * nj * nk;
     const int blocks = (int)max((size_t)1, min((n + 255) / 256, (size_t)148 * 16));
     k_build_cells<<<blocks, 256, 0, stream>>>(g32, ni, nj, nk, out);
+}
+
+// Builds the bricked fp32 layout (GridDev::b32) from the plain fp32 grid: one thread per brick node,
+// node indices past n - 1 replicate the last layer.
+__global__ void k_build_bricks(const float* __restrict__ g, int ni, int nj, int nk, int nbx, int nby, int nbz,
+                               float* __restrict__ out) {
+    const size_t n = (size_t)nbx * nby * nbz * 64;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int in = (int)(idx & 63);
+        const size_t b = idx >> 6;
+        const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((size_t)nbx * nby));
+        const int i = min(4 * bx + (in & 3), ni - 1), j = min(4 * by + ((in >> 2) & 3), nj - 1), k = min(4 * bz + (in >> 4), nk - 1);
+        out[idx] = g[(size_t)i + (size_t)ni * ((size_t)j + (size_t)nj * (size_t)k)];
+    }
+}
+void launch_build_bricks(const float* g32, int ni, int nj, int nk, int nbx, int nby, int nbz, float* out, cudaStream_t stream) {
+    const size_t n = (size_t)nbx * nby * nbz * 64;
+    const int blocks = (int)max((size_t)1, min((n + 255) / 256, (size_t)148 * 16));
+    k_build_bricks<<<blocks, 256, 0, stream>>>(g32, ni, nj, nk, nbx, nby, nbz, out);
 }
 
 // Squared Lipschitz bound of the trilinear interpolant (GridDev::lip): inside a cell each gradient

@@ -17,6 +17,10 @@ struct PairDev {
     // in the contact body's frame: lets detection skip whole words that cannot
     // reach the SDF's box (they would all return FLT_MAX, BodySDFObj.cpp:170)
     const double* wsphere;
+    // axis-aligned box (lo[3], hi[3]) of every detection tile (kDetectTileWords words) of the sorted copy,
+    // in the contact body's frame: the voxel brick a tile stages in shared memory is the grid region under
+    // the image of this box (sdfc_kernels.cu, k_detect_brick)
+    const double* tile_box;
     double bsphere[4];   // bounding sphere of the whole point set (pair-level culling of the stepper)
     int n;            // number of contact points
     int n_words;      // ceil(n / 32) mask words
@@ -60,6 +64,7 @@ struct BatchDev {
     const int* tile_word0;
     int n_tiles;
     int splits;  // force CTAs per (env, pair)
+    int any_bricks;     // some pair samples a bricked grid (GridDev::b32): detection stages voxel bricks with TMA
     uint32_t* mask;     // [n_envs][words_per_env]
     int32_t* n_active;  // [n_envs][n_pairs]
     double* partial;    // [n_envs][n_pairs][splits][kPartial*]
@@ -109,8 +114,16 @@ void launch_query_points(const PairDev& pair_host_copy, const double* E1, const 
 // Raw SDF sampling (SDFMesh::distance): SoA points in the grid's frame.
 void launch_sdf_distance(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, double* out,
                          cudaStream_t stream);
+// query_SDF(x, true) / query_dSDF / query_ddSDF at SoA points of the grid's frame (any output may be nullptr).
+void launch_sdf_stencil(const GridDev& G, int64_t n, const double* x, const double* y, const double* z, int fast,
+                        double* acc, double* grad, double* hess, cudaStream_t stream);
 void launch_min_reduce(const double* v, int64_t n, double* out_scalar, double* scratch, cudaStream_t stream);
 void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, cudaStream_t stream);
+// plain fp32 grid -> 4 x 4 x 4 bricks with one replicated node layer past n - 1 (GridDev::b32)
+void launch_build_bricks(const float* g32, int ni, int nj, int nk, int nbx, int nby, int nbz, float* out, cudaStream_t stream);
+// shared-memory bytes a k_detect_brick CTA may use for its voxel brick
+constexpr int kBrickSmemBytes = 72 * 1024;
+constexpr int kBrickMaxXY = 16;   // tensor-map table: box = 64 floats x (1..16) x (1..16) x 1 bricks
 // *out (zeroed by the caller) = bit pattern of the squared Lipschitz bound of the interpolant (GridDev::lip)
 void launch_grid_lipschitz(const double* g64, int ni, int nj, int nk, double dx, double dy, double dz,
                            unsigned long long* out, cudaStream_t stream);

@@ -5,6 +5,7 @@
 #include "ForceGeneralSDFContactB200.h"
 
 #include "Body/Body.h"
+#include "Body/BodyCuboid.h"
 #include "Body/BodySDFObj.h"
 #include "Robot.h"
 #include "Simulation.h"
@@ -19,18 +20,42 @@ using b200::cache;
 using b200::check;
 using b200::DeviceCache;
 
-sdfc_points* b200::contact_points_of(Body* body) {
+sdfc_points* b200::contact_points_of(Body* body, bool general_sdf) {
     DeviceCache& c = cache();
-    auto ip = c.pts.find(body);
+    std::vector<Vector3> cp = body->get_contact_points();  // Body.h:129
+    if (general_sdf) {                                     // CollisionDetection.cpp:128-131
+        if (auto* cuboid = dynamic_cast<BodyCuboid*>(body)) cp = cuboid->get_general_contact_points();
+    }
+    std::vector<double> xyz(3 * cp.size());
+    for (size_t i = 0; i < cp.size(); ++i) { xyz[3 * i] = cp[i](0); xyz[3 * i + 1] = cp[i](1); xyz[3 * i + 2] = cp[i](2); }
+    const uint64_t n = cp.size();
+    const uint64_t key = b200::fnv1a(xyz.data(), xyz.size() * sizeof(double), b200::fnv1a(&n, sizeof(n)));
+    auto ip = c.pts.find(key);
     if (ip == c.pts.end()) {
-        std::vector<Vector3> cp = body->get_contact_points();  // Body.h:129
-        std::vector<double> xyz(3 * cp.size());
-        for (size_t i = 0; i < cp.size(); ++i) { xyz[3 * i] = cp[i](0); xyz[3 * i + 1] = cp[i](1); xyz[3 * i + 2] = cp[i](2); }
         sdfc_points* p = nullptr;
         check(sdfc_points_create(c.ctx, (int)cp.size(), xyz.data(), /*morton_sort=*/1, &p), "B200 contact path: contact point upload");
-        ip = c.pts.emplace(body, p).first;
+        ip = c.pts.emplace(key, p).first;
     }
     return ip->second;
+}
+
+sdfc_sdf* b200::sdf_of(const BodySDFObj* body) {
+    DeviceCache& c = cache();
+    // fields of BodySDFObj (Body/BodySDFObj.h:13-16); grid a[i + ni*(j + nj*k)]
+    const auto& G = body->_SDF;
+    const double meta[13] = {(double)G.ni, (double)G.nj, (double)G.nk, body->_min_box(0), body->_min_box(1), body->_min_box(2),
+                             body->_max_box(0), body->_max_box(1), body->_max_box(2), body->_dx, body->_dy, body->_dz,
+                             body->_col_th};
+    const uint64_t key = b200::fnv1a(G.a.data(), G.a.size() * sizeof(double), b200::fnv1a(meta, sizeof(meta)));
+    auto is = c.sdf.find(key);
+    if (is == c.sdf.end()) {
+        sdfc_sdf* s = nullptr;
+        check(sdfc_sdf_create(c.ctx, G.ni, G.nj, G.nk, body->_min_box.data(), body->_max_box.data(), body->_dx, body->_dy,
+                              body->_dz, body->_col_th, G.a.data(), &s),
+              "ForceGeneralSDFContactB200: SDF upload");
+        is = c.sdf.emplace(key, s).first;
+    }
+    return is->second;
 }
 
 ForceGeneralSDFContactB200::ForceGeneralSDFContactB200(Simulation* sim, Body* contact_body, Body* SDF_body, dtype kn,
@@ -41,21 +66,11 @@ void ForceGeneralSDFContactB200::init() { ensure_uploaded(); }
 
 void ForceGeneralSDFContactB200::ensure_uploaded() {
     if (_pair != nullptr) return;
-    DeviceCache& c = cache();
-    _ctx = c.ctx;
-    auto is = c.sdf.find(_SDF_body);
-    if (is == c.sdf.end()) {
-        // fields of BodySDFObj (Body/BodySDFObj.h:13-16); grid a[i + ni*(j + nj*k)]
-        const auto& G = _SDF_body->_SDF;
-        sdfc_sdf* s = nullptr;
-        check(sdfc_sdf_create(_ctx, G.ni, G.nj, G.nk, _SDF_body->_min_box.data(), _SDF_body->_max_box.data(),
-                              _SDF_body->_dx, _SDF_body->_dy, _SDF_body->_dz, _SDF_body->_col_th, G.a.data(), &s),
-              "ForceGeneralSDFContactB200: SDF upload");
-        is = c.sdf.emplace(_SDF_body, s).first;
-    }
-    _sdf = is->second;
-    _pts = b200::contact_points_of(_contact_body);
+    _ctx = cache().ctx;
+    _sdf = b200::sdf_of(_SDF_body);
+    _pts = b200::contact_points_of(_contact_body, /*general_sdf=*/true);
     check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
+    _sync_col_th = _SDF_body->_col_th;
     _synced = false;
 }
 
@@ -69,7 +84,15 @@ void ForceGeneralSDFContactB200::sync_parameters() {
     check(sdfc_pair_set_damping(_pair, _damping), "set_damping");
     check(sdfc_pair_set_scale(_pair, _scale), "set_scale");
     check(sdfc_pair_set_contact_scale(_pair, cs), "set_contact_scale");
-    if (!_synced || _sync_col_th != cth) check(sdfc_sdf_set_col_th(_sdf, cth), "set_col_th");
+    if (_sync_col_th != cth) {
+        // device grids are shared between bodies with equal content (B200DeviceCache.h) and col_th is part
+        // of the key: a changed threshold re-points this force at the matching grid instead of mutating a
+        // shared one
+        check(sdfc_pair_destroy(_pair), "pair_destroy");
+        _pair = nullptr;
+        _sdf = b200::sdf_of(_SDF_body);
+        check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
+    }
     _sync_kn = _kn; _sync_kt = _kt; _sync_mu = _mu; _sync_damping = _damping; _sync_scale = _scale;
     _sync_contact_scale = cs; _sync_col_th = cth;
     _synced = true;

@@ -96,6 +96,10 @@ SDFC_API sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk,
 SDFC_API sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th);
 /* 1 if the fp32-lossless copy is in use, else 0. */
 SDFC_API int sdfc_sdf_is_fp32(const sdfc_sdf* sdf);
+/* device storage of the grid: 0 = fp64 only, 1 = fp32 cell records (32 B per cell), 2 = fp32 bricks (4 B per
+ * node, 4x4x4 bricks staged per detection tile with TMA; chosen for grids whose records exceed ~96 MB, or with
+ * the environment variable SDFC_GRID_LAYOUT=bricks|records) */
+SDFC_API int sdfc_sdf_layout_kind(const sdfc_sdf* sdf);
 SDFC_API sdfc_status sdfc_sdf_destroy(sdfc_sdf* sdf);
 
 /* Batched raw sampling = SDFMesh::distance / min_distance (Mesh.cpp:143-198,
@@ -104,6 +108,12 @@ SDFC_API sdfc_status sdfc_sdf_destroy(sdfc_sdf* sdf);
 SDFC_API sdfc_status sdfc_sdf_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_host);
 SDFC_API sdfc_status sdfc_sdf_min_distance(sdfc_sdf* sdf, int64_t n, const double* X_host, double* out_min);
 /* Device-resident form: SoA inputs already in HBM, result left in HBM. */
+/* BodySDFObj::query_SDF(x, true), query_dSDF and query_ddSDF (Body/BodySDFObj.cpp:123-205) at n points
+ * (AoS, grid frame): sdf_acc_out[n], grad_out[3n], hess_out[9n] row-major; any output may be NULL.
+ * fast != 0 evaluates the shared-stencil path of the planner kernel, 0 the sample-by-sample path;
+ * both are bit-identical to the reference (rows a6 / a7 of the scope table). */
+SDFC_API sdfc_status sdfc_sdf_stencil(sdfc_sdf* sdf, int64_t n, const double* X_host, int fast, double* sdf_acc_out,
+                                      double* grad_out, double* hess_out);
 SDFC_API sdfc_status sdfc_sdf_distance_device(sdfc_sdf* sdf, int64_t n, const double* dx, const double* dy,
                                               const double* dz, double* dout);
 
@@ -133,8 +143,9 @@ SDFC_API sdfc_status sdfc_sdf_load_text(const char* path, double min_box[3], dou
                                         double* grid, int64_t capacity);
 
 /* ---- contact points: Body::_contact_points (Body/Body.h:36,129) -------- */
-/* morton_sort != 0 stores a spatially sorted SoA copy for the force path (the
- * original order is kept for every per-point output). */
+/* morton_sort != 0 stores a spatially sorted SoA copy for the force path and batched detection (the
+ * original order is kept for every per-point output): 1 = 30-bit Morton order, 2 = k-d order whose
+ * 2048-point detection tiles and 32-point words are compact boxes (what the TMA brick staging wants). */
 SDFC_API sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host, int morton_sort,
                                         sdfc_points** out);
 SDFC_API int sdfc_points_count(const sdfc_points* pts);
@@ -250,6 +261,10 @@ SDFC_API sdfc_status sdfc_batch_eval_device(sdfc_batch* batch, const double* E_d
 SDFC_API sdfc_status sdfc_batch_detect_device(sdfc_batch* batch, const double* E_dev, int32_t* n_active_dev);
 
 /* Total detection queries one batch evaluation performs = n_envs * sum_p n_p. */
+/* The 1-bit active mask of the last detection (batched kernel) for one (environment, pair), expanded
+ * to active_out[n] (0 / 1) in the ORIGINAL contact-point order: the d < 0 test of
+ * collision_detection_general_SDF (CollisionDetection.cpp:137-138). Synchronises. */
+SDFC_API sdfc_status sdfc_batch_get_active(sdfc_batch* batch, int env, int pair, uint8_t* active_out);
 SDFC_API int64_t sdfc_batch_queries_per_eval(const sdfc_batch* batch);
 
 /* ---- batched BDF1 stepper: Simulation::forward for E environments -------- */

@@ -9,6 +9,7 @@ on the same box (oracle/_ref/ref_probe, CPU). The reference builds the scene fro
 Bars: per-step q to 1e-9 relative while the trajectories are comparable step by step (C1 up to
 and through the first impacts, C3 throughout); for the free-running 2000-step C1 trajectory the
 accumulated drift is REPORTED (north_star asks for it) and bounded by the bar below."""
+import os
 import time
 
 import numpy as np
@@ -143,3 +144,178 @@ def test_c4_twenty_part_candidate_removals(cuda_ctx):
         assert touched >= 1
         sim.close()
     print("\nC4: " + "; ".join(report))
+
+
+# --------------------------------------------------------------------------- round 2 additions
+_POOL_PROBE = None
+
+
+def _pool_rollout(job):
+    """Worker of the fork pool below: the parent built `_POOL_PROBE` (reference Simulation) before forking."""
+    from oracle import ref_scene
+    q0, qd0, force, steps = job
+    p = _POOL_PROBE
+    t, qf, qdf, Q, QD = ref_scene.rollout(p, q0, qd0, force, steps, trajectory=True)
+    return t, Q, len(p.get_contact_bodies("part0")) > 0
+
+
+def _pool_freefall(job):
+    """Free-fall rollout of the reference from a given initial state; per-step q and convergence flags. Stops
+    a few steps after the first non-converged step (a failed Newton solve runs hundreds of evaluations)."""
+    q0, qd0, steps, tail = job
+    p = _POOL_PROBE
+    p.reset()
+    p.set_state_init(np.asarray(q0), np.asarray(qd0))
+    p.reset()
+    Q, conv, stop = [], [], None
+    for s in range(steps):
+        p.forward(1)
+        Q.append(p.get_q())
+        conv.append(bool(p.is_converged()))
+        if not conv[-1] and stop is None:
+            stop = s + tail
+        if stop is not None and s >= stop:
+            break
+    return np.array(Q), np.array(conv)
+
+
+def _fork_map(fn, jobs, procs):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(procs, len(jobs))) as pool:
+        return pool.map(fn, jobs, chunksize=1)
+
+
+def test_c3_all_twelve_actions_100_steps(cuda_ctx):
+    """C3 (BASELINE.json configs[2]) in full: ~100 000 contact points per part, every one of the rotational
+    planner's 12 actions (run_joint_plan.py:585-598) for frame_skip = 100 steps from a start inside the hole,
+    per-step q against the reference's Simulation::forward, contact-history flags equal. The reference
+    rollouts are fanned out over the host cores (fork after the probe is built)."""
+    global _POOL_PROBE
+    from assemble_them_all_b200 import contact
+    from assemble_them_all_b200 import planner as PL
+    p, ref_scene = _probe(synth.peg_in_hole(n_vertices=100000),
+                          lambda d: synth.planner_xml(d, "0", ["1"], joint_type="free3d-exp", sdf_dx=0.05))
+    sc = ref_scene.extract_scene(p)
+    steps, n_act = 100, 12
+    forces = np.array([PL.action_to_force(PL.ROT_ACTIONS[a], 100.0) for a in range(n_act)])
+    q0 = np.zeros(6)
+    q0[2] = 1.0
+    sim = contact.build_simulation(cuda_ctx, sc, n_act)
+    sim.reset(np.tile(q0, (n_act, 1)), np.zeros((n_act, 6)))
+    sim.set_body_external_force(0, forces)
+    q, _ = sim.forward(steps, trajectory=True)
+    hist = sim.get_contact_history().any(axis=1)
+    _POOL_PROBE = p
+    t0 = time.perf_counter()
+    res = _fork_map(_pool_rollout, [(q0, np.zeros(6), forces[a], steps) for a in range(n_act)], os.cpu_count() or 1)
+    wall = time.perf_counter() - t0
+    _POOL_PROBE = None
+    worst = [rel_err(Q, q[:, a]) for a, (_, Q, _) in enumerate(res)]
+    touched = [t for _, _, t in res]
+    print(f"\nC3 full: {n_act} actions x {steps} steps; reference {sum(r[0] for r in res):.1f} s CPU ({wall:.1f} s wall); "
+          f"max rel err of q per action {['%.1e' % w for w in worst]}; touched {sum(touched)}/{n_act}")
+    assert max(worst) <= 1e-9
+    assert [bool(h) for h in hist] == touched
+    assert sum(touched) >= 6
+    assert sim.is_converged().all()
+    sim.close()
+
+
+def test_c1_batch_convergence_flags_match_reference(cuda_ctx):
+    """The batched C1 drops (bench.py c1_leg: seeded tilts / lateral velocities onto a frictional ground):
+    a few of them do not converge after hard impacts. Newton convergence must agree with the reference
+    environment by environment and step by step: every drop whose GPU run has a non-converged step, plus a
+    sample of converged ones, is re-run on the reference from the same initial state. Until the first failed
+    solve q agrees to 1e-9; the step index of the first failed solve is the same on both sides."""
+    global _POOL_PROBE
+    from assemble_them_all_b200 import contact
+    p, ref_scene = _probe(synth.peg_in_hole(n_vertices=10000), lambda d: synth.freefall_xml(d, sdf_dx=0.05, gravity=9.8, friction=0))
+    sc = ref_scene.extract_scene(p)
+    n_envs, steps = 256, 100
+    rng = np.random.default_rng(20221)
+    q0 = np.zeros((n_envs, 12))
+    qd0 = np.zeros((n_envs, 12))
+    q0[:, 2] = rng.uniform(-0.9, -0.6, n_envs) - 2.0     # as scenes.c1_freefall_rollouts, in this scene's joint coordinates
+    q0[:, 8] = -3.0 + rng.uniform(0.005, 0.05, n_envs)
+    q0[:, 3:6] = rng.normal(scale=0.01, size=(n_envs, 3))
+    q0[:, 9:12] = rng.normal(scale=0.005, size=(n_envs, 3))
+    qd0[:, 0:2] = rng.normal(scale=0.2, size=(n_envs, 2))
+    qd0[:, 6:8] = rng.normal(scale=0.2, size=(n_envs, 2))
+    sim = contact.build_simulation(cuda_ctx, sc, n_envs)
+    sim.reset(q0, qd0)
+    Q = np.empty((steps, n_envs, 12))
+    conv = np.empty((steps, n_envs), dtype=bool)
+    for s in range(steps):
+        qs, _ = sim.forward(1, trajectory=True)
+        Q[s] = qs[0]
+        conv[s] = sim.is_converged()
+    bad = np.where(~conv.all(axis=0))[0]
+    good = np.where(conv.all(axis=0))[0]
+    pick = list(bad[:24]) + list(good[:: max(1, len(good) // 8)][:8])
+    _POOL_PROBE = p
+    t0 = time.perf_counter()
+    res = _fork_map(_pool_freefall, [(q0[e], qd0[e], steps, 2) for e in pick], os.cpu_count() or 1)
+    wall = time.perf_counter() - t0
+    _POOL_PROBE = None
+    report = []
+    for e, (Qr, cr) in zip(pick, res):
+        n = len(cr)
+        first_ref = int(np.argmin(cr)) if not cr.all() else -1
+        first_gpu = int(np.argmin(conv[:, e])) if not conv[:, e].all() else -1
+        upto = n if first_ref < 0 else first_ref       # steps before the first failed solve
+        err = rel_err(Qr[:upto], Q[:upto, e]) if upto else 0.0
+        report.append((int(e), first_gpu, first_ref, err))
+        assert first_gpu == first_ref, f"env {e}: first non-converged step GPU {first_gpu} vs reference {first_ref}"
+        assert err <= 1e-9, f"env {e}: q differs by {err:.2e} before the first failed solve"
+    print(f"\nC1 batch: {n_envs} drops x {steps} steps, {len(bad)} with a non-converged step on the GPU; "
+          f"{len(pick)} re-run on the reference ({wall:.1f} s wall): (env, first failed step GPU, reference, rel err of q before it) = {report}")
+    sim.close()
+
+
+def test_three_part_rollout_on_reloaded_sdf_cache(cuda_ctx, tmp_path):
+    """The path every run_multi_plan planner after the first one takes: the reference writes
+    `<part>.sdf` through BodySDFObj::save_SDF, a second construction reloads the 6-significant-digit text
+    (BodySDFObj.cpp:86-116), so its grids are fp64 and no longer fp32-representable. The CUDA stepper runs on
+    exactly those reloaded grids (fp64 storage path) and must follow the reference's rollouts to 1e-9;
+    the library's own reader must return the same grids from the reference's files bit for bit."""
+    from assemble_them_all_b200 import contact
+    from assemble_them_all_b200 import planner as PL
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    rp = ref_scene._import_probe()
+    parts = synth.l_channel_with_plug()
+    folder = str(tmp_path / "asm")
+    synth.write_assembly(parts, folder)
+    xml = synth.planner_xml(folder, "2", ["0", "1"], sdf_dx=0.1, save_sdf=True)   # plug moves; cube and block still
+    p1 = rp.Probe(xml, folder)                     # computes the grids, save_SDF writes 0.sdf 1.sdf 2.sdf
+    fresh = ref_scene.extract_scene(p1)
+    p2 = rp.Probe(xml, folder)                     # load_SDF
+    sc = ref_scene.extract_scene(p2)
+    assert len(sc["bodies"]) == 3 and len(sc["forces"]) == 4
+    for b, body in enumerate(sc["bodies"]):
+        g = body["grid"]["grid"]
+        assert not np.array_equal(g, fresh["bodies"][b]["grid"]["grid"])                       # lossy round trip
+        assert not np.array_equal(g, g.astype(np.float32).astype(np.float64))                  # -> fp64 storage on the device
+        mine = contact.load_sdf_text(os.path.join(folder, f"{body['name'][4:]}.sdf"), col_th=body["grid"]["col_th"])
+        assert np.array_equal(mine["grid"], g.reshape(-1)) and mine["dx"] == body["grid"]["dx"]
+        assert np.array_equal(mine["min_box"], body["grid"]["min_box"]) and np.array_equal(mine["max_box"], body["grid"]["max_box"])
+    acts = [0, 4, 5, 2]                             # +z (pulls the plug out along the shaft), +x, -x, +y (shaft walls)
+    steps = 100
+    forces = np.array([PL.action_to_force(PL.TRANS_ACTIONS[a], 100.0) for a in acts])
+    sim = contact.build_simulation(cuda_ctx, sc, len(acts))
+    assert not any(s.is_fp32 for s in sim._keep[2].values())
+    sim.reset()
+    sim.set_body_external_force(0, forces)
+    q, _ = sim.forward(steps, trajectory=True)
+    hist = sim.get_contact_history()
+    worst, touched = 0.0, 0
+    for e in range(len(acts)):
+        t, qf, qdf, Q, QD = ref_scene.rollout(p2, np.zeros(3), np.zeros(3), forces[e], steps, trajectory=True, move_name="part2")
+        worst = max(worst, rel_err(Q, q[:, e]))
+        ref_touch = len(p2.get_contact_bodies("part2")) > 0
+        assert bool(hist[e].any()) == ref_touch
+        touched += ref_touch
+    print(f"\nreloaded .sdf grids: 3 parts, {len(acts)} rollouts x {steps} steps, max rel err of q {worst:.2e}, touched {touched}")
+    assert worst <= 1e-9 and touched >= 2
+    sim.close()

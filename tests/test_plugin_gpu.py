@@ -65,30 +65,9 @@ def test_reference_freefall_with_b200_ground_sdf_contact_and_sdfgen_matches_stoc
     print(msg_b)
     h = float(np.float32(1e-3))
 
-    def first_bad_step(a, b):
-        for s in range(a["Q"].shape[1]):
-            try:
-                assert_state_close(a["Q"][0, s], a["QD"][0, s], b["Q"][0, s], b["QD"][0, s], h, f"step {s}")
-            except AssertionError as exc:
-                return s, str(exc)
-        return -1, ""
-
-    bad, why = first_bad_step(stock, b200)
-    if bad >= 0:
-        # Seen twice in r1i inside a full-suite run (never in 30 stand-alone runs of either module): one
-        # arm's trajectory jumped by ~3e-7 at a contact event. Re-run both arms to say WHICH arm is not
-        # reproducible; a b200 arm that does not reproduce itself bit for bit is a failure of this repo.
-        stock2, _ = _run(REF, str(tmp_path / "stock2.npz"), "free3d-exp", steps=300, scene="freefall")
-        b2002, _ = _run(os.path.join(REF, "b200"), str(tmp_path / "b2002.npz"), "free3d-exp", steps=300, scene="freefall")
-        stock_rep = np.array_equal(stock["Q"], stock2["Q"])
-        b200_rep = np.array_equal(b200["Q"], b2002["Q"])
-        print(f"MISMATCH at step {bad} ({why}); second run: stock reproducible {stock_rep}, b200 reproducible {b200_rep}, "
-              f"stock2 vs b200 first bad {first_bad_step(stock2, b200)[0]}, stock vs b2002 first bad {first_bad_step(stock, b2002)[0]}")
-        assert b200_rep, f"b200 arm is not reproducible (first mismatch vs stock at step {bad}: {why})"
-        assert not stock_rep, f"both arms reproducible and different at step {bad}: {why}"
-        stock = stock2                                       # the reference arm changed between two runs of the same inputs
-        bad, why = first_bad_step(stock, b200)
-        assert bad < 0, why
+    # the reference's CPU path is deterministic: any stock != b200 difference is a failure of this repo
+    for s in range(stock["Q"].shape[1]):
+        assert_state_close(stock["Q"][0, s], stock["QD"][0, s], b200["Q"][0, s], b200["QD"][0, s], h, f"step {s}")
     assert np.array_equal(stock["sdfmesh_distance"], b200["sdfmesh_distance"])   # GPU sdfgen grid + GPU sampling (sdfc_sdf_distance)
     assert float(stock["sdfmesh_min_distance"]) == float(b200["sdfmesh_min_distance"])
     assert (stock["sdfmesh_distance"] < 1e30).any() and (stock["sdfmesh_distance"] > 1e30).any()  # inside and outside the box

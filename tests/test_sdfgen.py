@@ -67,6 +67,32 @@ def test_sdf_text_cache_round_trip(tmp_path):
     assert back["dx"] == float("%g" % sp[0])
 
 
+def test_sdf_text_cache_matches_the_reference_writer_and_reader(tmp_path):
+    """tests/golden/sdf_cache_small.sdf is the file the UNMODIFIED reference wrote through
+    BodySDFObj::save_SDF (BodySDFObj.cpp:105-116) for the fp32-valued grid in the .npz
+    (oracle/make_golden_sdf_cache.py); `reloaded_*` is what a second reference construction read
+    back through BodySDFObj::load_SDF (:86-103). The library's writer must reproduce the file byte
+    for byte and its reader the reloaded fields bit for bit."""
+    from assemble_them_all_b200 import contact
+    z = np.load(os.path.join(GOLDEN, "sdf_cache_small.npz"))
+    ref_bytes = open(os.path.join(GOLDEN, "sdf_cache_small.sdf"), "rb").read()
+    ni, nj, nk = (int(v) for v in z["fresh_dims"])
+    sp = z["fresh_spacing"]
+    g = {"ni": ni, "nj": nj, "nk": nk, "min_box": z["fresh_min_box"], "max_box": z["fresh_max_box"], "dx": sp[0], "dy": sp[1],
+         "dz": sp[2], "col_th": 0.0, "grid": z["fresh_grid"]}
+    path = tmp_path / "part.sdf"
+    contact.save_sdf_text(path, g)
+    assert open(path, "rb").read() == ref_bytes
+    back = contact.load_sdf_text(os.path.join(GOLDEN, "sdf_cache_small.sdf"), col_th=0.01)
+    assert (back["ni"], back["nj"], back["nk"]) == tuple(int(v) for v in z["reloaded_dims"])
+    assert np.array_equal(back["grid"], z["reloaded_grid"])
+    assert np.array_equal(back["min_box"], z["reloaded_min_box"]) and np.array_equal(back["max_box"], z["reloaded_max_box"])
+    assert np.array_equal([back["dx"], back["dy"], back["dz"]], z["reloaded_spacing"])
+    # the round trip is lossy (6 significant digits): reloaded grids are no longer fp32-representable
+    assert not np.array_equal(z["reloaded_grid"], z["fresh_grid"])
+    assert not np.array_equal(z["reloaded_grid"], z["reloaded_grid"].astype(np.float32).astype(np.float64))
+
+
 @pytest.mark.gpu
 def test_cuda_level_set_matches_reference_grids(cuda_ctx):
     from assemble_them_all_b200 import contact
