@@ -30,6 +30,7 @@ SIGNATURES = {
     "sdfc_context_launch_count": (C.c_int64, [C.c_void_p]),
     "sdfc_context_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "sdfc_context_read_timing": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int64), C.c_int]),
+    "sdfc_measure_peaks": (C.c_int, [C.c_void_p, c_double_p]),
     "sdfc_selftest_exact_div": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_double, C.POINTER(C.c_int64)]),
     "sdfc_sdf_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, C.c_double, C.c_double,
                                   C.c_double, C.c_double, c_double_p, c_void_pp]),
@@ -96,6 +97,7 @@ SIGNATURES = {
     "sdfc_sim_forward": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "sdfc_sim_get_status": (C.c_int, [C.c_void_p, c_uint8_p, c_uint8_p]),
     "sdfc_sim_get_poses": (C.c_int, [C.c_void_p, c_double_p]),
+    "sdfc_batch_get_brick_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "sdfc_batch_get_skin_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "sdfc_sim_get_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }

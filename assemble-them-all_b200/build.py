@@ -18,7 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("SDFC_OUT") or os.path.join(HERE, "libsdfcontact_b200.so")
-SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu", "sdfc_ground.cu", "sdfc_sdfgen.cu"]
+SOURCES = ["sdfc_kernels.cu", "sdfc_capi.cu", "sdfc_step.cu", "sdfc_ground.cu", "sdfc_sdfgen.cu", "sdfc_microbench.cu"]
 # sdfgen's fp32 / fp64 arithmetic has to match the reference's x86-64 build bit for bit: no FMA contraction
 PER_SOURCE_FLAGS = {"sdfc_sdfgen.cu": ["-fmad=false"]}
 FORCE_INST = "sdfc_force_inst.cu"  # compiled once per variant, -DSDFC_FORCE_VARIANT=0..7

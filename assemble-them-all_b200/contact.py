@@ -95,6 +95,12 @@ class Context:
         check(self._lib.sdfc_context_read_timing(self._h, ms, cnt, int(bool(reset))))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_SLOTS)}
 
+    def measure_peaks(self):
+        """{"fp64_gflops", "l2_read_gbs"}: DFMA and L2 -> SM ceilings measured on this device (roofline denominators)."""
+        out = (C.c_double * 4)()
+        check(self._lib.sdfc_measure_peaks(self._h, out))
+        return {"fp64_gflops": float(out[0]), "l2_read_gbs": float(out[1])}
+
     def selftest_exact_div(self, n, seed, b):
         """Mismatches between the library's reciprocal-based division and IEEE `/` (must be 0)."""
         bad = C.c_int64(-1)
@@ -445,6 +451,12 @@ class ContactBatch:
         s = (C.c_int64 * 4)()
         check(self._lib.sdfc_batch_get_skin_stats(self._h, s))
         return {"words_culled": int(s[0]), "margins_used_up": int(s[1]), "rebuilds": int(s[2]), "pairs_skipped": int(s[3])}
+
+    def brick_stats(self):
+        """{staged, too_large, outside}: detection tiles by how the TMA brick kernel served them (running totals)."""
+        s = (C.c_int64 * 3)()
+        check(self._lib.sdfc_batch_get_brick_stats(self._h, s))
+        return {"staged": int(s[0]), "too_large": int(s[1]), "outside": int(s[2])}
 
     def ground_active(self):
         """(n_envs, n_grounds) contact counts of the last evaluation."""

@@ -78,7 +78,7 @@ sdfc_status batch_refresh(sdfc_batch* b) {
 namespace sdfc_host {
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
                       bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev, int env0,
-                      int env_count) {
+                      int env_count, bool counts_zeroed) {
     sdfc_status st = batch_refresh(b);
     if (st != SDFC_OK) return st;
     if (env_count < 0) { env0 = 0; env_count = b->n_envs; }
@@ -90,7 +90,7 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     dev.env0 = env0; dev.env_count = env_count;
     c->begin(0);
     if (b->skin_on) { launch_skin_decide(dev, E_dev, s); c->launches += 1; }
-    launch_detect_mask(dev, E_dev, s);
+    launch_detect_mask(dev, E_dev, s, /*reset_counts=*/!counts_zeroed);
     c->end();
     c->begin(1);
     if (env_mode_dev != nullptr) {
@@ -833,6 +833,7 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     A(dev_alloc(&b->d_tile_word0, tile_word0.size()));
     A(dev_alloc(&b->d_mask, (size_t)n_envs * std::max(words, 1)));
     A(dev_alloc(&b->d_n_active, ep));
+    A(dev_alloc(&b->d_brick_stats, (size_t)3));
     A(dev_alloc(&b->d_partial, ep * splits * kPartialDerivDM));
     A(dev_alloc(&b->d_fm_sub, ep * 12));
     A(dev_alloc(&b->d_Km_sub, ep * 144));
@@ -850,6 +851,7 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
         if (e == cudaSuccess && !tile_pair.empty()) e = cudaMemcpy(b->d_tile_word0, tile_word0.data(), sizeof(int) * tile_word0.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(b->d_mask, 0, sizeof(uint32_t) * (size_t)n_envs * std::max(words, 1));
         if (e == cudaSuccess) e = cudaMemset(b->d_Dm_sub, 0, sizeof(double) * ep * 144);
+        if (e == cudaSuccess) e = cudaMemset(b->d_brick_stats, 0, sizeof(unsigned long long) * 3);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();  // null-stream work done before the context stream uses it
         if (e != cudaSuccess) st = fail(SDFC_ERR_CUDA, std::string("sdfc_batch_create: ") + cudaGetErrorString(e));
     }
@@ -862,6 +864,9 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     b->dev.n_tiles = (int)tile_pair.size();
     b->dev.splits = splits;
     b->dev.mask = b->d_mask; b->dev.n_active = b->d_n_active; b->dev.partial = b->d_partial;
+    b->dev.brick_stats = b->d_brick_stats;
+    b->dev.brick_cap = kBrickSmemBytes;
+    if (const char* cap = std::getenv("SDFC_BRICK_SMEM")) b->dev.brick_cap = std::max(0, std::min(kBrickSmemMax, std::atoi(cap)));
     *out = b;
     return SDFC_OK;
 }
@@ -870,7 +875,7 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     if (!b) return SDFC_OK;
     cudaSetDevice(b->ctx->device);
     cudaFree(b->d_pairs); cudaFree(b->d_tile_pair); cudaFree(b->d_tile_word0); cudaFree(b->d_mask);
-    cudaFree(b->d_n_active); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
+    cudaFree(b->d_n_active); cudaFree(b->d_brick_stats); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
     cudaFree(b->d_E); cudaFree(b->d_phi); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
     cudaFree(b->d_skin_margin); cudaFree(b->d_skin_pose); cudaFree(b->d_skin_int); cudaFree(b->d_skin_stats);
     if (b->h_in) cudaFreeHost(b->h_in);
@@ -899,6 +904,16 @@ sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* b, int64_t stats[4]) {
     SDFC_CUDA(cudaMemcpyAsync(c, b->d_skin_stats, sizeof(c), cudaMemcpyDeviceToHost, b->ctx->stream));
     SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
     for (int i = 0; i < 4; ++i) stats[i] = (int64_t)c[i];
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_get_brick_stats(sdfc_batch* b, int64_t stats[3]) {
+    SDFC_REQUIRE(b && stats, "sdfc_batch_get_brick_stats: NULL argument");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    unsigned long long c[3] = {0, 0, 0};
+    SDFC_CUDA(cudaMemcpyAsync(c, b->d_brick_stats, sizeof(c), cudaMemcpyDeviceToHost, b->ctx->stream));
+    SDFC_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    for (int i = 0; i < 3; ++i) stats[i] = (int64_t)c[i];
     return SDFC_OK;
 }
 
@@ -931,7 +946,7 @@ sdfc_status sdfc_batch_detect_device(sdfc_batch* b, const double* E_dev, int32_t
     // batch_run runs k_skin_decide before the SKIN kernel). The plain kernel leaves that state untouched.
     BatchDev dev = b->dev;
     dev.skin_margin = nullptr;
-    b->ctx->begin(0); launch_detect_mask(dev, E_dev, b->ctx->stream); b->ctx->end();
+    b->ctx->begin(0); launch_detect_mask(dev, E_dev, b->ctx->stream, true); b->ctx->end();
     b->ctx->launches += 1;
     if (n_active_dev != nullptr && n_active_dev != b->d_n_active)
         SDFC_CUDA(cudaMemcpyAsync(n_active_dev, b->d_n_active, sizeof(int32_t) * (size_t)b->n_envs * b->n_pairs,

@@ -121,6 +121,7 @@ struct sdfc_batch {
     uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; double* d_partial = nullptr;
     double* d_fm_sub = nullptr; double* d_Km_sub = nullptr; double* d_Dm_sub = nullptr;
     bool any_fric = false, any_damp = false;
+    unsigned long long* d_brick_stats = nullptr;
     int64_t queries = 0;
     // staging for the host-buffer entry
     double* d_E = nullptr; double* d_phi = nullptr; double* d_fm = nullptr; double* d_Km = nullptr; double* d_Dm = nullptr;
@@ -142,7 +143,7 @@ namespace sdfc_host {
 // env0 / env_count: environment range of this call (env_count < 0 = all environments).
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
                       bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev,
-                      int env0 = 0, int env_count = -1);
+                      int env0 = 0, int env_count = -1, bool counts_zeroed = false);
 // Allocates the skin state of a batch and switches the culling on (idempotent).
 sdfc_status batch_enable_skin(sdfc_batch* b);
 }  // namespace sdfc_host

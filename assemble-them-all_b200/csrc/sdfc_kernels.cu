@@ -114,6 +114,7 @@ void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream)
 // global bricks or the fp64 grid). BrickSampler (below): the tile's voxel brick staged in shared memory.
 template <bool F32>
 struct GlobalSampler {
+    static constexpr bool kPrefetch = false;
     __device__ __forceinline__ double eval(const GridDev& G, const double* R1, const double* p1, const double* R2,
                                            const double* p2, double x0, double x1, double x2) {
         return detect_point<F32>(G, R1, p1, R2, p2, x0, x1, x2);
@@ -123,7 +124,7 @@ struct GlobalSampler {
 template <bool F32, bool SKIN, class Sampler>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
-                                            int* s_count, const SkinCta& sk, Sampler& smp) {
+                                            int* s_count, const SkinCta& sk, Sampler& smp, bool all_live = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifndef SDFC_DETECT_U
 #define SDFC_DETECT_U 1
@@ -136,7 +137,12 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     // would evaluate to FLT_MAX + col_th > 0, i.e. inactive. Surviving words are compacted
     // (in word order) into shared memory and dealt round-robin to the warps, so that the
     // warps of a CTA finish together even when the contact region covers a few words only.
-    if (threadIdx.x < kDetectTileWords) {
+    if (all_live) {
+        // the whole tile lies inside the grid box (CTA-uniform): every word is live, in word order
+        const int nl = min(kDetectTileWords, pd.n_words - word0);
+        if (threadIdx.x < kDetectTileWords) s_live[kDetectTileWords + threadIdx.x] = word0 + threadIdx.x;
+        if (threadIdx.x == 0) { s_nlive[0] = min(nl, 32); s_nlive[1] = max(nl - 32, 0); }
+    } else if (threadIdx.x < kDetectTileWords) {
         const int w = word0 + threadIdx.x;
         bool keep = false, culled = false, used_up = false, elig_out = false;
         if (w < pd.n_words) {
@@ -193,25 +199,40 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     const int n0 = s_nlive[0], nlive = n0 + s_nlive[1];
     // rank -> word: scatter into a dense list (second half of s_live)
     int* list = s_live + kDetectTileWords;
-    if (threadIdx.x < kDetectTileWords) {
-        const int rk = s_live[threadIdx.x];
-        if (rk >= 0) list[rk + (threadIdx.x >= 32 ? n0 : 0)] = word0 + threadIdx.x;
+    if (!all_live) {
+        if (threadIdx.x < kDetectTileWords) {
+            const int rk = s_live[threadIdx.x];
+            if (rk >= 0) list[rk + (threadIdx.x >= 32 ? n0 : 0)] = word0 + threadIdx.x;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     int cnt = 0;
-    for (int k = warp * U; k < nlive; k += (kDetectThreads / 32) * U) {
+    // software pipeline: the coordinates of the warp's next group are requested before the current group is
+    // evaluated, so a warp never sits on an exposed global load between two words
+    constexpr int kStep = (kDetectThreads / 32) * U;
+    int nws[U];
+    double npx[U], npy[U], npz[U];
+    bool ninr[U];
+    auto fetch = [&](int k) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            nws[u] = (k + u < nlive) ? list[k + u] : -1;
+            const int idx = nws[u] * 32 + lane;
+            ninr[u] = (nws[u] >= 0) && (idx < pd.n);
+            npx[u] = ninr[u] ? __ldg(pd.sx + idx) : 0.0;
+            npy[u] = ninr[u] ? __ldg(pd.sy + idx) : 0.0;
+            npz[u] = ninr[u] ? __ldg(pd.sz + idx) : 0.0;
+        }
+    };
+    if (Sampler::kPrefetch) fetch(warp * U);
+    for (int k = warp * U; k < nlive; k += kStep) {
         int ws[U];
         double px[U], py[U], pz[U];
         bool inr[U];
+        if (!Sampler::kPrefetch) fetch(k);   // cache-resident grids: 40 registers / 6 CTAs per SM matter more than the overlap
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            ws[u] = (k + u < nlive) ? list[k + u] : -1;
-            const int idx = ws[u] * 32 + lane;
-            inr[u] = (ws[u] >= 0) && (idx < pd.n);
-            px[u] = inr[u] ? __ldg(pd.sx + idx) : 0.0;
-            py[u] = inr[u] ? __ldg(pd.sy + idx) : 0.0;
-            pz[u] = inr[u] ? __ldg(pd.sz + idx) : 0.0;
-        }
+        for (int u = 0; u < U; ++u) { ws[u] = nws[u]; px[u] = npx[u]; py[u] = npy[u]; pz[u] = npz[u]; inr[u] = ninr[u]; }
+        if (Sampler::kPrefetch && k + kStep < nlive) fetch(k + kStep);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (ws[u] < 0) continue;  // warp-uniform
@@ -329,17 +350,25 @@ __device__ __forceinline__ void tma_load_bricks(const void* tmap, uint64_t* bar,
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 struct BrickSampler {
-    const float* sb;     // staged bricks [nbz][nby][nbx][64] or nullptr (global gathers)
+    static constexpr bool kPrefetch = true;
+    uint32_t sb;         // shared-memory address of the staged bricks [nbz][nby][nbx][64], 0 = not staged (global gathers)
     uint64_t* bar;
     int bx0, by0, bz0, nbx, nby, nbz;
     bool waited;
+    bool all_inside;     // the image of the tile's box lies inside [mn, mx]: every point samples the grid
     __device__ __forceinline__ double eval(const GridDev& G, const double* R1, const double* p1, const double* R2,
                                            const double* p2, double x0, double x1, double x2) {
         double xw[3], x[3];
         to_world(R1, p1, x0, x1, x2, xw);
         to_local(R2, p2, xw, x);
-        if (!in_box(G, x[0], x[1], x[2])) return __dadd_rn((double)FLT_MAX, G.col_th);   // BodySDFObj.cpp:170,212
+        if (!all_inside && !in_box(G, x[0], x[1], x[2])) return __dadd_rn((double)FLT_MAX, G.col_th);   // BodySDFObj.cpp:170,212
         double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
         double cj = exact_div(__dsub_rn(x[1], G.mn[1]), G.dy, G.rdy);
         double ck = exact_div(__dsub_rn(x[2], G.mn[2]), G.dz, G.rdz);
@@ -351,17 +380,20 @@ struct BrickSampler {
         const int rx0 = (i >> 2) - bx0, rx1 = (i1 >> 2) - bx0, ry0 = (j >> 2) - by0, ry1 = (j1 >> 2) - by0;
         const int rz0 = (k >> 2) - bz0, rz1 = (k1 >> 2) - bz0;
         // the brick covers the image of the tile's box, so this always holds for a staged tile; checked anyway
-        const bool staged = sb != nullptr && rx0 >= 0 && rx1 < nbx && ry0 >= 0 && ry1 < nby && rz0 >= 0 && rz1 < nbz;
+        const bool staged = sb != 0u && rx0 >= 0 && rx1 < nbx && ry0 >= 0 && ry1 < nby && rz0 >= 0 && rz1 < nbz;
         if (staged) {
             if (!waited) { mbar_wait(bar, 0); waited = true; }
             const int sy = nbx * 64, sz = sy * nby;
             const int ox0 = rx0 * 64 + (i & 3), ox1 = rx1 * 64 + (i1 & 3);
             const int oy0 = ry0 * sy + (j & 3) * 4, oy1 = ry1 * sy + (j1 & 3) * 4;
             const int oz0 = rz0 * sz + (k & 3) * 16, oz1 = rz1 * sz + (k1 & 3) * 16;
-            v[0] = (double)sb[ox0 + oy0 + oz0]; v[1] = (double)sb[ox1 + oy0 + oz0];
-            v[2] = (double)sb[ox0 + oy1 + oz0]; v[3] = (double)sb[ox1 + oy1 + oz0];
-            v[4] = (double)sb[ox0 + oy0 + oz1]; v[5] = (double)sb[ox1 + oy0 + oz1];
-            v[6] = (double)sb[ox0 + oy1 + oz1]; v[7] = (double)sb[ox1 + oy1 + oz1];
+            const uint32_t a00 = sb + 4u * (uint32_t)(oy0 + oz0), a10 = sb + 4u * (uint32_t)(oy1 + oz0);
+            const uint32_t a01 = sb + 4u * (uint32_t)(oy0 + oz1), a11 = sb + 4u * (uint32_t)(oy1 + oz1);
+            const uint32_t x0b = 4u * (uint32_t)ox0, x1b = 4u * (uint32_t)ox1;
+            v[0] = (double)lds_f32(a00 + x0b); v[1] = (double)lds_f32(a00 + x1b);
+            v[2] = (double)lds_f32(a10 + x0b); v[3] = (double)lds_f32(a10 + x1b);
+            v[4] = (double)lds_f32(a01 + x0b); v[5] = (double)lds_f32(a01 + x1b);
+            v[6] = (double)lds_f32(a11 + x0b); v[7] = (double)lds_f32(a11 + x1b);
         } else {
             load_cell<true>(G, i, j, k, v);
         }
@@ -377,7 +409,7 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
     __shared__ int s_live[2 * kDetectTileWords];
     __shared__ int s_nlive[kDetectThreads / 32];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_brick[7];   // bx0, by0, bz0, nbx, nby, nbz, staged
+    __shared__ int s_brick[8];   // bx0, by0, bz0, nbx, nby, nbz, staged, tile image inside the grid box
     const int tile = blockIdx.x, env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr && __ldg(B.env_mode + env) == 0) return;
     const int pair = __ldg(B.tile_pair + tile), word0 = __ldg(B.tile_word0 + tile);
@@ -385,7 +417,7 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
         const int* src = reinterpret_cast<const int*>(B.pairs + pair);
         int* dst = reinterpret_cast<int*>(&pd);
         for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
-        if (threadIdx.x == 0) { s_count = 0; s_brick[6] = 0; mbar_init(&s_bar, 1); }
+        if (threadIdx.x == 0) { s_count = 0; s_brick[6] = 0; s_brick[7] = 0; mbar_init(&s_bar, 1); }
     }
     __syncthreads();
     if (threadIdx.x < 12) stage_pose(E, B.n_bodies, env, pd.body_a, R1, p1, threadIdx.x);
@@ -393,6 +425,14 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
     __syncthreads();
     float* sb = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(brick_raw) + 127) & ~(uintptr_t)127);
     const bool bricks = pd.grid.b32 != nullptr && pd.grid.tmaps != nullptr && pd.tile_box != nullptr;
+    if (bricks && threadIdx.x >= 32 && threadIdx.x < 35) {
+        // the tile's coordinates (3 contiguous runs of the SoA copy) are pulled into L2 now, so that the warps'
+        // loads below find them there instead of waiting on DRAM one word at a time
+        const double* base = (threadIdx.x == 32) ? pd.sx : (threadIdx.x == 33 ? pd.sy : pd.sz);
+        const int i0 = word0 * 32, cnt = min(pd.n - i0, kDetectTileWords * 32);
+        const uint32_t bytes = (uint32_t)(cnt * 8) & ~15u;
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + i0), "r"(bytes) : "memory");
+    }
     if (bricks && threadIdx.x < 32) {
         // image of the tile's box in the SDF frame: min / max over its 8 corners (lanes 0..7)
         const double* tb = pd.tile_box + 6 * (size_t)(word0 / kDetectTileWords);
@@ -414,11 +454,12 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
             const double dd[3] = {G.dx, G.dy, G.dz}, rd[3] = {G.rdx, G.rdy, G.rdz};
             const int nn[3] = {G.ni, G.nj, G.nk}, nbr[3] = {G.nbx, G.nby, G.nbz};
             int b0[3], nb[3];
-            bool any = true;
+            bool any = true, inside = true;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const double l = fmax(lo[a] - 1e-7, G.mn[a]), h = fmin(hi[a] + 1e-7, G.mx[a]);
                 any = any && (l <= h);
+                inside = inside && (lo[a] - 1e-7 >= G.mn[a]) && (hi[a] + 1e-7 <= G.mx[a]);
                 // cell index is monotonic in the coordinate (correctly rounded quotient, then floor)
                 int c0 = (int)floor(exact_div(__dsub_rn(l, G.mn[a]), dd[a], rd[a]));
                 int c1 = (int)floor(exact_div(__dsub_rn(h, G.mn[a]), dd[a], rd[a]));
@@ -427,10 +468,12 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
                 nb[a] = min(((c1 + 1) >> 2), nbr[a] - 1) - b0[a] + 1;   // + 1: upper neighbour node
             }
             const bool fits = any && nb[0] <= kBrickMaxXY && nb[1] <= kBrickMaxXY &&
-                              (size_t)nb[0] * nb[1] * nb[2] * 256 <= (size_t)kBrickSmemBytes;
+                              (size_t)nb[0] * nb[1] * nb[2] * 256 <= (size_t)B.brick_cap;
+            if (B.brick_stats != nullptr) atomicAdd(B.brick_stats + (fits ? 0 : (any ? 1 : 2)), 1ull);
             s_brick[0] = b0[0]; s_brick[1] = b0[1]; s_brick[2] = b0[2];
             s_brick[3] = nb[0]; s_brick[4] = nb[1]; s_brick[5] = nb[2];
             s_brick[6] = fits ? 1 : 0;
+            s_brick[7] = (any && inside) ? 1 : 0;
             if (fits) {
                 const uint32_t slice = (uint32_t)nb[0] * nb[1] * 256;
                 mbar_arrive_expect_tx(&s_bar, slice * nb[2]);
@@ -446,8 +489,9 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
     SkinCta sk_unused;
     const bool staged = s_brick[6] != 0;
     if (pd.grid.b32 != nullptr) {
-        BrickSampler smp{staged ? sb : nullptr, &s_bar, s_brick[0], s_brick[1], s_brick[2], s_brick[3], s_brick[4], s_brick[5], false};
-        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+        BrickSampler smp{staged ? smem_u32(sb) : 0u, &s_bar, s_brick[0], s_brick[1], s_brick[2], s_brick[3], s_brick[4], s_brick[5], false,
+                         s_brick[7] != 0};
+        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp, s_brick[7] != 0);
         if (staged && !smp.waited) mbar_wait(&s_bar, 0);   // the CTA must not retire under an in-flight bulk copy
     } else if (pd.grid.f32()) {
         GlobalSampler<true> smp;
@@ -460,17 +504,18 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
     if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
 }
 
-void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream) {
-    cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
+void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream, bool reset_counts) {
+    if (reset_counts)
+        cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
     if (B.n_tiles == 0 || B.env_count == 0) return;   // every pair has an empty point set: all counts stay 0
     dim3 grid(B.n_tiles, B.env_count);
     if (B.any_bricks && B.skin_margin == nullptr) {
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(k_detect_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrickSmemBytes + 128);
+            cudaFuncSetAttribute(k_detect_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrickSmemMax + 128);
             configured = true;
         }
-        k_detect_brick<<<grid, kDetectThreads, kBrickSmemBytes + 128, stream>>>(B, E);
+        k_detect_brick<<<grid, kDetectThreads, B.brick_cap + 128, stream>>>(B, E);
         return;
     }
     if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreads, 0, stream>>>(B, E);

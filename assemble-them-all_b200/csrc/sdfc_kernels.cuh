@@ -65,6 +65,8 @@ struct BatchDev {
     int n_tiles;
     int splits;  // force CTAs per (env, pair)
     int any_bricks;     // some pair samples a bricked grid (GridDev::b32): detection stages voxel bricks with TMA
+    int brick_cap;      // shared-memory bytes a tile's brick may take (larger bricks: global gathers); SDFC_BRICK_SMEM
+    unsigned long long* brick_stats;   // [3] tiles staged / too large / outside the grid box (diagnostics), or nullptr
     uint32_t* mask;     // [n_envs][words_per_env]
     int32_t* n_active;  // [n_envs][n_pairs]
     double* partial;    // [n_envs][n_pairs][splits][kPartial*]
@@ -94,7 +96,8 @@ struct BatchDev {
 };
 
 // launches (all asynchronous on `stream`)
-void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream);
+// reset_counts = false: the caller has already zeroed n_active of the environments it evaluates (the stepper)
+void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream, bool reset_counts = true);
 // skin bookkeeping of one evaluation (before launch_detect_mask when B.skin_margin != nullptr)
 void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream);
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
@@ -122,7 +125,8 @@ void launch_build_cells(const float* g32, int ni, int nj, int nk, float4* out, c
 // plain fp32 grid -> 4 x 4 x 4 bricks with one replicated node layer past n - 1 (GridDev::b32)
 void launch_build_bricks(const float* g32, int ni, int nj, int nk, int nbx, int nby, int nbz, float* out, cudaStream_t stream);
 // shared-memory bytes a k_detect_brick CTA may use for its voxel brick
-constexpr int kBrickSmemBytes = 72 * 1024;
+constexpr int kBrickSmemBytes = 72 * 1024;   // default BatchDev::brick_cap (3 CTAs / SM)
+constexpr int kBrickSmemMax = 200 * 1024;
 constexpr int kBrickMaxXY = 16;   // tensor-map table: box = 64 floats x (1..16) x (1..16) x 1 bricks
 // *out (zeroed by the caller) = bit pattern of the squared Lipschitz bound of the interpolant (GridDev::lip)
 void launch_grid_lipschitz(const double* g64, int ni, int nj, int nk, double dx, double dy, double dz,

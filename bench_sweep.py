@@ -40,9 +40,17 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--active-frac", type=float, default=0.05)
     ap.add_argument("--out", default="")
-    ap.add_argument("--no-morton", action="store_true",
-                    help="detect: keep the points in file order (default: the one-time Morton sort sdfc_points_create does)")
+    ap.add_argument("--order", choices=["none", "morton", "kd"], default="kd",
+                    help="detect: point order of the one-time sort sdfc_points_create does (none = file order)")
+    ap.add_argument("--no-morton", action="store_true", help="same as --order none")
+    ap.add_argument("--layout", choices=["auto", "records", "bricks"], default="auto",
+                    help="device storage of fp32-lossless grids (auto: cell records up to ~96 MB of records, bricks beyond)")
+    ap.add_argument("--entries", default="distance,detect")
     args = ap.parse_args()
+    if args.no_morton:
+        args.order = "none"
+    if args.layout != "auto":
+        os.environ["SDFC_GRID_LAYOUT"] = args.layout
     import torch
     import torch.distributed as dist
     from assemble_them_all_b200 import contact, scenes, synth
@@ -68,7 +76,9 @@ def main():
         probe = rng.uniform(spec.min_box * 0.999, spec.max_box * 0.999, size=(200000, 3))
         spec.col_th = float(-np.quantile(np.linalg.norm(probe, axis=1) - 3.5, args.active_frac))
         sdf = contact.SdfGrid.from_spec(ctx, spec)
-        grid_bytes = gn ** 3 * (32 if sdf.is_fp32 else 8)
+        layout = sdf.layout
+        grid_bytes = gn ** 3 * {"records": 32, "bricks": 4, "fp64": 8}[layout]
+        corner_bytes = 32 if sdf.is_fp32 else 64   # the gather is 32 B when the grid is stored fp32
         for npts in [int(float(x)) for x in args.points.split(",")]:
             n_local = npts // world
             pts = rng.uniform(spec.min_box * 0.999, spec.max_box * 0.999, size=(n_local, 3))
@@ -78,7 +88,7 @@ def main():
             def run_distance():
                 sdf.distance_device(n_local, soa[0].data_ptr(), soa[1].data_ptr(), soa[2].data_ptr(), dout.data_ptr())
             # ---- detect (1 environment, identity-ish poses with a small seeded rotation)
-            cp = contact.ContactPoints(ctx, pts, morton_sort=not args.no_morton)
+            cp = contact.ContactPoints(ctx, pts, morton_sort={"none": False, "morton": True, "kd": "kd"}[args.order])
             pair = contact.ForceGeneralSDFContact(ctx, cp, sdf, 1e6, 1e3)
             batch = contact.ContactBatch(ctx, 1, 2, [pair], [0], [1])
             R = synth.axis_angle_rotation([0.3, -0.2, 0.9], 0.01)
@@ -90,6 +100,8 @@ def main():
                 batch.detect_device(dE.data_ptr(), dna.data_ptr())
 
             for name, fn, comp in (("distance", run_distance, 24 + 32 + 8), ("detect", run_detect, 24 + 32 + 0.125)):
+                if name not in args.entries.split(","):
+                    continue
                 for _ in range(3):
                     fn()
                 ms = []
@@ -107,13 +119,18 @@ def main():
                 sec = float(t.item()) * 1e-3
                 qps = n_local * world / sec
                 line = {"entry": name, "points": npts, "grid": gn, "n_gpus": world, "ms": sec * 1e3, "queries_per_sec": qps,
-                        "algorithmic_GBs": qps * 96 / 1e9, "compulsory_dram_GBs": qps * comp / 1e9,
-                        "frac_of_hbm_peak_algorithmic": qps * 96 / 1e9 / (peak * world),
-                        "frac_of_hbm_peak_compulsory": qps * comp / 1e9 / (peak * world),
-                        "hbm_peak_GBs_per_gpu": peak, "grid_storage": "fp32 cell records" if sdf.is_fp32 else "fp64",
+                        # SURVEY 8(d) unit: 24 B point + 8-corner gather (32 B fp32 storage / 64 B fp64) + 8 B result
+                        "unit_bytes": 24 + corner_bytes + 8,
+                        "algorithmic_GBs": qps * (24 + corner_bytes + 8) / 1e9,
+                        "frac_of_hbm_peak": qps * (24 + corner_bytes + 8) / 1e9 / (peak * world),
+                        "frac_of_hbm_peak_96B_unit": qps * 96 / 1e9 / (peak * world),
+                        "hbm_peak_GBs_per_gpu": peak, "grid_storage": layout,
                         "grid_bytes": grid_bytes, "fits_l2": grid_bytes < 120e6,
-                        "point_order": ("as given" if name == "distance" or args.no_morton else "Morton-sorted at upload"),
-                        "active_fraction": float(dna.item()) / n_local if name == "detect" else None}
+                        "point_order": ("as given" if name == "distance" else {"none": "file order", "morton": "Morton-sorted at upload",
+                                                                               "kd": "k-d sorted at upload"}[args.order]),
+                        "active_fraction": float(dna.item()) / n_local if name == "detect" else None,
+                        "brick_tiles": batch.brick_stats() if name == "detect" and layout == "bricks" else None,
+                        "brick_smem": os.environ.get("SDFC_BRICK_SMEM")}
                 if rank == 0:
                     print(json.dumps(line), flush=True)
                     lines.append(line)

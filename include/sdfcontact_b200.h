@@ -82,6 +82,11 @@ SDFC_API sdfc_status sdfc_context_read_timing(sdfc_context* ctx, double ms[4], i
  * reciprocal-based exact division, compared bit for bit with the IEEE division.
  * mismatches must come back 0 (the cell index and the interpolation weights of
  * query_SDF, BodySDFObj.cpp:132-134, depend on it). */
+/* Roofline denominators measured on this device (MEASURED_PEAKS.json covers HBM and bf16 only):
+ * out[0] = FP64 DFMA throughput in GFLOP/s (8 independent chains per thread, all SMs),
+ * out[1] = L2 -> SM read bandwidth in GB/s (every CTA streams a 48 MiB buffer with 128-bit loads),
+ * out[2..3] reserved (0). Takes a few milliseconds. */
+SDFC_API sdfc_status sdfc_measure_peaks(sdfc_context* ctx, double out[4]);
 SDFC_API sdfc_status sdfc_selftest_exact_div(sdfc_context* ctx, int64_t n, uint64_t seed, double b, int64_t* mismatches);
 
 /* ---- SDF grid: fields of BodySDFObj (Body/BodySDFObj.h:13-16) ---------- */
@@ -238,6 +243,9 @@ SDFC_API sdfc_status sdfc_batch_set_grounds(sdfc_batch* batch, int n_grounds, sd
  * (CollisionDetection.cpp:137-138). */
 SDFC_API sdfc_status sdfc_batch_get_skin_stats(sdfc_batch* batch, int64_t stats[4]);
 /* Ground contact counts of the last evaluation: [n_envs][n_grounds], host. */
+/* Running totals of the TMA-staged detection (bricked grids): detection tiles whose voxel brick was staged in
+ * shared memory, tiles whose brick exceeded the budget (global gathers), tiles outside the grid box. */
+SDFC_API sdfc_status sdfc_batch_get_brick_stats(sdfc_batch* batch, int64_t stats[3]);
 SDFC_API sdfc_status sdfc_batch_get_ground_active(sdfc_batch* batch, int32_t* n_active_out);
 
 /* Host-buffer entry (the plug-in-facing call): E_host [n_envs][n_bodies][16],
