@@ -124,6 +124,34 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     return SDFC_OK;
 }
 
+sdfc_status batch_prepare(sdfc_batch* b) { return batch_refresh(b); }
+
+sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* phi_dev, const int* env_mode_dev, int env0,
+                              int env_count, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev) {
+    sdfc_context* c = b->ctx;
+    BatchDev dev = b->dev;
+    dev.env_mode = env_mode_dev;
+    dev.env0 = env0; dev.env_count = env_count;
+    if (b->gset) {
+        SDFC_CUDA(cudaEventRecord(ev[0], s0));
+        SDFC_CUDA(cudaStreamWaitEvent(s2, ev[0], 0));
+        sdfc_status st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, 0, env_mode_dev, env0, env_count, s2, /*counts_zeroed=*/true);
+        if (st != SDFC_OK) return st;
+        SDFC_CUDA(cudaEventRecord(ev[1], s2));
+    }
+    launch_detect_mask(dev, E_dev, s0, /*reset_counts=*/false);
+    SDFC_CUDA(cudaEventRecord(ev[2], s0));
+    SDFC_CUDA(cudaStreamWaitEvent(s1, ev[2], 0));
+    launch_force(dev, E_dev, phi_dev, false, b->any_fric, b->any_damp, s0);
+    launch_force(dev, E_dev, phi_dev, true, b->any_fric, b->any_damp, s1);
+    SDFC_CUDA(cudaEventRecord(ev[3], s1));
+    SDFC_CUDA(cudaStreamWaitEvent(s0, ev[3], 0));
+    if (b->gset) SDFC_CUDA(cudaStreamWaitEvent(s0, ev[1], 0));
+    c->launches += 3;
+    SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
 sdfc_status batch_enable_skin(sdfc_batch* b) {
     if (b->skin_on) return SDFC_OK;
     const size_t ep = (size_t)b->n_envs * b->n_pairs;

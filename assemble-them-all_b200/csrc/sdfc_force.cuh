@@ -49,6 +49,52 @@ __host__ __device__ inline int tr_index(int lane, int j) {
     return rel;
 }
 
+// Fixed-order sum of the split partials of one (environment, pair) into its blocks fm_sub[12], Km_sub[144],
+// Dm_sub[144] (column-major), undoing the slot layout of the warp transpose-reduce. `tid` of `nthreads`
+// cooperating threads (k_reduce_splits: a CTA; the stepper's round kernel: the environment's warp).
+__device__ __forceinline__ void reduce_splits_one(const BatchDev& B, int env, int pair, int deriv, int dm, int tid, int nthreads,
+                                                  double* fm_sub, double* Km_sub, double* Dm_sub) {
+    const size_t ep = (size_t)env * B.n_pairs + pair;
+    const bool empty = B.n_active[ep] == 0;
+    const bool nf = deriv && !dm;  // layout of contact_eval_nf: 12 Km columns + fm
+    const int npart = nf ? kPartialNF : (deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
+    const double* part = B.partial + ep * B.splits * kPartialDerivDM;  // fixed slot stride, see k_force
+    for (int slot = tid; slot < npart; slot += nthreads) {
+        double s = 0.0;
+        if (!empty)
+            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * kPartialDerivDM + slot];
+        const int lane = slot & 31;
+        if (nf) {
+            const int j = slot >> 5, e = tr_index<12>(lane, 0);
+            if (e >= 0) {
+                if (j < 12) Km_sub[ep * 144 + e + 12 * j] = s;
+                else fm_sub[ep * 12 + e] = s;
+            }
+        } else if (!deriv) {
+            const int e = tr_index<12>(lane, slot >> 5);
+            if (e >= 0) fm_sub[ep * 12 + e] = s;
+        } else if (slot < kPartialDeriv) {
+            const int b = (slot >> 5) / kOutK, j = (slot >> 5) % kOutK;
+            const int e = tr_index<39>(lane, j);
+            if (e >= 36) fm_sub[ep * 12 + 3 * b + (e - 36)] = s;
+            else if (e >= 0) {
+                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
+                Km_sub[ep * 144 + r + 12 * c] = s;
+            }
+        } else {
+            const int q = (slot - kPartialDeriv) >> 5;
+            const int b = q / kOutD, j = q % kOutD;
+            const int e = tr_index<36>(lane, j);
+            if (e >= 0) {
+                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
+                Dm_sub[ep * 144 + r + 12 * c] = s;
+            }
+        }
+    }
+    if (deriv && !dm && Dm_sub != nullptr)
+        for (int i = tid; i < 144; i += nthreads) Dm_sub[ep * 144 + i] = 0.0;
+}
+
 // Sink handed to contact_eval: reduces each emitted block across the warp at once.
 template <bool DERIV, bool DM>
 struct WarpSink {

@@ -393,15 +393,17 @@ static sdfc_status ground_set_refresh(sdfc_ground_set* s) {
 
 // deriv / env_mode_dev as in batch_run. Results stay in the set's buffers.
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
-                           const int* env_mode_dev, int env0, int env_count) {
+                           const int* env_mode_dev, int env0, int env_count, cudaStream_t stream_override,
+                           bool counts_zeroed) {
     sdfc_status st = ground_set_refresh(s);
     if (st != SDFC_OK) return st;
-    cudaStream_t stream = s->ctx->stream;
+    cudaStream_t stream = stream_override ? stream_override : s->ctx->stream;
     GroundBatchDev D = s->dev;
     D.env_mode = env_mode_dev;
     if (env_count < 0) { env0 = 0; env_count = s->n_envs; }
     D.env0 = env0; D.env_count = env_count;
-    SDFC_CUDA(cudaMemsetAsync(s->d_n_active + (size_t)env0 * D.n_grounds, 0, sizeof(int32_t) * (size_t)env_count * D.n_grounds, stream));
+    if (!counts_zeroed)
+        SDFC_CUDA(cudaMemsetAsync(s->d_n_active + (size_t)env0 * D.n_grounds, 0, sizeof(int32_t) * (size_t)env_count * D.n_grounds, stream));
     dim3 grid(D.splits, D.n_grounds, env_count);
     if (env_mode_dev != nullptr) {
         k_ground<false><<<grid, kGroundThreads, 0, stream>>>(D, E_dev, phi_dev);
@@ -426,7 +428,7 @@ sdfc_status ground_set_scatter(sdfc_ground_set* s, int deriv, double* fm_dev, do
 }
 
 const double* ground_set_out(const sdfc_ground_set* s) { return s->d_out; }
-const int32_t* ground_set_n_active(const sdfc_ground_set* s) { return s->d_n_active; }
+int32_t* ground_set_n_active(const sdfc_ground_set* s) { return s->d_n_active; }
 int ground_set_count(const sdfc_ground_set* s) { return (int)s->grounds.size(); }
 const int32_t* ground_set_bodies(const sdfc_ground_set* s) { return s->body.data(); }
 

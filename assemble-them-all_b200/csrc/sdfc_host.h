@@ -144,6 +144,15 @@ namespace sdfc_host {
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
                       bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev,
                       int env0 = 0, int env_count = -1, bool counts_zeroed = false);
+// The contact kernels of one stepper round (sdfc_step.cu), fork / join over three streams so that the value-only
+// and the derivative force kernels and the ground kernels run side by side: detection (s0) -> force<value> (s0)
+// | force<deriv> (s1), ground contacts (s2) from the start. The round kernel has already zeroed the contact
+// counters and run the temporal-coherence bookkeeping, and sums the split partials itself afterwards.
+// ev: 4 events. Capturable into a CUDA graph.
+sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* phi_dev, const int* env_mode_dev, int env0,
+                              int env_count, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev);
+// Uploads the pair table if parameters changed (batch_run does it on every call).
+sdfc_status batch_prepare(sdfc_batch* b);
 // Allocates the skin state of a batch and switches the culling on (idempotent).
 sdfc_status batch_enable_skin(sdfc_batch* b);
 }  // namespace sdfc_host
@@ -155,10 +164,11 @@ sdfc_status ground_set_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
                               const int32_t* body, sdfc_ground_set** out);
 void ground_set_destroy(sdfc_ground_set* s);
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
-                           const int* env_mode_dev, int env0, int env_count);
+                           const int* env_mode_dev, int env0, int env_count, cudaStream_t stream_override = nullptr,
+                           bool counts_zeroed = false);
 sdfc_status ground_set_scatter(sdfc_ground_set* s, int deriv, double* fm_dev, double* Km_dev, double* Dm_dev);
 const double* ground_set_out(const sdfc_ground_set* s);
-const int32_t* ground_set_n_active(const sdfc_ground_set* s);
+int32_t* ground_set_n_active(const sdfc_ground_set* s);
 int ground_set_count(const sdfc_ground_set* s);
 const int32_t* ground_set_bodies(const sdfc_ground_set* s);
 }  // namespace sdfc_host

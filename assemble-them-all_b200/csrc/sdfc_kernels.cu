@@ -59,50 +59,13 @@ struct SkinCta {
     int* pair_margin;
 };
 
-// One thread per (env, pair): relative pose now, decide whether the margins are rebuilt.
+// One thread per (env, pair): relative pose now, decide whether the margins are rebuilt (skin_decide_one, sdfc_kernels.cuh).
 __global__ void k_skin_decide(BatchDev B, const double* __restrict__ E) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B.env_count * B.n_pairs) return;
     const int env = B.env0 + idx / B.n_pairs, pair = idx % B.n_pairs;
     if (B.env_mode != nullptr && B.env_mode[env] == 0) return;
-    const size_t ep = (size_t)env * B.n_pairs + pair;
-    const PairDev& pd = B.pairs[pair];
-    const double* E1 = E + ((size_t)env * B.n_bodies + pd.body_a) * 16;
-    const double* E2 = E + ((size_t)env * B.n_bodies + pd.body_b) * 16;
-    double cur[12];
-    for (int r = 0; r < 3; ++r) {          // R_rel = R2^T R1, p_rel = R2^T (p1 - p2); column-major poses
-        for (int c = 0; c < 3; ++c)
-            cur[3 * r + c] = E2[4 * r] * E1[4 * c] + E2[4 * r + 1] * E1[4 * c + 1] + E2[4 * r + 2] * E1[4 * c + 2];
-        cur[9 + r] = E2[4 * r] * (E1[12] - E2[12]) + E2[4 * r + 1] * (E1[13] - E2[13]) + E2[4 * r + 2] * (E1[14] - E2[14]);
-    }
-    int mode = 0;
-    if (!B.skin_valid[ep]) mode = 1;
-    else if (4 * B.skin_fail[ep] > B.skin_elig[ep]) mode = 1;   // > 25 % of the margins are used up
-    else {
-        // whole pair: every word has a margin and the smallest one outlasts the largest displacement of the set
-        const float pm = __int_as_float(B.skin_pair_margin[ep]);
-        if (pm >= 0.f) {
-            const double* ref = B.skin_ref + ep * 12;
-            double d[12], f2 = 0.0;
-            for (int i = 0; i < 12; ++i) { d[i] = cur[i] - ref[i]; if (i < 9) f2 += d[i] * d[i]; }
-            const double cx = pd.bsphere[0], cy = pd.bsphere[1], cz = pd.bsphere[2];
-            const double ux = d[0] * cx + d[1] * cy + d[2] * cz + d[9];
-            const double uy = d[3] * cx + d[4] * cy + d[5] * cz + d[10];
-            const double uz = d[6] * cx + d[7] * cy + d[8] * cz + d[11];
-            const double delta = sqrt(ux * ux + uy * uy + uz * uz) + sqrt(f2) * pd.bsphere[3];
-            if ((double)pm - pd.grid.lip * delta * (1.0 + 1e-9) > 1e-9) { mode = 2; atomicAdd(B.skin_stats + 3, 1ull); }
-        }
-    }
-    B.skin_fail[ep] = 0;
-    for (int i = 0; i < 12; ++i) B.skin_cur[ep * 12 + i] = cur[i];
-    if (mode == 1) {
-        for (int i = 0; i < 12; ++i) B.skin_ref[ep * 12 + i] = cur[i];
-        B.skin_valid[ep] = 1;
-        B.skin_elig[ep] = 0;
-        B.skin_pair_margin[ep] = __float_as_int(3e38f);
-        atomicAdd(B.skin_stats + 2, 1ull);
-    }
-    B.skin_mode[ep] = mode;
+    skin_decide_one(B, E, env, pair);
 }
 
 void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream) {
@@ -545,45 +508,7 @@ __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restric
         if (m == 0) return;
         deriv = (m == 2) ? 1 : 0;
     }
-    const size_t ep = (size_t)env * B.n_pairs + pair;
-    const bool empty = B.n_active[ep] == 0;
-    const bool nf = deriv && !dm;  // layout of contact_eval_nf: 12 Km columns + fm
-    const int npart = nf ? kPartialNF : (deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
-    const double* part = B.partial + ep * B.splits * kPartialDerivDM;  // fixed slot stride, see k_force
-    for (int slot = threadIdx.x; slot < npart; slot += blockDim.x) {
-        double s = 0.0;
-        if (!empty)
-            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * kPartialDerivDM + slot];
-        const int lane = slot & 31;
-        if (nf) {
-            const int j = slot >> 5, e = tr_index<12>(lane, 0);
-            if (e >= 0) {
-                if (j < 12) Km_sub[ep * 144 + e + 12 * j] = s;
-                else fm_sub[ep * 12 + e] = s;
-            }
-        } else if (!deriv) {
-            const int e = tr_index<12>(lane, slot >> 5);
-            if (e >= 0) fm_sub[ep * 12 + e] = s;
-        } else if (slot < kPartialDeriv) {
-            const int b = (slot >> 5) / kOutK, j = (slot >> 5) % kOutK;
-            const int e = tr_index<39>(lane, j);
-            if (e >= 36) fm_sub[ep * 12 + 3 * b + (e - 36)] = s;
-            else if (e >= 0) {
-                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
-                Km_sub[ep * 144 + r + 12 * c] = s;
-            }
-        } else {
-            const int q = (slot - kPartialDeriv) >> 5;
-            const int b = q / kOutD, j = q % kOutD;
-            const int e = tr_index<36>(lane, j);
-            if (e >= 0) {
-                const int r = e / 6 + 6 * (b >> 1), c = e % 6 + 6 * (b & 1);
-                Dm_sub[ep * 144 + r + 12 * c] = s;
-            }
-        }
-    }
-    if (deriv && !dm && Dm_sub != nullptr)
-        for (int i = threadIdx.x; i < 144; i += blockDim.x) Dm_sub[ep * 144 + i] = 0.0;
+    reduce_splits_one(B, env, pair, deriv, dm, threadIdx.x, blockDim.x, fm_sub, Km_sub, Dm_sub);
 }
 
 // Gather form of the reference's scatter (.cpp:60-61,88-99): one thread per system

@@ -95,6 +95,50 @@ struct BatchDev {
     unsigned long long* skin_stats;   // [4] running totals: words culled, words whose margin was used up, rebuilds, pairs skipped
 };
 
+// Skin bookkeeping of one (environment, pair) before a detection of the stepper: the relative pose now,
+// and whether this evaluation rebuilds the margins (mode 1), skips the whole pair (mode 2) or tests words
+// against their margins (mode 0). Called by k_skin_decide and, fused, by the stepper's round kernel.
+__device__ __forceinline__ void skin_decide_one(const BatchDev& B, const double* E, int env, int pair) {
+    const size_t ep = (size_t)env * B.n_pairs + pair;
+    const PairDev& pd = B.pairs[pair];
+    const double* E1 = E + ((size_t)env * B.n_bodies + pd.body_a) * 16;
+    const double* E2 = E + ((size_t)env * B.n_bodies + pd.body_b) * 16;
+    double cur[12];
+    for (int r = 0; r < 3; ++r) {          // R_rel = R2^T R1, p_rel = R2^T (p1 - p2); column-major poses
+        for (int c = 0; c < 3; ++c)
+            cur[3 * r + c] = E2[4 * r] * E1[4 * c] + E2[4 * r + 1] * E1[4 * c + 1] + E2[4 * r + 2] * E1[4 * c + 2];
+        cur[9 + r] = E2[4 * r] * (E1[12] - E2[12]) + E2[4 * r + 1] * (E1[13] - E2[13]) + E2[4 * r + 2] * (E1[14] - E2[14]);
+    }
+    int mode = 0;
+    if (!B.skin_valid[ep]) mode = 1;
+    else if (4 * B.skin_fail[ep] > B.skin_elig[ep]) mode = 1;   // > 25 % of the margins are used up
+    else {
+        // whole pair: every word has a margin and the smallest one outlasts the largest displacement of the set
+        const float pm = __int_as_float(B.skin_pair_margin[ep]);
+        if (pm >= 0.f) {
+            const double* ref = B.skin_ref + ep * 12;
+            double d[12], f2 = 0.0;
+            for (int i = 0; i < 12; ++i) { d[i] = cur[i] - ref[i]; if (i < 9) f2 += d[i] * d[i]; }
+            const double cx = pd.bsphere[0], cy = pd.bsphere[1], cz = pd.bsphere[2];
+            const double ux = d[0] * cx + d[1] * cy + d[2] * cz + d[9];
+            const double uy = d[3] * cx + d[4] * cy + d[5] * cz + d[10];
+            const double uz = d[6] * cx + d[7] * cy + d[8] * cz + d[11];
+            const double delta = sqrt(ux * ux + uy * uy + uz * uz) + sqrt(f2) * pd.bsphere[3];
+            if ((double)pm - pd.grid.lip * delta * (1.0 + 1e-9) > 1e-9) { mode = 2; atomicAdd(B.skin_stats + 3, 1ull); }
+        }
+    }
+    B.skin_fail[ep] = 0;
+    for (int i = 0; i < 12; ++i) B.skin_cur[ep * 12 + i] = cur[i];
+    if (mode == 1) {
+        for (int i = 0; i < 12; ++i) B.skin_ref[ep * 12 + i] = cur[i];
+        B.skin_valid[ep] = 1;
+        B.skin_elig[ep] = 0;
+        B.skin_pair_margin[ep] = __float_as_int(3e38f);
+        atomicAdd(B.skin_stats + 2, 1ull);
+    }
+    B.skin_mode[ep] = mode;
+}
+
 // launches (all asynchronous on `stream`)
 // reset_counts = false: the caller has already zeroed n_active of the environments it evaluates (the stepper)
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream, bool reset_counts = true);

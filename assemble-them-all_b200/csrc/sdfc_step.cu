@@ -20,6 +20,7 @@
 // One thread per environment: everything here is O(100) - O(10^4) flops per
 // evaluation against O(10^7) in the contact kernels.
 #include "sdfc_host.h"
+#include "sdfc_force.cuh"
 #include "sdfc_step_math.cuh"
 
 #include <algorithm>
@@ -52,12 +53,14 @@ struct SimDev {
     const double* fext;                      // [n_envs][n_bodies][6]
     double *E, *phi;                         // contact-path inputs
     int* env_mode;
-    const double *fm_sub, *Km_sub, *Dm_sub;  // contact-path outputs per (env, pair)
+    double *fm_sub, *Km_sub, *Dm_sub;        // contact-path outputs per (env, pair): summed here from the force kernels' split partials
     int32_t* n_active;                       // [n_envs][n_pairs]; zeroed here for the next detection
+    BatchDev B;                              // the contact batch (split partials, temporal-coherence state)
+    int dm;                                  // some pair has friction or damping (layout of the partials)
     int n_grounds;                           // ForceGroundContact forces (0 = none)
     const int* ground_body;                  // [n_grounds]
     const double* g_out;                     // [n_envs][n_grounds][78]: fm 6, Km 36, Dm 36 (column-major)
-    const int32_t* g_n_active;               // [n_envs][n_grounds]
+    int32_t* g_n_active;                     // [n_envs][n_grounds]; zeroed here for the next evaluation
     uint8_t* touched_ground;                 // [n_envs][n_grounds]
     double *q_traj, *qdot_traj;              // [steps][n_envs][nr] or nullptr
     int* n_unfinished;
@@ -135,6 +138,10 @@ __global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind
             if (S.n_active[(size_t)env * S.n_pairs + p] > 0) S.touched[(size_t)env * S.n_pairs + p] = 1;
         WFOR(gi, S.n_grounds)
             if (S.g_n_active[(size_t)env * S.n_grounds + gi] > 0) S.touched_ground[(size_t)env * S.n_grounds + gi] = 1;
+        // split partials of the force kernels -> per-pair blocks (what k_reduce_splits does outside the stepper)
+        for (int p = 0; p < S.n_pairs; ++p)
+            reduce_splits_one(S.B, env, p, deriv ? 1 : 0, S.dm, wx.lane, 32, S.fm_sub, S.Km_sub, S.Dm_sub);
+        WSYNC();
         EvalIn in;
         in.bodies = S.bodies; in.n_bodies = S.n_bodies; in.n_pairs = S.n_pairs; in.n_dyn = S.n_dyn; in.nr = nr;
         in.n_grounds = S.n_grounds; in.pair_a = S.pair_a; in.pair_b = S.pair_b; in.ground_body = S.ground_body;
@@ -245,8 +252,11 @@ __global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind
     if (WLANE0) S.env_mode[env] = (phase == PH_DONE) ? 0 : (phase == PH_LS ? 1 : 2);
     if (phase == PH_DONE) return;
     WFOR(p, S.n_pairs) S.n_active[(size_t)env * S.n_pairs + p] = 0;   // the detection kernel accumulates into it
+    WFOR(gi, S.n_grounds) S.g_n_active[(size_t)env * S.n_grounds + gi] = 0;
     w_candidate(wx, S, env, phase, W);
     w_poses(wx, S.bodies, S.n_bodies, W, S.E + (size_t)env * S.n_bodies * 16, S.phi + (size_t)env * S.n_bodies * 6);
+    // temporal-coherence bookkeeping of the next detection (k_skin_decide outside the stepper)
+    if (S.B.skin_margin != nullptr) WFOR(p, S.n_pairs) skin_decide_one(S.B, S.E, env, p);
 }
 
 }  // namespace sdfc
@@ -277,6 +287,12 @@ struct sdfc_sim {
     cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t lane_event[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_event = nullptr;
+    // fork / join streams and events of a lane's contact kernels, and the captured steady-state round
+    cudaStream_t lane_aux[kMaxLanes][2] = {};
+    cudaEvent_t lane_ev[kMaxLanes][4] = {};
+    cudaGraphExec_t lane_graph[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t lane_graph_key[kMaxLanes] = {0, 0, 0, 0};
+    bool use_graph = true;
     bool use_active = false;
     double* d_fext = nullptr;
     int* d_unfinished = nullptr;
@@ -357,7 +373,10 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         for (int l = 0; l < s->n_lanes && e == cudaSuccess; ++l) {
             e = cudaStreamCreateWithFlags(&s->lane_stream[l], cudaStreamNonBlocking);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->lane_event[l], cudaEventDisableTiming);
+            for (int a = 0; a < 2 && e == cudaSuccess; ++a) e = cudaStreamCreateWithFlags(&s->lane_aux[l][a], cudaStreamNonBlocking);
+            for (int a = 0; a < 4 && e == cudaSuccess; ++a) e = cudaEventCreateWithFlags(&s->lane_ev[l][a], cudaEventDisableTiming);
         }
+        if (const char* g = std::getenv("SDFC_SIM_GRAPH")) s->use_graph = std::atoi(g) != 0;   // 0: launch every round kernel by kernel
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_bodies, hb.data(), sizeof(BodyDev) * nb, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_pair_a, batch->body_a.data(), sizeof(int) * np, cudaMemcpyHostToDevice);
@@ -408,8 +427,11 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
     for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) {
+        if (s->lane_graph[l]) cudaGraphExecDestroy(s->lane_graph[l]);
         if (s->lane_stream[l]) cudaStreamDestroy(s->lane_stream[l]);
         if (s->lane_event[l]) cudaEventDestroy(s->lane_event[l]);
+        for (int a = 0; a < 2; ++a) if (s->lane_aux[l][a]) cudaStreamDestroy(s->lane_aux[l][a]);
+        for (int a = 0; a < 4; ++a) if (s->lane_ev[l][a]) cudaEventDestroy(s->lane_ev[l][a]);
     }
     if (s->fork_event) cudaEventDestroy(s->fork_event);
     delete s;
@@ -484,15 +506,30 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
         if (a != SDFC_OK) return a;
         s->traj_cap = (size_t)n_steps;
     }
+    {
+        sdfc_status pr = sdfc_host::batch_prepare(s->batch);   // pair table / parameter changes since the last call
+        if (pr != SDFC_OK) return pr;
+    }
     SimDev D = s->dev;
     D.q_traj = q_traj_host ? s->d_traj_q : nullptr;
     D.qdot_traj = qdot_traj_host ? s->d_traj_qd : nullptr;
     D.active = s->use_active ? s->d_active : nullptr;
+    D.B = s->batch->dev;
+    D.B.env_mode = D.env_mode;
+    D.dm = (s->batch->any_fric || s->batch->any_damp) ? 1 : 0;
+    // everything a captured round depends on besides the (fixed) device buffers
+    uint64_t graph_key = 1469598103934665603ull;
+    {
+        const uint64_t parts[8] = {(uint64_t)(uintptr_t)D.q_traj, (uint64_t)(uintptr_t)D.qdot_traj, (uint64_t)(uintptr_t)D.active,
+                                   (uint64_t)s->batch->any_fric * 2 + (uint64_t)s->batch->any_damp, (uint64_t)(uintptr_t)D.B.skin_margin,
+                                   (uint64_t)D.B.any_bricks, (uint64_t)(uintptr_t)s->ctx->stream, (uint64_t)D.B.brick_cap};
+        for (uint64_t v : parts) { graph_key ^= v; graph_key *= 1099511628211ull; }
+        if (graph_key == 0) graph_key = 1;
+    }
     // Lanes: each environment range advances through its own rounds on its own stream; the
     // host feeds the lanes round-robin, so the 32-CTA assembly / solve kernels of one lane run
     // under the contact kernels of another. Results do not depend on the lane count.
     const int L = s->n_lanes;
-    cudaStream_t ctx_stream = s->ctx->stream;
     SDFC_CUDA(cudaMemsetAsync(s->d_unfinished, 0, sizeof(int) * sdfc_sim::kMaxLanes, st));
     SDFC_CUDA(cudaEventRecord(s->fork_event, st));
     int lane_env0[sdfc_sim::kMaxLanes], lane_cnt[sdfc_sim::kMaxLanes];
@@ -532,16 +569,38 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             any = true;
             SimDev Dl = D;
             Dl.env0 = lane_env0[l]; Dl.env_count = lane_cnt[l]; Dl.n_unfinished = s->d_unfinished + l;
-            // k_sim_round: state machine on the evaluation of the previous round (none in the first one), then the
-            // poses of the next candidate; the contact kernels evaluate them
-            rc = launch_round(s, Dl, lane_round[l] == 0 ? ROUND_FIRST : ROUND_FULL, ls);
+            // One round = k_sim_round (state machine on the evaluation of the previous round - none in the first one -
+            // then poses, evaluation modes, zeroed counters and culling decisions of the next candidate) followed by
+            // the contact kernels that evaluate it. The steady-state round is captured once into a CUDA graph
+            // (fork / join: value and derivative force kernels and the ground kernels side by side) and replayed.
+            auto issue = [&](int kind) -> sdfc_status {
+                sdfc_status r = launch_round(s, Dl, kind, ls);
+                if (r != SDFC_OK) return r;
+                return sdfc_host::batch_run_stepper(s->batch, D.E, D.phi, D.env_mode, lane_env0[l], lane_cnt[l], ls, s->lane_aux[l][0],
+                                                    s->lane_aux[l][1], s->lane_ev[l]);
+            };
+            if (lane_round[l] == 0 || !s->use_graph) {
+                rc = issue(lane_round[l] == 0 ? ROUND_FIRST : ROUND_FULL);
+            } else {
+                if (s->lane_graph[l] == nullptr || s->lane_graph_key[l] != graph_key) {
+                    if (s->lane_graph[l]) { cudaGraphExecDestroy(s->lane_graph[l]); s->lane_graph[l] = nullptr; }
+                    cudaGraph_t g = nullptr;
+                    const int64_t launches0 = s->ctx->launches;
+                    if (cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph capture failed to start"); break; }
+                    rc = issue(ROUND_FULL);
+                    const cudaError_t ce = cudaStreamEndCapture(ls, &g);
+                    s->ctx->launches = launches0;   // captured, not launched
+                    if (rc == SDFC_OK && (ce != cudaSuccess || g == nullptr)) rc = fail(SDFC_ERR_CUDA, std::string("sdfc_sim_forward: graph capture: ") + cudaGetErrorString(ce));
+                    if (rc == SDFC_OK && cudaGraphInstantiate(&s->lane_graph[l], g, 0) != cudaSuccess) rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph instantiation failed");
+                    if (g) cudaGraphDestroy(g);
+                    if (rc != SDFC_OK) break;
+                    s->lane_graph_key[l] = graph_key;
+                }
+                if (cudaGraphLaunch(s->lane_graph[l], ls) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph launch failed"); break; }
+                s->ctx->launches += 4 + (s->n_grounds ? 2 : 0);
+            }
             if (rc != SDFC_OK) break;
             lane_round[l] += 1;
-            s->ctx->stream = ls;  // the batch launches (and their timing events) go to the lane's stream
-            rc = sdfc_host::batch_run(s->batch, D.E, D.phi, 0, D.env_mode, /*scatter=*/false, nullptr, nullptr, nullptr,
-                                      nullptr, lane_env0[l], lane_cnt[l], /*counts_zeroed=*/true);
-            s->ctx->stream = ctx_stream;
-            if (rc != SDFC_OK) break;
             if (round & 1) {
                 if (cudaMemcpyAsync(s->h_unfinished + l, s->d_unfinished + l, sizeof(int), cudaMemcpyDeviceToHost, ls) != cudaSuccess ||
                     cudaEventRecord(s->lane_event[l], ls) != cudaSuccess)
