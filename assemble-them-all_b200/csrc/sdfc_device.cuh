@@ -790,7 +790,7 @@ __device__ __forceinline__ int contact_eval(const GridDev& G, const PairPose& P,
 // operands, so the same bits. Falls back to sample-by-sample evaluation when any
 // coordinate leaves the centre cell or the grid box.
 template <bool F32>
-__device__ __forceinline__ void sdf_stencil_generic(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
+__device__ __noinline__ void sdf_stencil_generic(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
     CellCache cc;
     {
         const double ci = exact_div(__dsub_rn(x[0], G.mn[0]), G.dx, G.rdx);
@@ -879,7 +879,101 @@ __device__ __forceinline__ void stencil_on_cell(const double c[8], const double 
     s[15] = S(0, 3, 3); s[16] = S(0, 4, 4); s[17] = S(0, 3, 4); s[18] = S(0, 4, 3);
 }
 
+// d, g, H from the 19 samples of one cell, evaluated x-variant by x-variant so that only the 8 corners, the 15
+// fractions, the 4 x-lerps of the current variant and a handful of partial results are live at any time (the
+// sample-ordered form above keeps all 19 samples and most stage results in registers: > 230 of them).
+// Same lerps on the same operands as stencil_on_cell, so the same bits; 65 lerps.
+__device__ __forceinline__ void stencil_reduce_on_cell(const double c[8], const double fi[5], const double fj[5], const double fk[5],
+                                                       double col_th, double& d, double g[3], double H[9]) {
+    constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
+    constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
+    double v00, v10, v01, v11, w0, w1;
+#define SDFC_ST1(vi)                                                   \
+    v00 = lerp1(fi[vi], c[0], c[1]); v10 = lerp1(fi[vi], c[2], c[3]);  \
+    v01 = lerp1(fi[vi], c[4], c[5]); v11 = lerp1(fi[vi], c[6], c[7])
+#define SDFC_ST2(vj) w0 = lerp1(fj[vj], v00, v10); w1 = lerp1(fj[vj], v01, v11)
+#define SDFC_ST3(vk) lerp1(fk[vk], w0, w1)
+    // ---- x variant 0: centre, y / z axis samples, yz diagonals
+    SDFC_ST1(0);
+    SDFC_ST2(0);
+    const double s0 = SDFC_ST3(0), s5 = SDFC_ST3(1), s6 = SDFC_ST3(2);
+    SDFC_ST2(1);
+    const double s3 = SDFC_ST3(0);
+    SDFC_ST2(2);
+    const double s4 = SDFC_ST3(0);
+    SDFC_ST2(3);
+    const double s15 = SDFC_ST3(3), s17 = SDFC_ST3(4);
+    SDFC_ST2(4);
+    const double s16 = SDFC_ST3(4), s18 = SDFC_ST3(3);
+    const double two_s0 = __dmul_rn(2.0, s0);
+    d = __dadd_rn(s0, col_th);
+    g[1] = exact_div(__dsub_rn(s3, s4), kTwoEps, kRTwoEps);
+    g[2] = exact_div(__dsub_rn(s5, s6), kTwoEps, kRTwoEps);
+    H[4] = exact_div(__dsub_rn(__dadd_rn(s3, s4), two_s0), kEps2, kREps2);
+    H[8] = exact_div(__dsub_rn(__dadd_rn(s5, s6), two_s0), kEps2, kREps2);
+    // v = q(++) + q(--) - q(+-) - q(-+), left to right (BodySDFObj.cpp:196-203)
+    H[5] = H[7] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s15, s16), s17), s18), kEps2, kREps2);
+    // ---- x variants 1, 2: x axis samples
+    SDFC_ST1(1);
+    SDFC_ST2(0);
+    const double s1 = SDFC_ST3(0);
+    SDFC_ST1(2);
+    SDFC_ST2(0);
+    const double s2 = SDFC_ST3(0);
+    g[0] = exact_div(__dsub_rn(s1, s2), kTwoEps, kRTwoEps);
+    H[0] = exact_div(__dsub_rn(__dadd_rn(s1, s2), two_s0), kEps2, kREps2);
+    // ---- x variants 3, 4: xy and xz diagonals
+    SDFC_ST1(3);
+    SDFC_ST2(3);
+    const double s7 = SDFC_ST3(0);
+    SDFC_ST2(4);
+    const double s9 = SDFC_ST3(0);
+    SDFC_ST2(0);
+    const double s11 = SDFC_ST3(3), s13 = SDFC_ST3(4);
+    SDFC_ST1(4);
+    SDFC_ST2(4);
+    const double s8 = SDFC_ST3(0);
+    SDFC_ST2(3);
+    const double s10 = SDFC_ST3(0);
+    SDFC_ST2(0);
+    const double s12 = SDFC_ST3(4), s14 = SDFC_ST3(3);
+    H[1] = H[3] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s7, s8), s9), s10), kEps2, kREps2);
+    H[2] = H[6] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s11, s12), s13), s14), kEps2, kREps2);
+#undef SDFC_ST1
+#undef SDFC_ST2
+#undef SDFC_ST3
+}
+
+// One-face crossing: every sample on its own cell (base c or neighbour c2). Rare; kept out of line so that
+// its registers do not count against the common path.
+__device__ __noinline__ void stencil_crossing(const double* c, const double* c2, const double* fi, const double* fj, const double* fk,
+                                              const int* oi, const int* oj, const int* ok_, double col_th, double* d, double* g, double* H) {
+    auto S = [&](int vi, int vj, int vk) {
+        const bool nb = (oi[vi] + oj[vj] + ok_[vk]) != 0;
+        double q[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) q[t] = nb ? c2[t] : c[t];
+        return lerp8(q, fi[vi], fj[vj], fk[vk]);
+    };
+    constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
+    constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
+    const double s0 = S(0, 0, 0), two_s0 = __dmul_rn(2.0, s0);
+    *d = __dadd_rn(s0, col_th);
+    { const double a = S(1, 0, 0), b = S(2, 0, 0); g[0] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[0] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
+    { const double a = S(0, 1, 0), b = S(0, 2, 0); g[1] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[4] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
+    { const double a = S(0, 0, 1), b = S(0, 0, 2); g[2] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[8] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
+    H[1] = H[3] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(3, 3, 0), S(4, 4, 0)), S(3, 4, 0)), S(4, 3, 0)), kEps2, kREps2);
+    H[2] = H[6] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(3, 0, 3), S(4, 0, 4)), S(3, 0, 4)), S(4, 0, 3)), kEps2, kREps2);
+    H[5] = H[7] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(0, 3, 3), S(0, 4, 4)), S(0, 3, 4)), S(0, 4, 3)), kEps2, kREps2);
+}
+
 // Must be called by all 32 lanes of a warp (uses a warp vote).
+// Three paths, all bit-identical to the reference's 26 query_SDF calls:
+//   * the stencil lies in one cell (almost always): stencil_reduce_on_cell;
+//   * it crosses one cell face along one axis: every sample is evaluated on its own cell (base or neighbour),
+//     sample by sample without sharing (133 lerps; ~0.1 % of the contacts, so the cost is irrelevant and the
+//     second cell does not inflate the register footprint of the common path);
+//   * anything else (outside the box, two crossings): the sample-by-sample generic sequence.
 template <bool F32>
 __device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
     double fi[5], fj[5], fk[5];
@@ -887,50 +981,40 @@ __device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3],
     bool ok = axis_variants(x[0], G.mn[0], G.mx[0], G.dx, G.rdx, bi, oi, fi, cx);
     ok = axis_variants(x[1], G.mn[1], G.mx[1], G.dy, G.rdy, bj, oj, fj, cy) && ok;
     ok = axis_variants(x[2], G.mn[2], G.mx[2], G.dz, G.rdz, bk, ok_, fk, cz) && ok;
-    // fast path: the stencil touches the base cell and at most one neighbour along one axis
     ok = ok && (cx + cy + cz <= 1);
-    double s[19];
-    if (ok) {
-        double c[8];
-        load_cell<F32>(G, bi, bj, bk, c);
-        stencil_on_cell(c, fi, fj, fk, s);
-    }
     const bool crossing = ok && (cx + cy + cz == 1);
+    // the rare paths come first: what only they need (cell offsets per variant, the second cell) is dead
+    // before the common path starts, and only copies have their address taken
     if (__any_sync(0xffffffffu, crossing)) {
         if (crossing) {
-            double c[8], t[19];
-            load_cell<F32>(G, bi + cx, bj + cy, bk + cz, c);
-            stencil_on_cell(c, fi, fj, fk, t);
-            // sample (vi, vj, vk) lives in the neighbour cell iff its variant on the crossing axis does
-#define SDFC_PICK(n, vi, vj, vk) s[n] = (oi[vi] + oj[vj] + ok_[vk]) ? t[n] : s[n]
-            SDFC_PICK(0, 0, 0, 0);
-            SDFC_PICK(1, 1, 0, 0); SDFC_PICK(2, 2, 0, 0); SDFC_PICK(3, 0, 1, 0); SDFC_PICK(4, 0, 2, 0);
-            SDFC_PICK(5, 0, 0, 1); SDFC_PICK(6, 0, 0, 2);
-            SDFC_PICK(7, 3, 3, 0); SDFC_PICK(8, 4, 4, 0); SDFC_PICK(9, 3, 4, 0); SDFC_PICK(10, 4, 3, 0);
-            SDFC_PICK(11, 3, 0, 3); SDFC_PICK(12, 4, 0, 4); SDFC_PICK(13, 3, 0, 4); SDFC_PICK(14, 4, 0, 3);
-            SDFC_PICK(15, 0, 3, 3); SDFC_PICK(16, 0, 4, 4); SDFC_PICK(17, 0, 3, 4); SDFC_PICK(18, 0, 4, 3);
-#undef SDFC_PICK
+            double cc[16], ff[15], dd, gg[3], HH[9];
+            int oo[15];
+            load_cell<F32>(G, bi, bj, bk, cc);
+            load_cell<F32>(G, bi + cx, bj + cy, bk + cz, cc + 8);
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { ff[t] = fi[t]; ff[5 + t] = fj[t]; ff[10 + t] = fk[t]; oo[t] = oi[t]; oo[5 + t] = oj[t]; oo[10 + t] = ok_[t]; }
+            stencil_crossing(cc, cc + 8, ff, ff + 5, ff + 10, oo, oo + 5, oo + 10, G.col_th, &dd, gg, HH);
+            d = dd;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) g[t] = gg[t];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) H[t] = HH[t];
         }
     }
-    if (!ok) { sdf_stencil_generic<F32>(G, x, d, g, H); return; }
-    const double s0 = s[0];
-    d = __dadd_rn(s0, G.col_th);
-    constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
-    g[0] = exact_div(__dsub_rn(s[1], s[2]), kTwoEps, kRTwoEps);
-    g[1] = exact_div(__dsub_rn(s[3], s[4]), kTwoEps, kRTwoEps);
-    g[2] = exact_div(__dsub_rn(s[5], s[6]), kTwoEps, kRTwoEps);
-    const double two_s0 = __dmul_rn(2.0, s0);
-    H[0] = __dsub_rn(__dadd_rn(s[1], s[2]), two_s0);
-    H[4] = __dsub_rn(__dadd_rn(s[3], s[4]), two_s0);
-    H[8] = __dsub_rn(__dadd_rn(s[5], s[6]), two_s0);
-    // v = q(++) + q(--) - q(+-) - q(-+), left to right (BodySDFObj.cpp:196-203)
-    const double xy = __dsub_rn(__dsub_rn(__dadd_rn(s[7], s[8]), s[9]), s[10]);
-    const double xz = __dsub_rn(__dsub_rn(__dadd_rn(s[11], s[12]), s[13]), s[14]);
-    const double yz = __dsub_rn(__dsub_rn(__dadd_rn(s[15], s[16]), s[17]), s[18]);
-    H[1] = H[3] = xy; H[2] = H[6] = xz; H[5] = H[7] = yz;
-    constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
+    if (!ok) {
+        double xx[3] = {x[0], x[1], x[2]}, dd, gg[3], HH[9];
+        sdf_stencil_generic<F32>(G, xx, dd, gg, HH);
+        d = dd;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) H[i] = exact_div(H[i], kEps2, kREps2);
+        for (int t = 0; t < 3; ++t) g[t] = gg[t];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) H[t] = HH[t];
+    }
+    if (ok && !crossing) {
+        double c[8];
+        load_cell<F32>(G, bi, bj, bk, c);
+        stencil_reduce_on_cell(c, fi, fj, fk, G.col_th, d, g, H);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1039,6 +1123,116 @@ __device__ __forceinline__ void contact_eval_nf(const GridDev& G, const PairPose
             col[9 + r] = kg * u2[3 + r] + c * PX[r];
         }
         sink.emit(j, col);
+    }
+}
+
+// contact_eval_nf with the constant columns of X factored out. Writing column j of Km_sub as Y X_j + Z_j with
+//   Y = [ -kn u1 g^T - c [[xi1]; I] R12 P ;  kn u2 g^T + c [ [x] P - [e] ; P ] ]     (12 x 3, per contact)
+// the columns 3..5 (X_j = R21 e_m) and 9..11 (X_j = -e_m) of the SUM over contacts are (sum Y) R21 and -(sum Y):
+// only the 6 pose-dependent columns 0..2, 6..8 are formed per contact, plus the three columns of Y and fm:
+// 10 warp reductions of 12 values instead of 13, and half of the per-column algebra. Emission order
+// (sink.emit(slot, v12)): 9 = fm, 6..8 = Y columns, 0..2 = Km columns 0..2, 3..5 = Km columns 6..8.
+constexpr int kNf2Slots = 10;
+
+template <bool F32, class ColSink>
+__device__ __forceinline__ void contact_eval_nf2(const GridDev& G, const PairPoseNF& P, double kn, const double xi1[3],
+                                                 ColSink& sink) {
+    double xw1[3], x[3];
+    to_world(P.R1, P.p1, xi1[0], xi1[1], xi1[2], xw1);
+    to_local(P.R2, P.p2, xw1, x);
+    double d, g[3], H[9];
+    sdf_stencil<F32>(G, x, d, g, H);
+    const double gn = sqrt(dot3(g, g));
+    const double rgn = 1.0 / gn;
+    double e[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) e[a] = g[a] / gn;
+    const double c = kn * d;
+    double Pm[9];   // P = (H - e (e^T H)) / |g|
+    {
+        double eH[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) eH[k] = e[0] * H[k] + e[1] * H[3 + k] + e[2] * H[6 + k];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Pm[r * 3 + k] = (H[r * 3 + k] - e[r] * eH[k]) * rgn;
+    }
+    double a1[3], u1[6], u2[6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a1[r] = P.R21[r] * e[0] + P.R21[3 + r] * e[1] + P.R21[6 + r] * e[2];
+    cross3(xi1, a1, u1); cross3(x, e, u2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { u1[3 + a] = a1[a]; u2[3 + a] = e[a]; }
+    {
+        double f12[12];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { f12[i] = -c * u1[i]; f12[6 + i] = c * u2[i]; }
+        sink.emit(9, f12);
+    }
+    // the three columns of Y
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double pk[3], rp[3], t1[3], t2[3], t3[3], uk[3] = {0.0, 0.0, 0.0};
+        uk[k] = 1.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) pk[r] = Pm[r * 3 + k];                                                     // P e_k
+#pragma unroll
+        for (int r = 0; r < 3; ++r) rp[r] = P.R21[r] * pk[0] + P.R21[3 + r] * pk[1] + P.R21[6 + r] * pk[2];    // R12 P e_k
+        cross3(xi1, rp, t1);
+        cross3(x, pk, t2);
+        cross3(e, uk, t3);
+        const double kg = kn * g[k];
+        double col[12];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            col[r] = -kg * u1[r] - c * t1[r];
+            col[3 + r] = -kg * u1[3 + r] - c * rp[r];
+            col[6 + r] = kg * u2[r] + c * (t2[r] - t3[r]);
+            col[9 + r] = kg * u2[3 + r] + c * pk[r];
+        }
+        sink.emit(6 + k, col);
+    }
+    // the pose-dependent columns 0..2 (X = -R21 [xi1] e_j) and 6..8 (X = [x] e_j), as contact_eval_nf forms them
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) {
+        const int m = jj % 3;
+        double X[3], ex[3], uj[3] = {0.0, 0.0, 0.0};
+        uj[m] = 1.0;
+        if (jj < 3) {
+            double sk[3], sa[3];
+            cross3(xi1, uj, sk);
+            cross3(a1, uj, sa);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) X[r] = -(P.R21[r * 3] * sk[0] + P.R21[r * 3 + 1] * sk[1] + P.R21[r * 3 + 2] * sk[2]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) ex[r] = sa[r];
+        } else {
+            double se[3];
+            cross3(x, uj, X);
+            cross3(e, uj, se);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) ex[r] = -(P.R21[r] * se[0] + P.R21[3 + r] * se[1] + P.R21[6 + r] * se[2]);
+        }
+        const double gX = dot3(g, X);
+        double PX[3], da1[3], t1[3], t2[3], t3[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) PX[r] = Pm[r * 3] * X[0] + Pm[r * 3 + 1] * X[1] + Pm[r * 3 + 2] * X[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) da1[r] = P.R21[r] * PX[0] + P.R21[3 + r] * PX[1] + P.R21[6 + r] * PX[2] + ex[r];
+        cross3(xi1, da1, t1);
+        cross3(x, PX, t2);
+        cross3(e, X, t3);
+        double col[12];
+        const double kg = kn * gX;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            col[r] = -kg * u1[r] - c * t1[r];
+            col[3 + r] = -kg * u1[3 + r] - c * da1[r];
+            col[6 + r] = kg * u2[r] + c * (t2[r] - t3[r]);
+            col[9 + r] = kg * u2[3 + r] + c * PX[r];
+        }
+        sink.emit(jj, col);
     }
 }
 

@@ -155,3 +155,19 @@ def test_planner_wall_time_report(cuda_ctx):
     assert (r.status, r.actions, r.stages, r.rollouts) == (st, acts, stages, seq.rollouts)
     assert r.path.shape == path.shape and rel_err(path, r.path) <= 1e-9
     sim.close()
+
+
+def test_plan_matches_the_reference_script(cuda_ctx):
+    """tests/golden/run_joint_plan_bfs.npz: status and substep path of the reference's UNMODIFIED
+    `examples/run_joint_plan.py --planner bfs` on the stock CPU simulator (oracle/make_golden_planner.py).
+    The batched planner on the CUDA stepper must take the same decisions (status, number of substeps = which
+    rollout ended the search and after how many frame_skip chunks) and follow the same path to 1e-9."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "run_joint_plan_bfs.npz"))
+    p, hulls, sim = _setup(cuda_ctx, synth.l_channel(), "translational", float(z["sdf_dx"]), 64)
+    r = PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=None)
+    assert r.status == str(z["status"]) == "Success"
+    assert r.path.shape == z["path"].shape
+    assert rel_err(z["path"], r.path) <= 1e-9
+    sim.close()
