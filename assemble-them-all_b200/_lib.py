@@ -70,6 +70,8 @@ SIGNATURES = {
     "sdfc_batch_destroy": (C.c_int, [C.c_void_p]),
     "sdfc_batch_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p,
                                   c_int32_p]),
+    "sdfc_batch_eval_blocks": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p,
+                                         c_int32_p, c_double_p, c_int32_p]),
     "sdfc_batch_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "sdfc_batch_detect_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -683,26 +683,31 @@ sdfc_status sdfc_pair_create(sdfc_context* ctx, sdfc_points* contact_points, sdf
 }
 sdfc_status sdfc_pair_set_stiffness(sdfc_pair* p, double kn, double kt) {
     SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_stiffness: pair is NULL");
+    if (p->kn == kn && p->kt == kt) return SDFC_OK;   // unchanged: no re-upload of the pair table
     p->kn = kn; p->kt = kt; p->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_pair_set_friction(sdfc_pair* p, double mu) {
     SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_friction: pair is NULL");
+    if (p->mu == mu) return SDFC_OK;   // unchanged: no re-upload of the pair table
     p->mu = mu; p->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_pair_set_damping(sdfc_pair* p, double damping) {
     SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_damping: pair is NULL");
+    if (p->damping == damping) return SDFC_OK;   // unchanged: no re-upload of the pair table
     p->damping = damping; p->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_pair_set_scale(sdfc_pair* p, double scale) {
     SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_scale: pair is NULL");
+    if (p->scale == scale) return SDFC_OK;   // unchanged: no re-upload of the pair table
     p->scale = scale; p->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_pair_set_contact_scale(sdfc_pair* p, double contact_scale) {
     SDFC_REQUIRE(p != nullptr, "sdfc_pair_set_contact_scale: pair is NULL");
+    if (p->contact_scale == contact_scale) return SDFC_OK;   // unchanged: no re-upload of the pair table
     p->contact_scale = contact_scale; p->version++;
     return SDFC_OK;
 }
@@ -866,8 +871,8 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     A(dev_alloc(&b->d_fm_sub, ep * 12));
     A(dev_alloc(&b->d_Km_sub, ep * 144));
     A(dev_alloc(&b->d_Dm_sub, ep * 144));
-    A(dev_alloc(&b->d_E, (size_t)n_envs * n_bodies * 16));
-    A(dev_alloc(&b->d_phi, (size_t)n_envs * n_bodies * 6));
+    A(dev_alloc(&b->d_E, (size_t)n_envs * n_bodies * 22));   // poses, then twists: one upload
+    b->d_phi = b->d_E ? b->d_E + (size_t)n_envs * n_bodies * 16 : nullptr;
     A(dev_alloc(&b->d_fm, (size_t)n_envs * nm));
     A(dev_alloc(&b->d_Km, (size_t)n_envs * nm * nm));
     A(dev_alloc(&b->d_Dm, (size_t)n_envs * nm * nm));
@@ -904,10 +909,11 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaFree(b->d_pairs); cudaFree(b->d_tile_pair); cudaFree(b->d_tile_word0); cudaFree(b->d_mask);
     cudaFree(b->d_n_active); cudaFree(b->d_brick_stats); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
-    cudaFree(b->d_E); cudaFree(b->d_phi); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
+    cudaFree(b->d_E); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
     cudaFree(b->d_skin_margin); cudaFree(b->d_skin_pose); cudaFree(b->d_skin_int); cudaFree(b->d_skin_stats);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->h_blocks) cudaFreeHost(b->h_blocks);
     if (b->h_nact) cudaFreeHost(b->h_nact);
     sdfc_host::ground_set_destroy(b->gset);
     delete b;
@@ -1059,6 +1065,60 @@ sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* p
         if (!pd && !dm_zero) std::memcpy(Dm_out, b->h_out + nF + nK, nK * sizeof(double));
     }
     if (n_active_out && !pa) std::memcpy(n_active_out, b->h_nact, sizeof(int32_t) * nA);
+    return SDFC_OK;
+}
+
+sdfc_status sdfc_batch_eval_blocks(sdfc_batch* b, const double* E_host, const double* phi_host, int deriv, double* fm_sub_out,
+                                   double* Km_sub_out, double* Dm_sub_out, int32_t* n_active_out, double* ground_out,
+                                   int32_t* ground_active_out) {
+    SDFC_REQUIRE(b && E_host && phi_host && fm_sub_out && n_active_out, "sdfc_batch_eval_blocks: NULL argument");
+    SDFC_REQUIRE(!deriv || (Km_sub_out && Dm_sub_out), "sdfc_batch_eval_blocks: Km_sub_out / Dm_sub_out NULL with deriv != 0");
+    const int ng = b->gset ? sdfc_host::ground_set_count(b->gset) : 0;
+    SDFC_REQUIRE(ng == 0 || (ground_out && ground_active_out), "sdfc_batch_eval_blocks: the batch has ground contacts, ground outputs are NULL");
+    SDFC_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    const size_t nE = (size_t)b->n_envs * b->n_bodies * 16, nP = (size_t)b->n_envs * b->n_bodies * 6;
+    const size_t ep = (size_t)b->n_envs * b->n_pairs, eg = (size_t)b->n_envs * ng;
+    // one pinned staging block for all results: fm_sub | Km_sub | Dm_sub | ground | counts
+    const size_t n_dbl = ep * 12 + (deriv ? ep * 288 : 0) + eg * 78;
+    const size_t bytes = n_dbl * sizeof(double) + (ep + eg) * sizeof(int32_t);
+    if (b->h_blocks_bytes < bytes) {
+        if (b->h_blocks) cudaFreeHost(b->h_blocks);
+        b->h_blocks = nullptr; b->h_blocks_bytes = 0;
+        SDFC_CUDA(cudaMallocHost((void**)&b->h_blocks, bytes));
+        b->h_blocks_bytes = bytes;
+    }
+    std::memcpy(b->h_in, E_host, nE * sizeof(double));
+    std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double));
+    SDFC_CUDA(cudaMemcpyAsync(b->d_E, b->h_in, (nE + nP) * sizeof(double), cudaMemcpyHostToDevice, s));   // d_E | d_phi are one allocation
+    sdfc_status st = batch_run(b, b->d_E, b->d_E + nE, deriv, nullptr, /*scatter=*/false, nullptr, nullptr, nullptr, nullptr);
+    if (st != SDFC_OK) return st;
+    double* h = b->h_blocks;
+    double* h_fm = h; h += ep * 12;
+    double* h_Km = h; double* h_Dm = h + (deriv ? ep * 144 : 0); h += deriv ? ep * 288 : 0;
+    double* h_g = h; h += eg * 78;
+    int32_t* h_na = reinterpret_cast<int32_t*>(h);
+    SDFC_CUDA(cudaMemcpyAsync(h_fm, b->d_fm_sub, ep * 12 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (deriv) {
+        SDFC_CUDA(cudaMemcpyAsync(h_Km, b->d_Km_sub, ep * 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SDFC_CUDA(cudaMemcpyAsync(h_Dm, b->d_Dm_sub, ep * 144 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    SDFC_CUDA(cudaMemcpyAsync(h_na, b->d_n_active, ep * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (ng) {
+        SDFC_CUDA(cudaMemcpyAsync(h_g, sdfc_host::ground_set_out(b->gset), eg * 78 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SDFC_CUDA(cudaMemcpyAsync(h_na + ep, sdfc_host::ground_set_n_active(b->gset), eg * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    SDFC_CUDA(cudaStreamSynchronize(s));   // the one synchronisation of the evaluation
+    std::memcpy(fm_sub_out, h_fm, ep * 12 * sizeof(double));
+    if (deriv) {
+        std::memcpy(Km_sub_out, h_Km, ep * 144 * sizeof(double));
+        std::memcpy(Dm_sub_out, h_Dm, ep * 144 * sizeof(double));
+    }
+    std::memcpy(n_active_out, h_na, ep * sizeof(int32_t));
+    if (ng) {
+        std::memcpy(ground_out, h_g, eg * 78 * sizeof(double));
+        std::memcpy(ground_active_out, h_na + ep, eg * sizeof(int32_t));
+    }
     return SDFC_OK;
 }
 

@@ -946,7 +946,7 @@ __device__ __forceinline__ void stencil_reduce_on_cell(const double c[8], const 
 
 // One-face crossing: every sample on its own cell (base c or neighbour c2). Rare; kept out of line so that
 // its registers do not count against the common path.
-__device__ __noinline__ void stencil_crossing(const double* c, const double* c2, const double* fi, const double* fj, const double* fk,
+static __device__ __noinline__ void stencil_crossing(const double* c, const double* c2, const double* fi, const double* fj, const double* fk,
                                               const int* oi, const int* oj, const int* ok_, double col_th, double* d, double* g, double* H) {
     auto S = [&](int vi, int vj, int vk) {
         const bool nb = (oi[vi] + oj[vj] + ok_[vk]) != 0;

@@ -203,15 +203,34 @@ __device__ __forceinline__ void force_rounds(const ForceShared& S, int total, Si
     }
 }
 
+// Sink of contact_eval_nf2: 10 reductions of 12 values per round (Km columns 0..2, 6..8, the three columns of Y, fm).
+struct Nf2Sink {
+    double acc[kNf2Slots];
+    unsigned lane;
+    __device__ __forceinline__ void init(unsigned l) {
+        lane = l;
+#pragma unroll
+        for (int j = 0; j < kNf2Slots; ++j) acc[j] = 0.0;
+    }
+    __device__ __forceinline__ void emit(int j, const double* c12) {
+        // lanes beyond the last contact evaluate a duplicate with kn = 0: every output is proportional to kn
+        double v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = c12[i];
+        TransposeReduce<12, 16>::run(v, lane);
+        acc[j] += v[0];
+    }
+};
+
 template <bool F32>
-__device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total, ColSink& sink) {
+__device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total, Nf2Sink& sink) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = warp * 32; base < total; base += kForceThreads) {
         const int c = base + lane;
-        sink.valid = c < total;
-        const int id = S.ids[sink.valid ? c : base];
+        const bool valid = c < total;
+        const int id = S.ids[valid ? c : base];
         const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
-        contact_eval_nf<F32>(S.pd.grid, S.nf, sink.valid ? S.pd.prm.kn : 0.0, xi1, sink);
+        contact_eval_nf2<F32>(S.pd.grid, S.nf, valid ? S.pd.prm.kn : 0.0, xi1, sink);
     }
 }
 
@@ -243,24 +262,25 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
         for (int i = tid; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    // 36 threads stage the two poses and twists (any CTA width from one warp pair up)
     if (tid < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, tid);
-    else if (tid >= 32 && tid < 44) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, tid - 32);
-    else if (tid >= 64 && tid < 70) S.pose.phi1[tid - 64] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + tid - 64);
-    else if (tid >= 96 && tid < 102) S.pose.phi2[tid - 96] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + tid - 96);
+    else if (tid < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, tid - 12);
+    else if (tid < 30) S.pose.phi1[tid - 24] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + tid - 24);
+    else if (tid < 36) S.pose.phi2[tid - 30] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + tid - 30);
 
     if constexpr (NF) {
         __syncthreads();
         if (tid < 9) {
             const int r = tid / 3, c = tid % 3;  // R21 = R2^T R1
             S.nf.R21[tid] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
-        } else if (tid >= 32 && tid < 41) {
-            S.nf.R1[tid - 32] = S.pose.R1[tid - 32]; S.nf.R2[tid - 32] = S.pose.R2[tid - 32];
-        } else if (tid >= 64 && tid < 67) {
-            S.nf.p1[tid - 64] = S.pose.p1[tid - 64]; S.nf.p2[tid - 64] = S.pose.p2[tid - 64];
+        } else if (tid >= 9 && tid < 18) {
+            S.nf.R1[tid - 9] = S.pose.R1[tid - 9]; S.nf.R2[tid - 9] = S.pose.R2[tid - 9];
+        } else if (tid >= 18 && tid < 21) {
+            S.nf.p1[tid - 18] = S.pose.p1[tid - 18]; S.nf.p2[tid - 18] = S.pose.p2[tid - 18];
         }
     }
     WarpSink<DERIV && !NF, DM> sink;
-    ColSink csink;
+    Nf2Sink csink;
     if constexpr (NF) csink.init(lane); else sink.init(lane);
 
     const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
     double* mine = red + (size_t)warp * NPART;
     if constexpr (NF) {
 #pragma unroll
-        for (int j = 0; j < kNfCols; ++j) mine[j * 32 + lane] = csink.acc[j];
+        for (int j = 0; j < kNf2Slots; ++j) mine[j * 32 + lane] = csink.acc[j];
     } else if (DERIV) {
 #pragma unroll
         for (int b = 0; b < 4; ++b)
@@ -335,6 +355,28 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
     // fixed slot stride (the largest layout): value-only and derivative environments share the
     // buffer within one evaluation round of the stepper, so the stride must not depend on the variant
     double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * kPartialDerivDM;
+    if constexpr (NF) {
+        // 10 reduced slots -> the 13-column layout of the partials: columns 3..5 = (sum Y) R21, 9..11 = -(sum Y)
+        if (tid < 32) {
+            double a[kNf2Slots];
+#pragma unroll
+            for (int j = 0; j < kNf2Slots; ++j) {
+                double s = red[j * 32 + tid];
+#pragma unroll
+                for (int w = 1; w < kNumWarps; ++w) s += red[(size_t)w * NPART + j * 32 + tid];
+                a[j] = s;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                out[m * 32 + tid] = a[m];
+                out[(6 + m) * 32 + tid] = a[3 + m];
+                out[(3 + m) * 32 + tid] = a[6] * S.nf.R21[m] + a[7] * S.nf.R21[3 + m] + a[8] * S.nf.R21[6 + m];
+                out[(9 + m) * 32 + tid] = -a[6 + m];
+            }
+            out[12 * 32 + tid] = a[9];
+        }
+        return;
+    }
     for (int i = tid; i < NPART; i += kForceThreads) {
         double s = red[i];
 #pragma unroll
@@ -343,127 +385,10 @@ __global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP)
     }
 }
 
-// --------------------------------------------------------------------------
-// planner force kernel (derivatives, mu = 0, damping = 0): one WARP per (environment, pair, split)
-// --------------------------------------------------------------------------
-// A planner batch has ~100-200 active contacts per (environment, pair): a 4-warp CTA per pair ran one or two
-// partly filled rounds, paid three block barriers per mask tile and a cross-warp combine through shared
-// memory. Here every warp owns one (environment, pair, split): it compacts its mask words 32 at a time into
-// its own id buffer, evaluates 32 contacts per round (contact_eval_nf2: 10 reductions of 12 values), keeps the
-// reduced sums in registers and writes the 13-column partial layout k_reduce_splits expects - no block
-// barrier anywhere, four independent pairs per CTA.
-struct Nf2Sink {
-    double acc[kNf2Slots];
-    unsigned lane;
-    __device__ __forceinline__ void init(unsigned l) {
-        lane = l;
-#pragma unroll
-        for (int j = 0; j < kNf2Slots; ++j) acc[j] = 0.0;
-    }
-    __device__ __forceinline__ void emit(int j, const double* c12) {
-        // lanes beyond the last contact evaluate a duplicate with kn = 0: every output is proportional to kn
-        double v[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = c12[i];
-        TransposeReduce<12, 16>::run(v, lane);
-        acc[j] += v[0];
-    }
-};
-
-struct NfWarpShared {
-    PairDev pd;
-    PairPoseNF nf;
-    int ids[32 * 32];
-};
-
-#ifndef SDFC_FORCE_NF2_MIN_BLOCKS
-#define SDFC_FORCE_NF2_MIN_BLOCKS 3
-#endif
-__global__ void __launch_bounds__(kForceThreads, SDFC_FORCE_NF2_MIN_BLOCKS) k_force_nf(BatchDev B, const double* __restrict__ E) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * kNumWarps + warp;
-    if (gw >= B.env_count * B.n_pairs * B.splits) return;   // warp-uniform from here on
-    const int split = gw % B.splits, pair = (gw / B.splits) % B.n_pairs;
-    const int env = B.env0 + gw / (B.splits * B.n_pairs);
-    if (B.env_mode != nullptr && __ldg(B.env_mode + env) != 2) return;
-    if (__ldg(B.n_active + (size_t)env * B.n_pairs + pair) == 0) return;
-    NfWarpShared& S = reinterpret_cast<NfWarpShared*>(smem_raw)[warp];
-    {
-        const int* src = reinterpret_cast<const int*>(B.pairs + pair);
-        int* dst = reinterpret_cast<int*>(&S.pd);
-        for (int i = lane; i < (int)(sizeof(PairDev) / sizeof(int)); i += 32) dst[i] = __ldg(src + i);
-    }
-    __syncwarp();
-    if (lane < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.nf.R1, S.nf.p1, lane);
-    else if (lane >= 16 && lane < 28) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.nf.R2, S.nf.p2, lane - 16);
-    __syncwarp();
-    if (lane < 9) {
-        const int r = lane / 3, c = lane % 3;  // R21 = R2^T R1
-        S.nf.R21[lane] = S.nf.R2[r] * S.nf.R1[c] + S.nf.R2[3 + r] * S.nf.R1[3 + c] + S.nf.R2[6 + r] * S.nf.R1[6 + c];
-    }
-    __syncwarp();
-    Nf2Sink sink;
-    sink.init(lane);
-    const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
-    const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
-    const uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
-    const bool f32 = S.pd.grid.f32();
-    const double kn = S.pd.prm.kn;
-    for (int tw = w0; tw < w1; tw += 32) {
-        uint32_t word = (tw + lane < w1) ? __ldg(mask_row + tw + lane) : 0u;
-        const int cnt = __popc(word);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        int off = incl - cnt;
-        while (word) {
-            const int b = __ffs(word) - 1;
-            S.ids[off++] = (tw + lane) * 32 + b;
-            word &= word - 1;
-        }
-        __syncwarp();
-        for (int base = 0; base < total; base += 32) {
-            const int c = base + lane;
-            const bool valid = c < total;
-            const int id = S.ids[valid ? c : base];
-            const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
-            if (f32) contact_eval_nf2<true>(S.pd.grid, S.nf, valid ? kn : 0.0, xi1, sink);
-            else contact_eval_nf2<false>(S.pd.grid, S.nf, valid ? kn : 0.0, xi1, sink);
-        }
-        __syncwarp();   // ids are rewritten by the next group of words
-    }
-    // 13-column layout of the partials (slot j * 32 + lane holds this lane's entry of column j; fm is column 12):
-    // columns 3..5 = (sum Y) R21, 9..11 = -(sum Y)
-    double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * kPartialDerivDM;
-    const double y0 = sink.acc[6], y1 = sink.acc[7], y2 = sink.acc[8];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        out[m * 32 + lane] = sink.acc[m];
-        out[(6 + m) * 32 + lane] = sink.acc[3 + m];
-        out[(3 + m) * 32 + lane] = y0 * S.nf.R21[m] + y1 * S.nf.R21[3 + m] + y2 * S.nf.R21[6 + m];
-    }
-    out[9 * 32 + lane] = -y0;
-    out[10 * 32 + lane] = -y1;
-    out[11 * 32 + lane] = -y2;
-    out[12 * 32 + lane] = sink.acc[9];
-}
-
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
 void launch_force_t(const BatchDev& B, const double* E, const double* phi, cudaStream_t stream) {
     constexpr bool DM = ANYFRIC || ANYDAMP;
-    if constexpr (DERIV && !DM) {
-        const size_t smem_nf = sizeof(NfWarpShared) * kNumWarps;
-        const int warps = B.env_count * B.n_pairs * B.splits;
-        if (warps <= 0) return;
-        k_force_nf<<<(warps + kNumWarps - 1) / kNumWarps, kForceThreads, smem_nf, stream>>>(B, E);
-        return;
-    } else {
+    {
     constexpr int NPART = (DERIV && !DM) ? kPartialNF : (DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
     const size_t smem = sizeof(ForceShared) + sizeof(double) * kNumWarps * NPART;
     static bool configured = false;

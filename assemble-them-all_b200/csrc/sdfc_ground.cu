@@ -453,21 +453,25 @@ sdfc_status sdfc_ground_create(sdfc_context* ctx, sdfc_points* contact_points, c
 }
 sdfc_status sdfc_ground_set_transform(sdfc_ground* g, const double E_g[16]) {
     SDFC_REQUIRE(g && E_g, "sdfc_ground_set_transform: NULL argument");
+    if (std::memcmp(g->E_g, E_g, sizeof(g->E_g)) == 0) return SDFC_OK;   // unchanged: no re-upload
     std::memcpy(g->E_g, E_g, sizeof(g->E_g)); g->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_ground_set_stiffness(sdfc_ground* g, double kn, double kt) {
     SDFC_REQUIRE(g != nullptr, "sdfc_ground_set_stiffness: ground is NULL");
+    if (g->kn == kn && g->kt == kt) return SDFC_OK;
     g->kn = kn; g->kt = kt; g->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_ground_set_friction(sdfc_ground* g, double mu) {
     SDFC_REQUIRE(g != nullptr, "sdfc_ground_set_friction: ground is NULL");
+    if (g->mu == mu) return SDFC_OK;
     g->mu = mu; g->version++;
     return SDFC_OK;
 }
 sdfc_status sdfc_ground_set_damping(sdfc_ground* g, double damping) {
     SDFC_REQUIRE(g != nullptr, "sdfc_ground_set_damping: ground is NULL");
+    if (g->damping == damping) return SDFC_OK;
     g->damping = damping; g->version++;
     return SDFC_OK;
 }

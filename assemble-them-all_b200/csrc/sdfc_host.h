@@ -128,6 +128,8 @@ struct sdfc_batch {
     double* h_in = nullptr;   // pinned: E then phi
     double* h_out = nullptr;  // pinned: fm, Km, Dm
     int32_t* h_nact = nullptr;
+    double* h_blocks = nullptr;   // pinned: per-pair / per-ground blocks of sdfc_batch_eval_blocks
+    size_t h_blocks_bytes = 0;
     // optional temporal-coherence culling of the detection kernel (BatchDev::skin_*), switched on by the stepper
     bool skin_on = false;
     float* d_skin_margin = nullptr; double* d_skin_pose = nullptr; int* d_skin_int = nullptr;

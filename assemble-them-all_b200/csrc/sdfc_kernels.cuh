@@ -34,7 +34,10 @@ struct PairDev {
 //   derivative: 4 K-blocks x kSlotK slots, then (if DM) 4 D-blocks x kSlotD slots
 //   value-only: kSlotF slots
 // Slot -> entry maps are produced by tr_index<N>() (see sdfc_kernels.cu).
-constexpr int kNumWarps = 4;           // force kernel: warps per CTA
+#ifndef SDFC_FORCE_WARPS
+#define SDFC_FORCE_WARPS 4
+#endif
+constexpr int kNumWarps = SDFC_FORCE_WARPS;   // force kernel: warps per CTA
 constexpr int kForceThreads = 32 * kNumWarps;
 constexpr int kDetectThreads = 256;
 constexpr int kDetectWordsPerWarp = 8; // 256 points per warp per tile (2048 per CTA)

@@ -11,6 +11,7 @@
 #include "Simulation.h"
 
 #include "B200DeviceCache.h"
+#include "B200RobotBatch.h"
 
 #include <vector>
 
@@ -62,40 +63,14 @@ ForceGeneralSDFContactB200::ForceGeneralSDFContactB200(Simulation* sim, Body* co
                                                        dtype kt, dtype mu, dtype damping)
     : ForceGeneralSDFContact(sim, contact_body, SDF_body, kn, kt, mu, damping) {}
 
-void ForceGeneralSDFContactB200::init() { ensure_uploaded(); }
+void ForceGeneralSDFContactB200::init() { ensure_registered(); }
 
-void ForceGeneralSDFContactB200::ensure_uploaded() {
-    if (_pair != nullptr) return;
-    _ctx = cache().ctx;
-    _sdf = b200::sdf_of(_SDF_body);
-    _pts = b200::contact_points_of(_contact_body, /*general_sdf=*/true);
-    check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
+void ForceGeneralSDFContactB200::ensure_registered() {
+    if (_rb) return;
+    cache();   // fails loudly without a CUDA device: there is no CPU path behind this force
+    _rb = b200::RobotBatch::of(_sim);
+    _slot = _rb->add(this);
     _sync_col_th = _SDF_body->_col_th;
-    _synced = false;
-}
-
-void ForceGeneralSDFContactB200::sync_parameters() {
-    const dtype cs = _contact_body->_contact_scale, cth = _SDF_body->_col_th;
-    if (_synced && _sync_kn == _kn && _sync_kt == _kt && _sync_mu == _mu && _sync_damping == _damping &&
-        _sync_scale == _scale && _sync_contact_scale == cs && _sync_col_th == cth)
-        return;
-    check(sdfc_pair_set_stiffness(_pair, _kn, _kt), "set_stiffness");
-    check(sdfc_pair_set_friction(_pair, _mu), "set_friction");
-    check(sdfc_pair_set_damping(_pair, _damping), "set_damping");
-    check(sdfc_pair_set_scale(_pair, _scale), "set_scale");
-    check(sdfc_pair_set_contact_scale(_pair, cs), "set_contact_scale");
-    if (_sync_col_th != cth) {
-        // device grids are shared between bodies with equal content (B200DeviceCache.h) and col_th is part
-        // of the key: a changed threshold re-points this force at the matching grid instead of mutating a
-        // shared one
-        check(sdfc_pair_destroy(_pair), "pair_destroy");
-        _pair = nullptr;
-        _sdf = b200::sdf_of(_SDF_body);
-        check(sdfc_pair_create(_ctx, _pts, _sdf, _kn, _kt, _mu, _damping, &_pair), "ForceGeneralSDFContactB200: pair");
-    }
-    _sync_kn = _kn; _sync_kt = _kt; _sync_mu = _mu; _sync_damping = _damping; _sync_scale = _scale;
-    _sync_contact_scale = cs; _sync_col_th = cth;
-    _synced = true;
 }
 
 void ForceGeneralSDFContactB200::record_history(int n_active) {
@@ -107,16 +82,13 @@ void ForceGeneralSDFContactB200::record_history(int n_active) {
 
 void ForceGeneralSDFContactB200::computeForce(VectorX& fm, VectorX& fr, bool verbose) {
     auto t0 = clock();
-    ensure_uploaded();
-    sync_parameters();
-    double fm_sub[12];
-    int32_t n_active = 0;
-    const Matrix4 E1 = _contact_body->_E_0i, E2 = _SDF_body->_E_0i;  // column-major, as the C-ABI expects
-    const Vector6 phi1 = _contact_body->_phi, phi2 = _SDF_body->_phi;
-    check(sdfc_pair_force(_pair, E1.data(), phi1.data(), E2.data(), phi2.data(), fm_sub, &n_active),
-          "ForceGeneralSDFContactB200::computeForce");
-    record_history(n_active);
-    sdfc_scatter_force(_contact_body->_index[0], _SDF_body->_index[0], fm_sub, fm.data());  // .cpp:60-61
+    ensure_registered();
+    // device grids are shared between bodies with equal content and col_th is part of their key: a changed
+    // threshold makes the batch look its grids up again
+    if (_sync_col_th != _SDF_body->_col_th) { _rb->invalidate(); _sync_col_th = _SDF_body->_col_th; }
+    _rb->evaluate(false);   // one device call per Robot evaluation, shared by all B200 forces
+    record_history(_rb->n_active(_slot));
+    sdfc_scatter_force(_contact_body->_index[0], _SDF_body->_index[0], _rb->fm_sub(_slot), fm.data());  // .cpp:60-61
     ++_n_evaluations;
     _time.add("collision detection", 0);
     _time.add("compute force", clock() - t0);
@@ -125,18 +97,13 @@ void ForceGeneralSDFContactB200::computeForce(VectorX& fm, VectorX& fr, bool ver
 void ForceGeneralSDFContactB200::computeForceWithDerivative(VectorX& fm, VectorX& fr, MatrixX& Km, MatrixX& Dm,
                                                             MatrixX& Kr, MatrixX& Dr, bool verbose) {
     auto t0 = clock();
-    ensure_uploaded();
-    sync_parameters();
-    double fm_sub[12], Km_sub[144], Dm_sub[144];
-    int32_t n_active = 0;
-    const Matrix4 E1 = _contact_body->_E_0i, E2 = _SDF_body->_E_0i;
-    const Vector6 phi1 = _contact_body->_phi, phi2 = _SDF_body->_phi;
-    check(sdfc_pair_force_deriv(_pair, E1.data(), phi1.data(), E2.data(), phi2.data(), fm_sub, Km_sub, Dm_sub, &n_active),
-          "ForceGeneralSDFContactB200::computeForceWithDerivative");
-    record_history(n_active);
+    ensure_registered();
+    if (_sync_col_th != _SDF_body->_col_th) { _rb->invalidate(); _sync_col_th = _SDF_body->_col_th; }
+    _rb->evaluate(true);
+    record_history(_rb->n_active(_slot));
     const int ia = _contact_body->_index[0], ib = _SDF_body->_index[0];
-    sdfc_scatter_force(ia, ib, fm_sub, fm.data());                                      // .cpp:88-89
-    sdfc_scatter_deriv((int)Km.rows(), ia, ib, Km_sub, Dm_sub, Km.data(), Dm.data());   // .cpp:91-99 (column-major)
+    sdfc_scatter_force(ia, ib, _rb->fm_sub(_slot), fm.data());                                                  // .cpp:88-89
+    sdfc_scatter_deriv((int)Km.rows(), ia, ib, _rb->Km_sub(_slot), _rb->Dm_sub(_slot), Km.data(), Dm.data());   // .cpp:91-99 (column-major)
     ++_n_evaluations;
     _time.add("collision detection", 0);
     _time.add("compute force", clock() - t0);

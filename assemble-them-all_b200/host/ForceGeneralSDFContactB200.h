@@ -17,20 +17,19 @@
 #pragma once
 #include "Force/ForceGeneralSDFContact.h"
 
-struct sdfc_context;
-struct sdfc_sdf;
-struct sdfc_points;
-struct sdfc_pair;
+#include <memory>
 
 namespace redmax {
+
+namespace b200 { class RobotBatch; }
 
 class ForceGeneralSDFContactB200 : public ForceGeneralSDFContact {
 public:
     ForceGeneralSDFContactB200(Simulation* sim, Body* contact_body, Body* SDF_body,
                                dtype kn = 1., dtype kt = 0., dtype mu = 0., dtype damping = 0.);
 
-    // uploads Body::_contact_points and the BodySDFObj grid once; Robot::init calls it
-    // after the first Robot::update (Robot.cpp:156-159)
+    // registers with the Simulation's RobotBatch (device uploads happen at the first evaluation, once per
+    // distinct grid / point set); Robot::init calls it after the first Robot::update (Robot.cpp:156-159)
     void init();
 
     void computeForce(VectorX& fm, VectorX& fr, bool verbose = false);
@@ -49,19 +48,13 @@ public:
     long long _n_evaluations = 0;  // GPU evaluations issued by this force (diagnostics)
 
 private:
-    void ensure_uploaded();
-    void sync_parameters();
+    void ensure_registered();
     void record_history(int n_active);
 
-    sdfc_context* _ctx = nullptr;
-    sdfc_sdf* _sdf = nullptr;
-    sdfc_points* _pts = nullptr;
-    sdfc_pair* _pair = nullptr;
-    // parameter values last pushed to the device (members are public and the setters
-    // are non-virtual in the reference, so changes are detected at evaluation time)
-    dtype _sync_kn = 0, _sync_kt = 0, _sync_mu = 0, _sync_damping = 0, _sync_scale = 0, _sync_contact_scale = 0,
-          _sync_col_th = 0;
-    bool _synced = false;
+    // every B200 force of this Simulation is evaluated in one device call (B200RobotBatch.h)
+    std::shared_ptr<b200::RobotBatch> _rb;
+    int _slot = -1;
+    dtype _sync_col_th = 0;
 };
 
 }  // namespace redmax

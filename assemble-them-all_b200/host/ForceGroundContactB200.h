@@ -10,10 +10,14 @@
 #pragma once
 #include "Force/ForceGroundContact.h"
 
+#include <memory>
+
 struct sdfc_ground;
 struct sdfc_points;
 
 namespace redmax {
+
+namespace b200 { class RobotBatch; }
 
 class ForceGroundContactB200 : public ForceGroundContact {
 public:
@@ -30,6 +34,10 @@ public:
 private:
     void ensure_uploaded();
     void sync_parameters();
+    bool evaluate_batched(bool deriv, const double** out, int* n_active);
+    // with SDF contact forces in the same Simulation the ground contacts ride in their device call (B200RobotBatch.h)
+    std::shared_ptr<b200::RobotBatch> _rb;
+    int _slot = -1;
     sdfc_ground* _ground = nullptr;
     Matrix4 _sync_E_g;
     dtype _sync_kn = 0, _sync_kt = 0, _sync_mu = 0, _sync_damping = 0;

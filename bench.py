@@ -607,6 +607,42 @@ def hbm_regime_leg(ctx, torch, stream, dev, peak, n_points=30_000_000, grid_n=51
     return out
 
 
+def plugin_leg(cpu):
+    """The drop-in path a RedMax user gets: the reference's OWN redmax_py (unmodified Simulation / Robot / BDF1 /
+    Newton / pybind objects), built with the B200 Force plug-ins (oracle/_ref/b200), driven per substep from
+    Python the way the BFS planner drives it (tests/drivers/redmax_rollout.py: 6 actions x 100 x forward(1)) on
+    the C2 geometry, next to the stock CPU module on the same inputs. Every Robot evaluation is one device call
+    (host/B200RobotBatch.h). Wall clock inside forward(); SDF construction excluded (reported by sdf_build)."""
+    import glob
+    import re
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not (glob.glob(os.path.join(ref, "redmax_py*.so")) and glob.glob(os.path.join(ref, "b200", "redmax_py*.so"))):
+        return {"unavailable": "oracle/_ref (stock + b200 redmax_py) not built"}
+    driver = os.path.join(ROOT, "tests", "drivers", "redmax_rollout.py")
+    out = {"workload": "C2 geometry (2 x ~10000 contact pts, dx 0.05), translational joint, 6 actions x 100 x forward(1) from Python",
+           "unit": "env-steps/s"}
+    arms = [("b200", os.path.join(ref, "b200"))] + ([("stock_cpu", ref)] if cpu else [])
+    finals = {}
+    for name, mod in arms:
+        with tempfile.TemporaryDirectory() as td:
+            npz = os.path.join(td, "o.npz")
+            r = subprocess.run([sys.executable, driver, mod, npz, "--nverts", "10000", "--dx", "0.05", "--steps", "100"],
+                               capture_output=True, text=True, timeout=900)
+            m = re.search(r"\(([0-9.]+) env-steps/s\)", r.stdout)
+            if r.returncode != 0 or not m:
+                return {"unavailable": f"{name}: " + (r.stdout + r.stderr)[-300:]}
+            out[name] = float(m.group(1))
+            finals[name] = np.load(npz)["Q"]
+    if "stock_cpu" in finals:
+        err = float(np.max(np.abs(finals["b200"] - finals["stock_cpu"])) / np.max(np.abs(finals["stock_cpu"])))
+        if err > 1e-9:
+            raise SystemExit(f"PARITY FAILURE: b200 redmax_py vs stock redmax_py per-substep q differ by {err:.3e}")
+        out["max_rel_err_q_vs_stock"] = err
+        out["speedup_vs_stock_1core"] = out["b200"] / out["stock_cpu"]
+    out["value"] = out["b200"]
+    return out
+
+
 def sdf_build_leg(ctx, cpu):
     """SDF construction (sdfgen::make_level_set3 drop-in) for the two C2 parts: wall time of the host call
     (upload, ~5 k wavefront launches, download); the CPU restatement timed on the larger part."""
@@ -873,6 +909,8 @@ def run_ours(args):
         extras["rotational_rollouts"] = rot_leg(ctx, args, torch, stream)
         extras["c3_rotational_100k"] = rot_leg(ctx, args, torch, stream, n_vertices=100000)
         extras["sdf_build"] = sdf_build_leg(ctx, cpu=(world == 1 and not args.no_cpu_baseline))
+        if world == 1:
+            extras["plugin_drop_in"] = plugin_leg(cpu=not args.no_cpu_baseline)
         extras["roofline_hbm_regime"] = hbm_regime_leg(ctx, torch, stream, dev, measured_hbm_peak()[0])
 
     live = ctx.measure_peaks()

@@ -260,6 +260,15 @@ SDFC_API sdfc_status sdfc_batch_eval(sdfc_batch* batch, const double* E_host, co
 
 /* Device-resident entry: same arrays, all in HBM; asynchronous on the context
  * stream. Dm_dev may be NULL (skipped). */
+/* Same evaluation, results PER FORCE instead of accumulated: fm_sub_out[env][pair][12], Km_sub_out / Dm_sub_out
+ * [env][pair][144] (column-major 12 x 12, deriv only), n_active_out[env][pair]; for the batch's ground contacts
+ * ground_out[env][ground][78] = fm 6 | Km 36 | Dm 36 (column-major 6 x 6) and ground_active_out[env][ground].
+ * One upload, one synchronisation. This is what a host whose plug-in interface is per force
+ * (redmax::Force::computeForce[WithDerivative], Force/Force.h:9-58) calls once per Robot evaluation: every
+ * force of the Robot then adds its own blocks (host/B200RobotBatch.h). */
+SDFC_API sdfc_status sdfc_batch_eval_blocks(sdfc_batch* batch, const double* E_host, const double* phi_host, int deriv,
+                                            double* fm_sub_out, double* Km_sub_out, double* Dm_sub_out,
+                                            int32_t* n_active_out, double* ground_out, int32_t* ground_active_out);
 SDFC_API sdfc_status sdfc_batch_eval_device(sdfc_batch* batch, const double* E_dev, const double* phi_dev,
                                             int deriv, double* fm_dev, double* Km_dev, double* Dm_dev,
                                             int32_t* n_active_dev);
