@@ -29,7 +29,7 @@ using sdfc_host::fail;
 
 namespace {
 
-void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, PairDev* out) {
+void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, int tile_offset, PairDev* out) {
     const sdfc_points* pts = p->pts;
     out->sx = pts->d_s; out->sy = pts->d_s + pts->n; out->sz = pts->d_s + 2 * (size_t)pts->n;
     out->ox = pts->d_o; out->oy = pts->d_o + pts->n; out->oz = pts->d_o + 2 * (size_t)pts->n;
@@ -39,6 +39,7 @@ void fill_pair_dev(const sdfc_pair* p, int body_a, int body_b, int word_offset, 
     out->n = pts->n;
     out->n_words = (pts->n + 31) / 32;
     out->word_offset = word_offset;
+    out->tile_offset = tile_offset;
     out->body_a = body_a; out->body_b = body_b;
     out->grid = p->sdf->dev;
     // ForceGeneralSDFContact.cpp:155-156 / 235-236
@@ -54,12 +55,13 @@ sdfc_status batch_refresh(sdfc_batch* b) {
         if (b->seen_pair_version[i] != b->pairs[i]->version || b->seen_sdf_version[i] != b->pairs[i]->sdf->version) dirty = true;
     if (!dirty) return SDFC_OK;
     std::vector<PairDev> host(b->n_pairs);
-    int word_offset = 0;
+    int word_offset = 0, tile_offset = 0;
     b->any_fric = b->any_damp = false;
     b->dev.any_bricks = 0;
     for (int i = 0; i < b->n_pairs; ++i) {
-        fill_pair_dev(b->pairs[i], b->body_a[i], b->body_b[i], word_offset, &host[i]);
+        fill_pair_dev(b->pairs[i], b->body_a[i], b->body_b[i], word_offset, tile_offset, &host[i]);
         word_offset += host[i].n_words;
+        tile_offset += (host[i].n_words + kDetectTileWords - 1) / kDetectTileWords;   // as sdfc_batch_create lists the tiles
         if (host[i].prm.mu > kEps) b->any_fric = true;
         if (host[i].prm.damping != 0.0) b->any_damp = true;
         if (host[i].grid.b32 != nullptr) b->dev.any_bricks = 1;
@@ -93,6 +95,7 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     launch_detect_mask(dev, E_dev, s, /*reset_counts=*/!counts_zeroed);
     c->end();
     c->begin(1);
+    launch_force_plan(dev, deriv != 0, s);
     if (env_mode_dev != nullptr) {
         launch_force(dev, E_dev, phi_dev, false, b->any_fric, b->any_damp, s);
         launch_force(dev, E_dev, phi_dev, true, b->any_fric, b->any_damp, s);
@@ -102,7 +105,7 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     }
     c->end();
     c->begin(2); launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
-    c->launches += 3;
+    c->launches += 4;
     if (b->gset) {
         st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, deriv, env_mode_dev, env0, env_count);
         if (st != SDFC_OK) return st;
@@ -127,11 +130,13 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
 sdfc_status batch_prepare(sdfc_batch* b) { return batch_refresh(b); }
 
 sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* phi_dev, const int* env_mode_dev, int env0,
-                              int env_count, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev) {
+                              int env_count, int plan_slot, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev) {
     sdfc_context* c = b->ctx;
+    if (plan_slot < 0 || plan_slot >= b->n_plan_slots) return fail(SDFC_ERR_INVALID, "batch_run_stepper: work-list slot was not allocated");
     BatchDev dev = b->dev;
     dev.env_mode = env_mode_dev;
     dev.env0 = env0; dev.env_count = env_count;
+    dev.plan[0] = b->plan_slot[plan_slot][0]; dev.plan[1] = b->plan_slot[plan_slot][1];
     if (b->gset) {
         SDFC_CUDA(cudaEventRecord(ev[0], s0));
         SDFC_CUDA(cudaStreamWaitEvent(s2, ev[0], 0));
@@ -140,6 +145,7 @@ sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* 
         SDFC_CUDA(cudaEventRecord(ev[1], s2));
     }
     launch_detect_mask(dev, E_dev, s0, /*reset_counts=*/false);
+    launch_force_plan(dev, false, s0);
     SDFC_CUDA(cudaEventRecord(ev[2], s0));
     SDFC_CUDA(cudaStreamWaitEvent(s1, ev[2], 0));
     launch_force(dev, E_dev, phi_dev, false, b->any_fric, b->any_damp, s0);
@@ -147,8 +153,29 @@ sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* 
     SDFC_CUDA(cudaEventRecord(ev[3], s1));
     SDFC_CUDA(cudaStreamWaitEvent(s0, ev[3], 0));
     if (b->gset) SDFC_CUDA(cudaStreamWaitEvent(s0, ev[1], 0));
-    c->launches += 3;
+    c->launches += 4;
     SDFC_CUDA(cudaGetLastError());
+    return SDFC_OK;
+}
+
+sdfc_status batch_ensure_plan_slots(sdfc_batch* b, int n) {
+    if (n > sdfc_batch::kMaxPlanSlots) return fail(SDFC_ERR_INVALID, "batch_ensure_plan_slots: too many concurrent evaluations");
+    const size_t ep = (size_t)b->n_envs * b->n_pairs;
+    int g_min = 1;
+    if (const char* g = std::getenv("SDFC_FORCE_G")) g_min = std::max(1, std::atoi(g));
+    for (; b->n_plan_slots < n; ++b->n_plan_slots) {
+        for (int m = 0; m < 2; ++m) {
+            ForcePlanDev& P = b->plan_slot[b->n_plan_slots][m];
+            P.cap = b->plan_cap; P.stride = m ? kPartialDerivDM : kPartialValue; P.g_min = g_min;
+            sdfc_status st = dev_alloc(&P.items, (size_t)P.cap);
+            if (st == SDFC_OK) st = dev_alloc(&P.pair_item0, ep);
+            if (st == SDFC_OK) st = dev_alloc(&P.hdr, (size_t)4);
+            if (st == SDFC_OK) st = dev_alloc(&P.partial, (size_t)P.cap * P.stride);
+            if (st != SDFC_OK) return st;
+            SDFC_CUDA(cudaMemset(P.hdr, 0, sizeof(int) * 4));
+        }
+    }
+    SDFC_CUDA(cudaDeviceSynchronize());   // null-stream memsets before any non-blocking stream uses the lists
     return SDFC_OK;
 }
 
@@ -739,7 +766,7 @@ sdfc_status sdfc_pair_query(sdfc_pair* p, const double E1[16], const double E2[1
     SDFC_CUDA(cudaMemcpyAsync(p->d_E, E1, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
     SDFC_CUDA(cudaMemcpyAsync(p->d_E + 16, E2, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
     PairDev pd;
-    fill_pair_dev(p, 0, 1, 0, &pd);
+    fill_pair_dev(p, 0, 1, 0, 0, &pd);
     launch_query_points(pd, p->d_E, p->d_E + 16, d_out ? p->d_d : nullptr, cell_out ? p->d_cell : nullptr,
                         active_out ? p->d_active : nullptr, p->d_count, s);
     p->ctx->launches += 1;
@@ -853,9 +880,11 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
         b->queries += pairs[i]->pts->n;
     }
     b->queries *= n_envs;
-    const int target_ctas = 148 * 4;
-    int splits = (target_ctas + n_envs * n_pairs - 1) / (n_envs * n_pairs);
-    splits = std::max(1, std::min(splits, std::max(1, (max_words + 7) / 8)));
+    // capacity of the force work lists: one item per 32-contact round while they fit, every pair gets at least one
+    {
+        const int64_t rounds_possible = (int64_t)words * n_envs;
+        b->plan_cap = (int)std::min<int64_t>((int64_t)1 << 30, std::min<int64_t>(16384, std::max<int64_t>(1024, rounds_possible)) + (int64_t)n_envs * n_pairs);
+    }
     const size_t ep = (size_t)n_envs * n_pairs;
     const int nm = 6 * n_bodies;
 
@@ -866,8 +895,9 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     A(dev_alloc(&b->d_tile_word0, tile_word0.size()));
     A(dev_alloc(&b->d_mask, (size_t)n_envs * std::max(words, 1)));
     A(dev_alloc(&b->d_n_active, ep));
+    A(dev_alloc(&b->d_tile_count, (size_t)n_envs * std::max<size_t>(tile_pair.size(), 1)));
     A(dev_alloc(&b->d_brick_stats, (size_t)3));
-    A(dev_alloc(&b->d_partial, ep * splits * kPartialDerivDM));
+    A(sdfc_host::batch_ensure_plan_slots(b, 1));
     A(dev_alloc(&b->d_fm_sub, ep * 12));
     A(dev_alloc(&b->d_Km_sub, ep * 144));
     A(dev_alloc(&b->d_Dm_sub, ep * 144));
@@ -895,8 +925,8 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     b->dev.words_per_env = std::max(words, 1);
     b->dev.tile_pair = b->d_tile_pair; b->dev.tile_word0 = b->d_tile_word0;
     b->dev.n_tiles = (int)tile_pair.size();
-    b->dev.splits = splits;
-    b->dev.mask = b->d_mask; b->dev.n_active = b->d_n_active; b->dev.partial = b->d_partial;
+    b->dev.mask = b->d_mask; b->dev.n_active = b->d_n_active; b->dev.tile_count = b->d_tile_count;
+    b->dev.plan[0] = b->plan_slot[0][0]; b->dev.plan[1] = b->plan_slot[0][1];
     b->dev.brick_stats = b->d_brick_stats;
     b->dev.brick_cap = kBrickSmemBytes;
     if (const char* cap = std::getenv("SDFC_BRICK_SMEM")) b->dev.brick_cap = std::max(0, std::min(kBrickSmemMax, std::atoi(cap)));
@@ -908,7 +938,12 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     if (!b) return SDFC_OK;
     cudaSetDevice(b->ctx->device);
     cudaFree(b->d_pairs); cudaFree(b->d_tile_pair); cudaFree(b->d_tile_word0); cudaFree(b->d_mask);
-    cudaFree(b->d_n_active); cudaFree(b->d_brick_stats); cudaFree(b->d_partial); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
+    for (int sl = 0; sl < sdfc_batch::kMaxPlanSlots; ++sl)
+        for (int m = 0; m < 2; ++m) {
+            const ForcePlanDev& P = b->plan_slot[sl][m];
+            cudaFree(P.items); cudaFree(P.pair_item0); cudaFree(P.hdr); cudaFree(P.partial);
+        }
+    cudaFree(b->d_n_active); cudaFree(b->d_tile_count); cudaFree(b->d_brick_stats); cudaFree(b->d_fm_sub); cudaFree(b->d_Km_sub); cudaFree(b->d_Dm_sub);
     cudaFree(b->d_E); cudaFree(b->d_fm); cudaFree(b->d_Km); cudaFree(b->d_Dm);
     cudaFree(b->d_skin_margin); cudaFree(b->d_skin_pose); cudaFree(b->d_skin_int); cudaFree(b->d_skin_stats);
     if (b->h_in) cudaFreeHost(b->h_in);

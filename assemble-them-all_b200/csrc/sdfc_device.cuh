@@ -1039,6 +1039,15 @@ struct PairPoseNF {
     double R21[9];                       // R2^T R1
 };
 
+// Constant columns factored out: writing column j of Km_sub as Y X_j + Z_j with
+//   Y = [ -kn u1 g^T - c [[xi1]; I] R12 P ;  kn u2 g^T + c [ [x] P - [e] ; P ] ]     (12 x 3, per contact)
+// the columns 3..5 (X_j = R21 e_m) and 9..11 (X_j = -e_m) of the SUM over contacts are (sum Y) R21 and -(sum Y):
+// only the 6 pose-dependent columns 0..2, 6..8 are formed per contact, plus the three columns of Y (the general
+// column with X = e_m and no explicit part) and fm. Emission (sink.emit(slot, v12)): slot 9 = fm, 6..8 = the
+// columns of Y, 0..2 = Km columns 0..2, 3..5 = Km columns 6..8; the sink's owner rebuilds the 13 columns from
+// the 10 summed slots (nf_slots_to_columns).
+constexpr int kNfSlots = 10;
+
 template <bool F32, class ColSink>
 __device__ __forceinline__ void contact_eval_nf(const GridDev& G, const PairPoseNF& P, double kn, const double xi1[3],
                                                 ColSink& sink) {
@@ -1064,45 +1073,44 @@ __device__ __forceinline__ void contact_eval_nf(const GridDev& G, const PairPose
 #pragma unroll
             for (int k = 0; k < 3; ++k) Pm[r * 3 + k] = (H[r * 3 + k] - e[r] * eH[k]) * rgn;
     }
-    // a1 = R12 e = R21^T e ; u1, u2
-    double a1[3], u1[6], u2[6];
+    // a1 = R12 e = R21^T e ; u1 = [xi1 x a1 ; a1], u2 = [x x e ; e]
+    double a1[3], u1[3], u2[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) a1[r] = P.R21[r] * e[0] + P.R21[3 + r] * e[1] + P.R21[6 + r] * e[2];
     cross3(xi1, a1, u1); cross3(x, e, u2);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { u1[3 + a] = a1[a]; u2[3 + a] = e[a]; }
     {
         double f12[12];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { f12[i] = -c * u1[i]; f12[6 + i] = c * u2[i]; }
-        sink.emit(12, f12);
+        for (int i = 0; i < 3; ++i) { f12[i] = -c * u1[i]; f12[3 + i] = -c * a1[i]; f12[6 + i] = c * u2[i]; f12[9 + i] = c * e[i]; }
+        sink.emit(9, f12);
     }
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        // column j of X and of the explicit part of da1
+    // The 9 columns in a ROLLED loop: the body (column algebra + warp reduction) is a few hundred instructions
+    // that stay in the instruction cache; the unrolled form was ~70 KB of straight-line code per round and the
+    // kernel stalled on instruction fetch a third of the time (ncu stall_no_inst, profiles/r2_force_kernel.md).
+#pragma unroll 1
+    for (int jj = 0; jj < 9; ++jj) {
+        const int t = jj / 3, m = jj - 3 * t;
+        const double uj[3] = {m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0};
+        // column of X and of the explicit part of da1
         double X[3], ex[3] = {0.0, 0.0, 0.0};
-        if (j < 3) {          // -R21 [xi1]_col j ;  extra = [a1]_col j
-            double sk[3], sa[3], uj[3] = {0.0, 0.0, 0.0};
-            uj[j] = 1.0;
-            cross3(xi1, uj, sk);   // [xi1] e_j
-            cross3(a1, uj, sa);    // [a1] e_j
+        int slot;
+        if (t == 0) {          // column m of Y: X = e_m
+            X[0] = uj[0]; X[1] = uj[1]; X[2] = uj[2];
+            slot = 6 + m;
+        } else if (t == 1) {   // Km column m: X = -R21 [xi1] e_m ; extra = [a1] e_m
+            double sk[3];
+            cross3(xi1, uj, sk);
+            cross3(a1, uj, ex);
 #pragma unroll
             for (int r = 0; r < 3; ++r) X[r] = -(P.R21[r * 3] * sk[0] + P.R21[r * 3 + 1] * sk[1] + P.R21[r * 3 + 2] * sk[2]);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) ex[r] = sa[r];
-        } else if (j < 6) {   // R21 col (j-3)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) X[r] = P.R21[r * 3 + (j - 3)];
-        } else if (j < 9) {   // [x]_col ; extra = -R12 [e]_col
-            double uj[3] = {0.0, 0.0, 0.0}, se[3];
-            uj[j - 6] = 1.0;
+            slot = m;
+        } else {               // Km column 6 + m: X = [x] e_m ; extra = -R12 [e] e_m
+            double se[3];
             cross3(x, uj, X);
             cross3(e, uj, se);
 #pragma unroll
             for (int r = 0; r < 3; ++r) ex[r] = -(P.R21[r] * se[0] + P.R21[3 + r] * se[1] + P.R21[6 + r] * se[2]);
-        } else {              // -I col
-#pragma unroll
-            for (int r = 0; r < 3; ++r) X[r] = (r == j - 9) ? -1.0 : 0.0;
+            slot = 3 + m;
         }
         const double gX = dot3(g, X);
         double PX[3], da1[3], t1[3], t2[3], t3[3];
@@ -1118,122 +1126,24 @@ __device__ __forceinline__ void contact_eval_nf(const GridDev& G, const PairPose
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             col[r] = -kg * u1[r] - c * t1[r];
-            col[3 + r] = -kg * u1[3 + r] - c * da1[r];
+            col[3 + r] = -kg * a1[r] - c * da1[r];
             col[6 + r] = kg * u2[r] + c * (t2[r] - t3[r]);
-            col[9 + r] = kg * u2[3 + r] + c * PX[r];
+            col[9 + r] = kg * e[r] + c * PX[r];
         }
-        sink.emit(j, col);
+        sink.emit(slot, col);
     }
 }
 
-// contact_eval_nf with the constant columns of X factored out. Writing column j of Km_sub as Y X_j + Z_j with
-//   Y = [ -kn u1 g^T - c [[xi1]; I] R12 P ;  kn u2 g^T + c [ [x] P - [e] ; P ] ]     (12 x 3, per contact)
-// the columns 3..5 (X_j = R21 e_m) and 9..11 (X_j = -e_m) of the SUM over contacts are (sum Y) R21 and -(sum Y):
-// only the 6 pose-dependent columns 0..2, 6..8 are formed per contact, plus the three columns of Y and fm:
-// 10 warp reductions of 12 values instead of 13, and half of the per-column algebra. Emission order
-// (sink.emit(slot, v12)): 9 = fm, 6..8 = Y columns, 0..2 = Km columns 0..2, 3..5 = Km columns 6..8.
-constexpr int kNf2Slots = 10;
-
-template <bool F32, class ColSink>
-__device__ __forceinline__ void contact_eval_nf2(const GridDev& G, const PairPoseNF& P, double kn, const double xi1[3],
-                                                 ColSink& sink) {
-    double xw1[3], x[3];
-    to_world(P.R1, P.p1, xi1[0], xi1[1], xi1[2], xw1);
-    to_local(P.R2, P.p2, xw1, x);
-    double d, g[3], H[9];
-    sdf_stencil<F32>(G, x, d, g, H);
-    const double gn = sqrt(dot3(g, g));
-    const double rgn = 1.0 / gn;
-    double e[3];
+// Entry `row` of the 13 columns (12 of Km_sub, then fm) from entry `row` of the 10 summed slots.
+__device__ __forceinline__ void nf_slots_to_columns(const double a[kNfSlots], const double* R21, double out[13]) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) e[a] = g[a] / gn;
-    const double c = kn * d;
-    double Pm[9];   // P = (H - e (e^T H)) / |g|
-    {
-        double eH[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) eH[k] = e[0] * H[k] + e[1] * H[3 + k] + e[2] * H[6 + k];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) Pm[r * 3 + k] = (H[r * 3 + k] - e[r] * eH[k]) * rgn;
+    for (int m = 0; m < 3; ++m) {
+        out[m] = a[m];
+        out[6 + m] = a[3 + m];
+        out[3 + m] = a[6] * R21[m] + a[7] * R21[3 + m] + a[8] * R21[6 + m];
+        out[9 + m] = -a[6 + m];
     }
-    double a1[3], u1[6], u2[6];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) a1[r] = P.R21[r] * e[0] + P.R21[3 + r] * e[1] + P.R21[6 + r] * e[2];
-    cross3(xi1, a1, u1); cross3(x, e, u2);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { u1[3 + a] = a1[a]; u2[3 + a] = e[a]; }
-    {
-        double f12[12];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { f12[i] = -c * u1[i]; f12[6 + i] = c * u2[i]; }
-        sink.emit(9, f12);
-    }
-    // the three columns of Y
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double pk[3], rp[3], t1[3], t2[3], t3[3], uk[3] = {0.0, 0.0, 0.0};
-        uk[k] = 1.0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) pk[r] = Pm[r * 3 + k];                                                     // P e_k
-#pragma unroll
-        for (int r = 0; r < 3; ++r) rp[r] = P.R21[r] * pk[0] + P.R21[3 + r] * pk[1] + P.R21[6 + r] * pk[2];    // R12 P e_k
-        cross3(xi1, rp, t1);
-        cross3(x, pk, t2);
-        cross3(e, uk, t3);
-        const double kg = kn * g[k];
-        double col[12];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            col[r] = -kg * u1[r] - c * t1[r];
-            col[3 + r] = -kg * u1[3 + r] - c * rp[r];
-            col[6 + r] = kg * u2[r] + c * (t2[r] - t3[r]);
-            col[9 + r] = kg * u2[3 + r] + c * pk[r];
-        }
-        sink.emit(6 + k, col);
-    }
-    // the pose-dependent columns 0..2 (X = -R21 [xi1] e_j) and 6..8 (X = [x] e_j), as contact_eval_nf forms them
-#pragma unroll
-    for (int jj = 0; jj < 6; ++jj) {
-        const int m = jj % 3;
-        double X[3], ex[3], uj[3] = {0.0, 0.0, 0.0};
-        uj[m] = 1.0;
-        if (jj < 3) {
-            double sk[3], sa[3];
-            cross3(xi1, uj, sk);
-            cross3(a1, uj, sa);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) X[r] = -(P.R21[r * 3] * sk[0] + P.R21[r * 3 + 1] * sk[1] + P.R21[r * 3 + 2] * sk[2]);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) ex[r] = sa[r];
-        } else {
-            double se[3];
-            cross3(x, uj, X);
-            cross3(e, uj, se);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) ex[r] = -(P.R21[r] * se[0] + P.R21[3 + r] * se[1] + P.R21[6 + r] * se[2]);
-        }
-        const double gX = dot3(g, X);
-        double PX[3], da1[3], t1[3], t2[3], t3[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) PX[r] = Pm[r * 3] * X[0] + Pm[r * 3 + 1] * X[1] + Pm[r * 3 + 2] * X[2];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) da1[r] = P.R21[r] * PX[0] + P.R21[3 + r] * PX[1] + P.R21[6 + r] * PX[2] + ex[r];
-        cross3(xi1, da1, t1);
-        cross3(x, PX, t2);
-        cross3(e, X, t3);
-        double col[12];
-        const double kg = kn * gX;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            col[r] = -kg * u1[r] - c * t1[r];
-            col[3 + r] = -kg * u1[3 + r] - c * da1[r];
-            col[6 + r] = kg * u2[r] + c * (t2[r] - t3[r]);
-            col[9 + r] = kg * u2[3 + r] + c * PX[r];
-        }
-        sink.emit(jj, col);
-    }
+    out[12] = a[9];
 }
 
 }  // namespace sdfc

@@ -3,6 +3,8 @@
 // (sdfc_force_inst.cu is compiled 8 times with -DSDFC_FORCE_VARIANT=0..7).
 #pragma once
 #include "sdfc_kernels.cuh"
+#include <algorithm>
+#include <type_traits>
 
 namespace sdfc {
 
@@ -49,28 +51,56 @@ __host__ __device__ inline int tr_index(int lane, int j) {
     return rel;
 }
 
-// Fixed-order sum of the split partials of one (environment, pair) into its blocks fm_sub[12], Km_sub[144],
-// Dm_sub[144] (column-major), undoing the slot layout of the warp transpose-reduce. `tid` of `nthreads`
-// cooperating threads (k_reduce_splits: a CTA; the stepper's round kernel: the environment's warp).
-__device__ __forceinline__ void reduce_splits_one(const BatchDev& B, int env, int pair, int deriv, int dm, int tid, int nthreads,
-                                                  double* fm_sub, double* Km_sub, double* Dm_sub) {
+// Fixed-order sum of the item partials of one (environment, pair) into its blocks fm_sub[12], Km_sub[144],
+// Dm_sub[144] (column-major), undoing the slot layout of the warp transpose-reduce. The pair's items are
+// consecutive in its plan (ForcePlanDev) and are summed in item order, so the result does not depend on which
+// warp evaluated which item. `tid` of `nthreads` cooperating threads (k_reduce_items: a CTA; the stepper's
+// round kernel: the environment's warp).
+__device__ __forceinline__ void reduce_items_one(const BatchDev& B, int env, int pair, int deriv, int dm, int tid, int nthreads,
+                                                 double* fm_sub, double* Km_sub, double* Dm_sub) {
     const size_t ep = (size_t)env * B.n_pairs + pair;
-    const bool empty = B.n_active[ep] == 0;
-    const bool nf = deriv && !dm;  // layout of contact_eval_nf: 12 Km columns + fm
-    const int npart = nf ? kPartialNF : (deriv ? (dm ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
-    const double* part = B.partial + ep * B.splits * kPartialDerivDM;  // fixed slot stride, see k_force
+    const ForcePlanDev& P = B.plan[deriv ? 1 : 0];
+    const int n_act = B.n_active[ep];
+    const int per_item = 32 * P.hdr[1];
+    const int n_items = (n_act + per_item - 1) / per_item;
+    const bool nf = deriv && !dm;  // layout of the planner fast path: 13 columns x 2 halves x 12 entries
+    const int npart = nf ? kNfCols * 12 : (deriv ? kPartialDerivDM : kPartialValue);
+    const double* part = n_items ? P.partial + (size_t)P.pair_item0[ep] * P.stride : nullptr;
     for (int slot = tid; slot < npart; slot += nthreads) {
-        double s = 0.0;
-        if (!empty)
-            for (int sp = 0; sp < B.splits; ++sp) s += part[(size_t)sp * kPartialDerivDM + slot];
-        const int lane = slot & 31;
         if (nf) {
-            const int j = slot >> 5, e = tr_index<12>(lane, 0);
-            if (e >= 0) {
-                if (j < 12) Km_sub[ep * 144 + e + 12 * j] = s;
-                else fm_sub[ep * 12 + e] = s;
+            // output (column j, entry e) = sum over the items, in item order, of its two half-sums
+            const int j = slot / 12, e = slot - 12 * j;
+            const double* src = part + j * kNfLanes + e;
+            double s = 0.0;
+            int it = 0;
+            for (; it + 4 <= n_items; it += 4) {   // eight loads in flight, additions strictly in order
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[2 * u] = __ldcg(src + (size_t)(it + u) * P.stride);
+                    a[2 * u + 1] = __ldcg(src + (size_t)(it + u) * P.stride + 12);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += a[u];
             }
-        } else if (!deriv) {
+            for (; it < n_items; ++it) { s += __ldcg(src + (size_t)it * P.stride); s += __ldcg(src + (size_t)it * P.stride + 12); }
+            if (j < 12) Km_sub[ep * 144 + e + 12 * j] = s;
+            else fm_sub[ep * 12 + e] = s;
+            continue;
+        }
+        // item order, eight loads in flight: the additions stay strictly sequential (same bits as a plain loop)
+        double s = 0.0;
+        int it = 0;
+        for (; it + 8 <= n_items; it += 8) {
+            double a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = __ldcg(part + (size_t)(it + u) * P.stride + slot);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += a[u];
+        }
+        for (; it < n_items; ++it) s += __ldcg(part + (size_t)it * P.stride + slot);
+        const int lane = slot & 31;
+        if (!deriv) {
             const int e = tr_index<12>(lane, slot >> 5);
             if (e >= 0) fm_sub[ep * 12 + e] = s;
         } else if (slot < kPartialDeriv) {
@@ -148,26 +178,48 @@ struct WarpSink {
     }
 };
 
-// Sink of contact_eval_nf: one 12-value column at a time.
+// Sink of contact_eval_nf: one 12-value column at a time, summed over the warp's 32 contacts through shared
+// memory. Every lane stores its column into a 12 x 33 tile; lanes 0..23 then each add 16 contacts of ONE entry
+// (entry r = lane % 12 over the contacts of half h = lane / 12, two chains of 8 in a fixed order) and keep the
+// running sum of the item in the warp's acc block. 12 STS + 16 LDS + 16 DADD per column against ~120
+// instructions (SHFL / FSEL / MOV / DADD) of the register transpose-reduce; the tiles are double-buffered, so
+// one __syncwarp per column orders everything (a tile is rewritten two emits later, i.e. after the next sync).
+constexpr int kNfTile = 12 * 33;
 struct ColSink {
-    double acc[kNfCols];
-    unsigned lane;
-    bool valid;
-    __device__ __forceinline__ void init(unsigned l) {
+    double* tile;        // the warp's two transpose tiles
+    double* acc;         // this lane's slot-0 accumulator: acc[slot * kNfLanes]
+    const double* rd;    // first element this lane reads of tile 0
+    int lane, rot, buf;
+    __device__ __forceinline__ void init(double* warp_tiles, double* warp_acc, int l) {
         lane = l;
-        valid = false;
+        buf = 0;
+        tile = warp_tiles;
+        const int r = l % 12, h = (l / 12) & 1;
+        rd = warp_tiles + r * 33 + 16 * h;
+        rot = 12 * h;    // the second half reads its 16 contacts rotated by 12: no bank shared with the first
+        acc = warp_acc + l;
+        if (l < kNfLanes)
 #pragma unroll
-        for (int j = 0; j < kNfCols; ++j) acc[j] = 0.0;
+            for (int j = 0; j < kNfSlots; ++j) acc[j * kNfLanes] = 0.0;
     }
-    __device__ __forceinline__ void emit(int j, const double* c12) {
-        // lanes beyond the last contact evaluate a duplicate with kn = 0 (force_rounds_nf): every
-        // output of contact_eval_nf is proportional to kn, so they contribute exact zeros without
-        // 24 selects per column here
-        double v[12];
+    __device__ __forceinline__ void emit(int slot, const double* c12) {
+        // lanes beyond the last contact evaluate a duplicate with kn = 0 (force_round): every output of
+        // contact_eval_nf is proportional to kn, so they contribute exact zeros
+        buf ^= kNfTile;   // the other tile
+        double* t = tile + buf + lane;
 #pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = c12[i];
-        TransposeReduce<12, 16>::run(v, lane);
-        acc[j] += v[0];
+        for (int i = 0; i < 12; ++i) t[i * 33] = c12[i];
+        __syncwarp();
+        if (lane < kNfLanes) {
+            const double* b = rd + buf;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s0 += b[(i + rot) & 15];
+                s1 += b[(i + 8 + rot) & 15];
+            }
+            acc[slot * kNfLanes] += s0 + s1;
+        }
     }
 };
 
@@ -181,56 +233,149 @@ __device__ __forceinline__ void stage_pose(const double* E, int n_bodies, int en
 }
 
 // --------------------------------------------------------------------------
-// force
+// force: a persistent kernel over the work list of the launch
 // --------------------------------------------------------------------------
-struct ForceShared {
+// The active contacts of an evaluation are spread very unevenly over the (environment, pair)s (none in most,
+// hundreds in some). k_force_plan (sdfc_kernels.cu) cuts them into ITEMS of G x 32 consecutive contacts of one
+// pair (mask order; G = 1 unless the list would overflow its capacity); the warps of this kernel take items
+// from a device-side counter until none is left, so every warp evaluates full 32-contact rounds whatever the
+// distribution is. An item's sums go to its own slot of the plan's partial buffer and the slots of a pair are
+// added in item order afterwards (reduce_items_one): the result is independent of the schedule.
+template <bool NF>
+struct ForceWarpShared {
     PairDev pd;
-    PairPose pose;
-    PairPoseNF nf;
-    int warp_tot[kNumWarps];
-    int ids[kForceThreads * 32];
+    typename std::conditional<NF, PairPoseNF, PairPose>::type pose;
+    double acc[NF ? kNfSlots * kNfLanes : 1];   // planner fast path: the running sums of the item (ColSink)
+    double tile[NF ? 2 * kNfTile : 1];          // ... and its transpose tiles
 };
 
-template <bool F32, bool DERIV, bool FRIC, bool DAMP, class Sink>
-__device__ __forceinline__ void force_rounds(const ForceShared& S, int total, Sink& sink) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = warp * 32; base < total; base += kForceThreads) {
-        const int c = base + lane;
-        sink.valid = c < total;
-        const int id = S.ids[sink.valid ? c : base];
-        const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
+// accumulators of one item -> its slot, then cleared
+template <bool DERIV, bool DM>
+__device__ __forceinline__ void flush_item(WarpSink<DERIV, DM>& sink, double* out, int lane) {
+    if constexpr (DERIV) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int j = 0; j < kOutK; ++j) { out[(b * kOutK + j) * 32 + lane] = sink.accK[b][j]; sink.accK[b][j] = 0.0; }
+        if constexpr (DM) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int j = 0; j < kOutD; ++j) { out[kPartialDeriv + (b * kOutD + j) * 32 + lane] = sink.accD[b][j]; sink.accD[b][j] = 0.0; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kOutF; ++j) { out[j * 32 + lane] = sink.accF[j]; sink.accF[j] = 0.0; }
+    }
+}
+// the 10 summed slots of the item -> the 13 columns of its partial (kPartialNF layout), lane = (half, entry)
+__device__ __forceinline__ void flush_item(ColSink& sink, const double* R21, double* out, int lane) {
+    if (lane < kNfLanes) {
+        double a[kNfSlots], col[kNfCols];
+#pragma unroll
+        for (int j = 0; j < kNfSlots; ++j) { a[j] = sink.acc[j * kNfLanes]; sink.acc[j * kNfLanes] = 0.0; }
+        nf_slots_to_columns(a, R21, col);
+#pragma unroll
+        for (int j = 0; j < kNfCols; ++j) out[j * kNfLanes + lane] = col[j];
+    }
+}
+
+// One round: contact `id` on this lane (`valid` = false: a duplicate that contributes zeros).
+template <bool F32, bool DERIV, bool FRIC, bool DAMP, bool NF, class Sink>
+__device__ __forceinline__ void force_round(const ForceWarpShared<NF>& S, int id, bool valid, Sink& sink) {
+    const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
+    if constexpr (NF) {
+        // lanes past the last contact evaluate a duplicate with kn = 0: every output is proportional to kn
+        contact_eval_nf<F32>(S.pd.grid, S.pose, valid ? S.pd.prm.kn : 0.0, xi1, sink);
+    } else {
+        sink.valid = valid;
         contact_eval<F32, DERIV, FRIC, DAMP>(S.pd.grid, S.pose, S.pd.prm, xi1, sink);
     }
 }
 
-// Sink of contact_eval_nf2: 10 reductions of 12 values per round (Km columns 0..2, 6..8, the three columns of Y, fm).
-struct Nf2Sink {
-    double acc[kNf2Slots];
-    unsigned lane;
-    __device__ __forceinline__ void init(unsigned l) {
-        lane = l;
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
 #pragma unroll
-        for (int j = 0; j < kNf2Slots; ++j) acc[j] = 0.0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
     }
-    __device__ __forceinline__ void emit(int j, const double* c12) {
-        // lanes beyond the last contact evaluate a duplicate with kn = 0: every output is proportional to kn
-        double v[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = c12[i];
-        TransposeReduce<12, 16>::run(v, lane);
-        acc[j] += v[0];
-    }
-};
+    return v;
+}
 
-template <bool F32>
-__device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total, Nf2Sink& sink) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = warp * 32; base < total; base += kForceThreads) {
-        const int c = base + lane;
-        const bool valid = c < total;
-        const int id = S.ids[valid ? c : base];
-        const double xi1[3] = {__ldg(S.pd.sx + id), __ldg(S.pd.sy + id), __ldg(S.pd.sz + id)};
-        contact_eval_nf2<F32>(S.pd.grid, S.nf, valid ? S.pd.prm.kn : 0.0, xi1, sink);
+// position of the n-th (0-based) set bit of w; w has more than n set bits
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const int c = __popc((w >> pos) & ((1u << s) - 1u));
+        if (n >= c) { n -= c; pos += s; }
+    }
+    return pos;
+}
+
+// The contacts of ranks [r0, r1) of the pair's mask row (set bits in word order), 32 at a time. The detection
+// tile that holds rank r0 comes from the per-tile contact counts (one load per lane and a warp scan); inside a
+// tile every lane finds ITS contact - rank c0 + lane - by a binary search over the scanned word counts
+// (shuffles) and a bit select: no serial bit loop, no shared-memory id list.
+template <bool F32, bool DERIV, bool FRIC, bool DAMP, bool NF, class Sink>
+__device__ __forceinline__ void force_item(const ForceWarpShared<NF>& S, const BatchDev& B, int env, int r0, int r1, int lane, Sink& sink) {
+    const uint32_t* __restrict__ row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
+    const int32_t* __restrict__ tcnt = B.tile_count + (size_t)env * B.n_tiles + S.pd.tile_offset;
+    const int nw = S.pd.n_words;
+    const int nt = (nw + kDetectTileWords - 1) / kDetectTileWords;
+    int t0 = 0, base = 0;
+    for (;;) {   // 32 tiles at a time (65 536 points)
+        const int c = (t0 + lane < nt) ? __ldg(tcnt + t0 + lane) : 0;
+        const int incl = warp_inclusive_scan(c, lane);
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (base + tot > r0) {
+            const int k = __popc(__ballot_sync(0xffffffffu, base + incl <= r0));   // tiles that end at or before r0
+            const int b = __shfl_sync(0xffffffffu, incl, max(k - 1, 0));
+            base += k ? b : 0;
+            t0 += k;
+            break;
+        }
+        base += tot;
+        t0 += 32;
+        if (t0 >= nt) return;   // counts and item table disagree: nothing to evaluate
+    }
+    int c0 = r0, id = 0;
+    for (int t = t0; t < nt; ++t) {
+        const int w = t * kDetectTileWords;
+        static_assert(kDetectTileWords == 64, "two words per lane and tile");
+        const uint32_t wa = (w + lane < nw) ? __ldg(row + w + lane) : 0u;
+        const uint32_t wb = (w + 32 + lane < nw) ? __ldg(row + w + 32 + lane) : 0u;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t word = half ? wb : wa;
+            const int cnt = __popc(word);
+            const int incl = warp_inclusive_scan(cnt, lane);
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int cb = base;   // rank of the first contact of these 32 words
+            base += tot;
+            if (base <= c0) continue;
+            for (;;) {
+                const int wend = min(c0 + 32, r1);
+                const int tgt = c0 + lane, rel = tgt - cb;
+                const bool here = tgt < wend && rel >= 0 && rel < tot;
+                const int relc = here ? rel : 0;
+                int src = 0;   // first lane whose inclusive count exceeds relc
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                    if (v <= relc) src += step;
+                }
+                const uint32_t ws = __shfl_sync(0xffffffffu, word, src);
+                const int es = __shfl_sync(0xffffffffu, incl - cnt, src);
+                if (here) id = (w + 32 * half + src) * 32 + nth_set_bit(ws, relc - es);
+                if (base < wend) break;   // the round continues in the next 32 words
+                const bool valid = tgt < wend;
+                const int id0 = __shfl_sync(0xffffffffu, id, 0);
+                force_round<F32, DERIV, FRIC, DAMP, NF>(S, valid ? id : id0, valid, sink);
+                c0 = wend;
+                if (c0 >= r1) return;
+            }
+        }
     }
 }
 
@@ -241,165 +386,100 @@ __device__ __forceinline__ void force_rounds_nf(const ForceShared& S, int total,
 #define SDFC_FORCE_NF_MIN_BLOCKS 3  // planner fast path: 168 registers, 12 warps / SM
 #endif
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
-__global__ void __launch_bounds__(kForceThreads, (DERIV && !ANYFRIC && !ANYDAMP) ? SDFC_FORCE_NF_MIN_BLOCKS
-                                                                                : SDFC_FORCE_MIN_BLOCKS) k_force(BatchDev B, const double* __restrict__ E,
-                                                         const double* __restrict__ phi) {
+constexpr int force_min_blocks() { return (DERIV && !ANYFRIC && !ANYDAMP) ? SDFC_FORCE_NF_MIN_BLOCKS : SDFC_FORCE_MIN_BLOCKS; }
+
+template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
+__global__ void __launch_bounds__(kForceThreads, force_min_blocks<DERIV, ANYFRIC, ANYDAMP>())
+    k_force(BatchDev B, const double* __restrict__ E, const double* __restrict__ phi) {
     constexpr bool DM = ANYFRIC || ANYDAMP;
     constexpr bool NF = DERIV && !DM;  // planner fast path (contact_eval_nf)
-    constexpr int NPART = NF ? kPartialNF : (DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ForceShared& S = *reinterpret_cast<ForceShared*>(smem_raw);
-    double* red = reinterpret_cast<double*>(smem_raw + sizeof(ForceShared));  // [kNumWarps][NPART]
+    __shared__ ForceWarpShared<NF> SW[kNumWarps];
+    const int lane = threadIdx.x & 31;
+    ForceWarpShared<NF>& S = SW[threadIdx.x >> 5];
+    const ForcePlanDev& P = B.plan[DERIV ? 1 : 0];
+    const int n_items = P.hdr[0];
+    const int total_warps = gridDim.x * kNumWarps;
 
-    const int env = blockIdx.y + B.env0;
-    if (B.env_mode != nullptr && __ldg(B.env_mode + env) != (DERIV ? 2 : 1)) return;  // CTA-uniform
-    const int pair = blockIdx.x / B.splits, split = blockIdx.x % B.splits;
-    if (__ldg(B.n_active + (size_t)env * B.n_pairs + pair) == 0) return;  // CTA-uniform
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const int* src = reinterpret_cast<const int*>(B.pairs + pair);
-        int* dst = reinterpret_cast<int*>(&S.pd);
-        for (int i = tid; i < (int)(sizeof(PairDev) / sizeof(int)); i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    // 36 threads stage the two poses and twists (any CTA width from one warp pair up)
-    if (tid < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, tid);
-    else if (tid < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, tid - 12);
-    else if (tid < 30) S.pose.phi1[tid - 24] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + tid - 24);
-    else if (tid < 36) S.pose.phi2[tid - 30] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + tid - 30);
-
-    if constexpr (NF) {
-        __syncthreads();
-        if (tid < 9) {
-            const int r = tid / 3, c = tid % 3;  // R21 = R2^T R1
-            S.nf.R21[tid] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
-        } else if (tid >= 9 && tid < 18) {
-            S.nf.R1[tid - 9] = S.pose.R1[tid - 9]; S.nf.R2[tid - 9] = S.pose.R2[tid - 9];
-        } else if (tid >= 18 && tid < 21) {
-            S.nf.p1[tid - 18] = S.pose.p1[tid - 18]; S.nf.p2[tid - 18] = S.pose.p2[tid - 18];
+    typename std::conditional<NF, ColSink, WarpSink<DERIV, DM>>::type sink;
+    if constexpr (NF) sink.init(S.tile, S.acc, lane); else sink.init(lane);
+    auto claim = [&]() {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(P.hdr + 2, 1);
+        return __shfl_sync(0xffffffffu, it, 0);
+    };
+    int cur_ep = -1;
+    int item = claim();
+    int4 tab = make_int4(0, 0, 0, 0);
+    if (item < n_items) tab = __ldg(P.items + item);
+    while (item < n_items) {
+        // the next item is claimed (and its table entry requested) before this one is evaluated, so that the
+        // atomic and the load are off the critical path - except near the end of the list, where holding an
+        // item in reserve would leave other warps idle
+        int next = -1;
+        int4 ntab = make_int4(0, 0, 0, 0);
+        if (item + total_warps < n_items) {
+            next = claim();
+            if (next < n_items) ntab = __ldg(P.items + next);
         }
-    }
-    WarpSink<DERIV && !NF, DM> sink;
-    Nf2Sink csink;
-    if constexpr (NF) csink.init(lane); else sink.init(lane);
-
-    const int wps = (S.pd.n_words + B.splits - 1) / B.splits;
-    const int w0 = split * wps, w1 = min(S.pd.n_words, w0 + wps);
-    const uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
-    const bool f32 = S.pd.grid.f32();
-    const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
-    const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
-
-    for (int tw = w0; tw < w1; tw += kForceThreads) {
-        __syncthreads();  // poses staged / previous tile's ids consumed
-        uint32_t word = (tw + tid < w1) ? __ldg(mask_row + tw + tid) : 0u;
-        const int cnt = __popc(word);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        const int ep = tab.x;
+        const int env = ep / B.n_pairs, pair = ep - env * B.n_pairs;
+        if (ep != cur_ep) {
+            cur_ep = ep;
+            __syncwarp();
+            {
+                const int* src = reinterpret_cast<const int*>(B.pairs + pair);
+                int* dst = reinterpret_cast<int*>(&S.pd);
+                for (int i = lane; i < (int)(sizeof(PairDev) / sizeof(int)); i += 32) dst[i] = __ldg(src + i);
+            }
+            __syncwarp();
+            if constexpr (NF) {
+                if (lane < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, lane);
+                else if (lane < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, lane - 12);
+                __syncwarp();
+                if (lane < 9) {
+                    const int r = lane / 3, c = lane % 3;  // R21 = R2^T R1
+                    S.pose.R21[lane] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
+                }
+            } else {
+                if (lane < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, lane);
+                else if (lane < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, lane - 12);
+                else if (lane < 30) S.pose.phi1[lane - 24] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + lane - 24);
+                if (lane < 6) S.pose.phi2[lane] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + lane);
+            }
+            __syncwarp();
         }
-        if (lane == 31) S.warp_tot[warp] = incl;
-        __syncthreads();
-        int off = incl - cnt, total = 0;
-#pragma unroll
-        for (int w = 0; w < kNumWarps; ++w) {
-            const int t = S.warp_tot[w];
-            if (w < warp) off += t;
-            total += t;
-        }
-        while (word) {
-            const int b = __ffs(word) - 1;
-            S.ids[off++] = (tw + tid) * 32 + b;
-            word &= word - 1;
-        }
-        __syncthreads();
-        if (total == 0) continue;
+        const int r0 = tab.y, r1 = tab.z;
+        const bool f32 = S.pd.grid.f32();
+        const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
+        const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
+        // warp-uniform variant dispatch (template flags prune what cannot occur)
         if constexpr (NF) {
-            if (f32) force_rounds_nf<true>(S, total, csink); else force_rounds_nf<false>(S, total, csink);
-            continue;
-        }
-        // CTA-uniform variant dispatch (template flags prune what cannot occur)
-        if (f32) {
-            if (fric) { if (damp) force_rounds<true, DERIV, ANYFRIC, ANYDAMP>(S, total, sink); else force_rounds<true, DERIV, ANYFRIC, false>(S, total, sink); }
-            else      { if (damp) force_rounds<true, DERIV, false, ANYDAMP>(S, total, sink);  else force_rounds<true, DERIV, false, false>(S, total, sink); }
+            if (f32) force_item<true, true, false, false, true>(S, B, env, r0, r1, lane, sink);
+            else force_item<false, true, false, false, true>(S, B, env, r0, r1, lane, sink);
+        } else if (f32) {
+            if (fric) { if (damp) force_item<true, DERIV, ANYFRIC, ANYDAMP, false>(S, B, env, r0, r1, lane, sink); else force_item<true, DERIV, ANYFRIC, false, false>(S, B, env, r0, r1, lane, sink); }
+            else      { if (damp) force_item<true, DERIV, false, ANYDAMP, false>(S, B, env, r0, r1, lane, sink);  else force_item<true, DERIV, false, false, false>(S, B, env, r0, r1, lane, sink); }
         } else {
-            if (fric) { if (damp) force_rounds<false, DERIV, ANYFRIC, ANYDAMP>(S, total, sink); else force_rounds<false, DERIV, ANYFRIC, false>(S, total, sink); }
-            else      { if (damp) force_rounds<false, DERIV, false, ANYDAMP>(S, total, sink);  else force_rounds<false, DERIV, false, false>(S, total, sink); }
+            if (fric) { if (damp) force_item<false, DERIV, ANYFRIC, ANYDAMP, false>(S, B, env, r0, r1, lane, sink); else force_item<false, DERIV, ANYFRIC, false, false>(S, B, env, r0, r1, lane, sink); }
+            else      { if (damp) force_item<false, DERIV, false, ANYDAMP, false>(S, B, env, r0, r1, lane, sink);  else force_item<false, DERIV, false, false, false>(S, B, env, r0, r1, lane, sink); }
         }
-    }
-
-    // cross-warp combine in fixed order
-    double* mine = red + (size_t)warp * NPART;
-    if constexpr (NF) {
-#pragma unroll
-        for (int j = 0; j < kNf2Slots; ++j) mine[j * 32 + lane] = csink.acc[j];
-    } else if (DERIV) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int j = 0; j < kOutK; ++j) mine[(b * kOutK + j) * 32 + lane] = sink.accK[DERIV ? b : 0][j];
-        if (DM) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int j = 0; j < kOutD; ++j)
-                    mine[kPartialDeriv + (b * kOutD + j) * 32 + lane] = sink.accD[(DERIV && DM) ? b : 0][j];
+        if constexpr (NF) flush_item(sink, S.pose.R21, P.partial + (size_t)item * P.stride, lane);
+        else flush_item(sink, P.partial + (size_t)item * P.stride, lane);
+        if (next < 0) {
+            next = claim();
+            if (next < n_items) ntab = __ldg(P.items + next);
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kOutF; ++j) mine[j * 32 + lane] = sink.accF[j];
-    }
-    __syncthreads();
-    // fixed slot stride (the largest layout): value-only and derivative environments share the
-    // buffer within one evaluation round of the stepper, so the stride must not depend on the variant
-    double* out = B.partial + (((size_t)env * B.n_pairs + pair) * B.splits + split) * kPartialDerivDM;
-    if constexpr (NF) {
-        // 10 reduced slots -> the 13-column layout of the partials: columns 3..5 = (sum Y) R21, 9..11 = -(sum Y)
-        if (tid < 32) {
-            double a[kNf2Slots];
-#pragma unroll
-            for (int j = 0; j < kNf2Slots; ++j) {
-                double s = red[j * 32 + tid];
-#pragma unroll
-                for (int w = 1; w < kNumWarps; ++w) s += red[(size_t)w * NPART + j * 32 + tid];
-                a[j] = s;
-            }
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                out[m * 32 + tid] = a[m];
-                out[(6 + m) * 32 + tid] = a[3 + m];
-                out[(3 + m) * 32 + tid] = a[6] * S.nf.R21[m] + a[7] * S.nf.R21[3 + m] + a[8] * S.nf.R21[6 + m];
-                out[(9 + m) * 32 + tid] = -a[6 + m];
-            }
-            out[12 * 32 + tid] = a[9];
-        }
-        return;
-    }
-    for (int i = tid; i < NPART; i += kForceThreads) {
-        double s = red[i];
-#pragma unroll
-        for (int w = 1; w < kNumWarps; ++w) s += red[(size_t)w * NPART + i];
-        out[i] = s;
+        item = next;
+        tab = ntab;
     }
 }
 
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
 void launch_force_t(const BatchDev& B, const double* E, const double* phi, cudaStream_t stream) {
-    constexpr bool DM = ANYFRIC || ANYDAMP;
-    {
-    constexpr int NPART = (DERIV && !DM) ? kPartialNF : (DERIV ? (DM ? kPartialDerivDM : kPartialDeriv) : kPartialValue);
-    const size_t smem = sizeof(ForceShared) + sizeof(double) * kNumWarps * NPART;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_force<DERIV, ANYFRIC, ANYDAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    dim3 grid(B.n_pairs * B.splits, B.env_count);
-    k_force<DERIV, ANYFRIC, ANYDAMP><<<grid, kForceThreads, smem, stream>>>(B, E, phi);
-    }
+    // persistent: as many CTAs as stay resident, never more than the work list can feed
+    const int resident = device_sm_count() * force_min_blocks<DERIV, ANYFRIC, ANYDAMP>();
+    const int useful = (B.plan[DERIV ? 1 : 0].cap + kNumWarps - 1) / kNumWarps;
+    k_force<DERIV, ANYFRIC, ANYDAMP><<<std::max(1, std::min(resident, useful)), kForceThreads, 0, stream>>>(B, E, phi);
 }
-
 
 }  // namespace sdfc

@@ -118,7 +118,13 @@ struct sdfc_batch {
     sdfc::BatchDev dev{};
     sdfc::PairDev* d_pairs = nullptr;
     int* d_tile_pair = nullptr; int* d_tile_word0 = nullptr;
-    uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; double* d_partial = nullptr;
+    uint32_t* d_mask = nullptr; int32_t* d_n_active = nullptr; int32_t* d_tile_count = nullptr;
+    // work lists of the force kernels (sdfc::ForcePlanDev): slot 0 serves every evaluation on the context's stream;
+    // the stepper takes one more per extra lane (lanes run concurrently on their own streams)
+    static constexpr int kMaxPlanSlots = 4;
+    sdfc::ForcePlanDev plan_slot[kMaxPlanSlots][2] = {};
+    int n_plan_slots = 0;
+    int plan_cap = 0;
     double* d_fm_sub = nullptr; double* d_Km_sub = nullptr; double* d_Dm_sub = nullptr;
     bool any_fric = false, any_damp = false;
     unsigned long long* d_brick_stats = nullptr;
@@ -152,7 +158,9 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
 // counters and run the temporal-coherence bookkeeping, and sums the split partials itself afterwards.
 // ev: 4 events. Capturable into a CUDA graph.
 sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* phi_dev, const int* env_mode_dev, int env0,
-                              int env_count, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev);
+                              int env_count, int plan_slot, cudaStream_t s0, cudaStream_t s1, cudaStream_t s2, cudaEvent_t* ev);
+// Work-list buffers for `n` concurrent evaluations of the batch (stepper lanes); slot 0 exists from creation.
+sdfc_status batch_ensure_plan_slots(sdfc_batch* b, int n);
 // Uploads the pair table if parameters changed (batch_run does it on every call).
 sdfc_status batch_prepare(sdfc_batch* b);
 // Allocates the skin state of a batch and switches the culling on (idempotent).

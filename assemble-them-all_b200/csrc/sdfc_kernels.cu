@@ -3,11 +3,13 @@
 //   k_detect_mask   LOOP C (collision_detection_general_SDF, CollisionDetection.cpp:124-147)
 //                   for E environments x P pairs: one 1-bit/pt active mask word per
 //                   warp-load of 32 points + an integer contact count per (env, pair).
-//   k_force         LOOP D (ForceGeneralSDFContact.cpp:147-447): compacts the mask in
-//                   shared memory, evaluates each active contact on one lane, reduces
-//                   the 12 / 156 / 300 outputs across the warp with a register
-//                   transpose-reduce, then across warps in a fixed order.
-//   k_reduce_splits / k_scatter_system   fixed-order sums -> per-pair blocks and the
+//   k_force_plan    cuts the active contacts of all (env, pair)s into items of 32 G contacts
+//                   (the work list of the force kernel, ForcePlanDev).
+//   k_force         LOOP D (ForceGeneralSDFContact.cpp:147-447): persistent; a warp takes an
+//                   item, picks its contacts out of the mask row, evaluates one contact per
+//                   lane and reduces the 12 / 156 / 300 outputs across the warp with a register
+//                   transpose-reduce; one partial per item.
+//   k_reduce_items / k_scatter_system   fixed-order sums -> per-pair blocks and the
 //                   per-environment system arrays (the += of .cpp:60-61,88-99).
 //   k_query_points  per-point d / cell / active in original order (parity + sweep entry).
 //   k_sdf_distance  raw trilinear sampling (SDFMesh::distance, Mesh.cpp:143-198).
@@ -277,7 +279,10 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     if (pd.grid.f32()) { GlobalSampler<true> smp; detect_tile<true, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk, smp); }
     else { GlobalSampler<false> smp; detect_tile<false, SKIN>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk, smp); }
     __syncthreads();
-    if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+    if (threadIdx.x == 0) {
+        B.tile_count[(size_t)env * B.n_tiles + tile] = s_count;   // the force kernel finds an item's contacts tile by tile
+        if (s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+    }
 }
 
 // --------------------------------------------------------------------------
@@ -464,7 +469,10 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
         detect_tile<false, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+    if (threadIdx.x == 0) {
+        B.tile_count[(size_t)env * B.n_tiles + tile] = s_count;   // the force kernel finds an item's contacts tile by tile
+        if (s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+    }
 }
 
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream, bool reset_counts) {
@@ -485,6 +493,99 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
     else k_detect_mask<false><<<grid, kDetectThreads, 0, stream>>>(B, E);
 }
 
+// --------------------------------------------------------------------------
+// work list of the force kernels
+// --------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+
+// One CTA per list (blockIdx.x = 0: value-only, 1: derivative when the launch carries per-environment modes).
+// Pass 1: rounds (32-contact groups) and pairs with contacts -> G, the smallest power-of-two multiple of g_min
+// for which the list fits its capacity (items <= rounds / G + pairs). Pass 2: exclusive scan of the items per
+// pair in (env, pair) order -> first item of every pair, then the item table, filled by the whole CTA.
+__global__ void __launch_bounds__(kPlanThreads) k_force_plan(BatchDev B, int deriv_sel) {
+    __shared__ int s_warp[32];
+    __shared__ int s_off[kPlanThreads + 1];
+    __shared__ int s_bcast[2];
+    const int sel = (B.env_mode != nullptr) ? (int)blockIdx.x : deriv_sel;
+    const ForcePlanDev P = B.plan[sel];
+    const int want = sel ? 2 : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ep0 = B.env0 * B.n_pairs, n_ep = B.env_count * B.n_pairs;
+    auto contacts_of = [&](int i) -> int {
+        if (i >= n_ep) return 0;
+        if (B.env_mode != nullptr && __ldg(B.env_mode + B.env0 + i / B.n_pairs) != want) return 0;
+        return B.n_active[ep0 + i];
+    };
+    // ---- pass 1
+    int rounds = 0, pairs = 0;
+    for (int i = tid; i < n_ep; i += kPlanThreads) {
+        const int n = contacts_of(i);
+        rounds += (n + 31) >> 5;
+        pairs += n > 0;
+    }
+    rounds = __reduce_add_sync(0xffffffffu, rounds);
+    pairs = __reduce_add_sync(0xffffffffu, pairs);
+    if (lane == 0) { s_warp[warp] = rounds; s_off[warp] = pairs; }
+    __syncthreads();
+    if (tid == 0) {
+        long long R = 0; int Np = 0;
+        for (int w = 0; w < kPlanThreads / 32; ++w) { R += s_warp[w]; Np += s_off[w]; }
+        int G = P.g_min;
+        while ((R + G - 1) / G + Np > P.cap) G *= 2;
+        s_bcast[0] = G;
+    }
+    __syncthreads();
+    const int G = s_bcast[0];
+    // ---- pass 2
+    int run = 0;
+    for (int i0 = 0; i0 < n_ep; i0 += kPlanThreads) {
+        const int i = i0 + tid;
+        const int n = contacts_of(i);
+        const int items = (((n + 31) >> 5) + G - 1) / G;
+        int incl = items;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();   // s_warp / s_off of the previous chunk consumed
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int off = incl - items;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        s_off[tid] = off;
+        if (tid == kPlanThreads - 1) s_off[kPlanThreads] = off + items;
+        if (items > 0) P.pair_item0[ep0 + i] = run + off;
+        __syncthreads();
+        const int chunk_items = s_off[kPlanThreads];
+        for (int t = tid; t < chunk_items; t += kPlanThreads) {
+            int lo = 0, hi = kPlanThreads;   // last entry with s_off[entry] <= t
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= t) lo = mid; else hi = mid;
+            }
+            const int k = t - s_off[lo], n_act = B.n_active[ep0 + i0 + lo];
+            P.items[run + t] = make_int4(ep0 + i0 + lo, k * 32 * G, min(n_act, (k + 1) * 32 * G), 0);
+        }
+        run += chunk_items;
+    }
+    if (tid == 0) { P.hdr[0] = run; P.hdr[1] = G; P.hdr[2] = 0; }
+}
+
+void launch_force_plan(const BatchDev& B, bool deriv, cudaStream_t stream) {
+    k_force_plan<<<B.env_mode != nullptr ? 2 : 1, kPlanThreads, 0, stream>>>(B, deriv ? 1 : 0);
+}
+
+int device_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
                   cudaStream_t stream) {
     if (deriv) {
@@ -497,10 +598,10 @@ void launch_force(const BatchDev& B, const double* E, const double* phi, bool de
 }
 
 // --------------------------------------------------------------------------
-// finalize: split partials -> per-pair blocks -> system arrays
+// finalize: item partials -> per-pair blocks -> system arrays
 // --------------------------------------------------------------------------
 // Per-pair block layout (natural): fm_sub[12], Km_sub[144] col-major, Dm_sub[144] col-major.
-__global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restrict__ fm_sub, double* __restrict__ Km_sub,
+__global__ void k_reduce_items(BatchDev B, int deriv, int dm, double* __restrict__ fm_sub, double* __restrict__ Km_sub,
                                 double* __restrict__ Dm_sub) {
     const int pair = blockIdx.x, env = blockIdx.y + B.env0;
     if (B.env_mode != nullptr) {
@@ -508,7 +609,7 @@ __global__ void k_reduce_splits(BatchDev B, int deriv, int dm, double* __restric
         if (m == 0) return;
         deriv = (m == 2) ? 1 : 0;
     }
-    reduce_splits_one(B, env, pair, deriv, dm, threadIdx.x, blockDim.x, fm_sub, Km_sub, Dm_sub);
+    reduce_items_one(B, env, pair, deriv, dm, threadIdx.x, blockDim.x, fm_sub, Km_sub, Dm_sub);
 }
 
 // Gather form of the reference's scatter (.cpp:60-61,88-99): one thread per system
@@ -553,7 +654,7 @@ __global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict
 void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
                            cudaStream_t stream) {
     dim3 grid(B.n_pairs, B.env_count);
-    k_reduce_splits<<<grid, 128, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub);
+    k_reduce_items<<<grid, 128, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub);
 }
 
 void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,

@@ -25,12 +25,13 @@ struct PairDev {
     int n;            // number of contact points
     int n_words;      // ceil(n / 32) mask words
     int word_offset;  // first mask word of this pair inside an environment's mask row
+    int tile_offset;  // first detection tile of this pair inside the batch's tile list
     int body_a, body_b;  // pose slots inside an environment
     GridDev grid;
     PairParams prm;   // effective kn, kt (scaled), mu, damping
 };
 
-// Output value layout of one (env, pair[, split]) partial, fp64:
+// Output value layout of one force item (ForcePlanDev) partial, fp64:
 //   derivative: 4 K-blocks x kSlotK slots, then (if DM) 4 D-blocks x kSlotD slots
 //   value-only: kSlotF slots
 // Slot -> entry maps are produced by tr_index<N>() (see sdfc_kernels.cu).
@@ -53,10 +54,25 @@ constexpr int kOutF = tr_out(12);  // 1
 constexpr int kPartialDeriv = 4 * kOutK * 32;         // 256 doubles
 constexpr int kPartialDerivDM = kPartialDeriv + 4 * kOutD * 32;  // 512 doubles
 constexpr int kPartialValue = kOutF * 32;             // 32 doubles
-// planner fast path (derivatives, no friction, no damping): 12 Km columns + fm,
-// each reduced as 12 values -> 1 per lane
+// planner fast path (derivatives, no friction, no damping): 12 Km columns + fm, 12 entries each, as two
+// half-sums (contacts on lanes 0..15 / 16..31 of a round): column j, half h, entry r at (j * 2 + h) * 12 + r
 constexpr int kNfCols = 13;
-constexpr int kPartialNF = kNfCols * 32;               // 416 doubles
+constexpr int kNfLanes = 24;                           // lanes that own one (half, entry) of every column
+constexpr int kPartialNF = kNfCols * kNfLanes;         // 312 doubles
+
+// Work list of one force launch. The active contacts of every (environment, pair) of the launch are cut into
+// ITEMS of G x 32 consecutive contacts (set bits of the pair's mask row, in word order); the items of a pair are
+// consecutive. Written by k_force_plan after detection, consumed by k_force (one warp per item, taken from the
+// `next` counter) and by reduce_items_one (fixed-order sum of a pair's item partials).
+struct ForcePlanDev {
+    int4* items;       // [cap]  x: env * n_pairs + pair, y / z: the item's contacts [y, z) in mask order (z - y <= 32 G)
+    int* pair_item0;   // [n_envs * n_pairs]  first item of the pair (meaningful while it has active contacts)
+    int* hdr;          // [4]  0: number of items, 1: G, 2: next item to hand out
+    double* partial;   // [cap][stride]  one slot per item
+    int cap;           // item capacity: G doubles until the list fits
+    int stride;        // doubles per slot
+    int g_min;         // smallest G (1; SDFC_FORCE_G)
+};
 
 struct BatchDev {
     const PairDev* pairs;  // [n_pairs]
@@ -66,13 +82,13 @@ struct BatchDev {
     const int* tile_pair;
     const int* tile_word0;
     int n_tiles;
-    int splits;  // force CTAs per (env, pair)
     int any_bricks;     // some pair samples a bricked grid (GridDev::b32): detection stages voxel bricks with TMA
     int brick_cap;      // shared-memory bytes a tile's brick may take (larger bricks: global gathers); SDFC_BRICK_SMEM
     unsigned long long* brick_stats;   // [3] tiles staged / too large / outside the grid box (diagnostics), or nullptr
     uint32_t* mask;     // [n_envs][words_per_env]
     int32_t* n_active;  // [n_envs][n_pairs]
-    double* partial;    // [n_envs][n_pairs][splits][kPartial*]
+    int32_t* tile_count;   // [n_envs][n_tiles]  active contacts per detection tile (written by every tile's CTA)
+    ForcePlanDev plan[2];   // work lists of the value-only (0) and the derivative (1) force kernel
     // optional per-environment evaluation mode (batched stepper): nullptr = every
     // environment, derivative flag taken from the launch; else 0 = skip,
     // 1 = value only, 2 = with derivatives
@@ -149,7 +165,11 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
 void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream);
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
                   cudaStream_t stream);
-// Sums the split partials in fixed order into per-pair blocks (overwrite):
+// Work lists of the force kernels from the contact counts of a finished detection. B.env_mode == nullptr: the
+// list `deriv` for every environment of the launch; else both lists, environments sorted by their mode.
+void launch_force_plan(const BatchDev& B, bool deriv, cudaStream_t stream);
+int device_sm_count();
+// Sums the item partials in fixed order into per-pair blocks (overwrite):
 // fm_sub [env][pair][12], Km_sub / Dm_sub [env][pair][144] column-major.
 void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
                            cudaStream_t stream);

@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind
             if (S.n_active[(size_t)env * S.n_pairs + p] > 0) S.touched[(size_t)env * S.n_pairs + p] = 1;
         WFOR(gi, S.n_grounds)
             if (S.g_n_active[(size_t)env * S.n_grounds + gi] > 0) S.touched_ground[(size_t)env * S.n_grounds + gi] = 1;
-        // split partials of the force kernels -> per-pair blocks (what k_reduce_splits does outside the stepper)
+        // item partials of the force kernels -> per-pair blocks (what k_reduce_items does outside the stepper)
         for (int p = 0; p < S.n_pairs; ++p)
-            reduce_splits_one(S.B, env, p, deriv ? 1 : 0, S.dm, wx.lane, 32, S.fm_sub, S.Km_sub, S.Dm_sub);
+            reduce_items_one(S.B, env, p, deriv ? 1 : 0, S.dm, wx.lane, 32, S.fm_sub, S.Km_sub, S.Dm_sub);
         WSYNC();
         EvalIn in;
         in.bodies = S.bodies; in.n_bodies = S.n_bodies; in.n_pairs = S.n_pairs; in.n_dyn = S.n_dyn; in.nr = nr;
@@ -369,6 +369,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         const char* lanes_env = std::getenv("SDFC_SIM_LANES");
         s->n_lanes = lanes_env ? std::max(1, std::min((int)sdfc_sim::kMaxLanes, std::atoi(lanes_env))) : (ne >= 512 ? 2 : 1);
         s->n_lanes = std::min(s->n_lanes, std::max(1, ne / 32));
+        A(sdfc_host::batch_ensure_plan_slots(batch, s->n_lanes));   // every lane plans its own force work lists
         cudaError_t e = cudaMallocHost((void**)&s->h_unfinished, sizeof(int) * sdfc_sim::kMaxLanes);
         for (int l = 0; l < s->n_lanes && e == cudaSuccess; ++l) {
             e = cudaStreamCreateWithFlags(&s->lane_stream[l], cudaStreamNonBlocking);
@@ -569,6 +570,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             any = true;
             SimDev Dl = D;
             Dl.env0 = lane_env0[l]; Dl.env_count = lane_cnt[l]; Dl.n_unfinished = s->d_unfinished + l;
+            Dl.B.plan[0] = s->batch->plan_slot[l][0]; Dl.B.plan[1] = s->batch->plan_slot[l][1];
             // One round = k_sim_round (state machine on the evaluation of the previous round - none in the first one -
             // then poses, evaluation modes, zeroed counters and culling decisions of the next candidate) followed by
             // the contact kernels that evaluate it. The steady-state round is captured once into a CUDA graph
@@ -576,7 +578,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             auto issue = [&](int kind) -> sdfc_status {
                 sdfc_status r = launch_round(s, Dl, kind, ls);
                 if (r != SDFC_OK) return r;
-                return sdfc_host::batch_run_stepper(s->batch, D.E, D.phi, D.env_mode, lane_env0[l], lane_cnt[l], ls, s->lane_aux[l][0],
+                return sdfc_host::batch_run_stepper(s->batch, D.E, D.phi, D.env_mode, lane_env0[l], lane_cnt[l], l, ls, s->lane_aux[l][0],
                                                     s->lane_aux[l][1], s->lane_ev[l]);
             };
             if (lane_round[l] == 0 || !s->use_graph) {
@@ -597,7 +599,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
                     s->lane_graph_key[l] = graph_key;
                 }
                 if (cudaGraphLaunch(s->lane_graph[l], ls) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph launch failed"); break; }
-                s->ctx->launches += 4 + (s->n_grounds ? 2 : 0);
+                s->ctx->launches += 5 + (s->n_grounds ? 2 : 0);
             }
             if (rc != SDFC_OK) break;
             lane_round[l] += 1;
