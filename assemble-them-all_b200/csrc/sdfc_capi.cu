@@ -167,12 +167,13 @@ sdfc_status batch_ensure_plan_slots(sdfc_batch* b, int n) {
         for (int m = 0; m < 2; ++m) {
             ForcePlanDev& P = b->plan_slot[b->n_plan_slots][m];
             P.cap = b->plan_cap; P.stride = m ? kPartialDerivDM : kPartialValue; P.g_min = g_min;
-            sdfc_status st = dev_alloc(&P.items, (size_t)P.cap);
+            sdfc_status st = dev_alloc(&P.items, (size_t)P.cap * 2);
             if (st == SDFC_OK) st = dev_alloc(&P.pair_item0, ep);
             if (st == SDFC_OK) st = dev_alloc(&P.hdr, (size_t)4);
             if (st == SDFC_OK) st = dev_alloc(&P.partial, (size_t)P.cap * P.stride);
             if (st != SDFC_OK) return st;
-            SDFC_CUDA(cudaMemset(P.hdr, 0, sizeof(int) * 4));
+            const int hdr0[4] = {0, 0, 0, g_min};
+            SDFC_CUDA(cudaMemcpy(P.hdr, hdr0, sizeof(hdr0), cudaMemcpyHostToDevice));
         }
     }
     SDFC_CUDA(cudaDeviceSynchronize());   // null-stream memsets before any non-blocking stream uses the lists

@@ -61,7 +61,7 @@ __device__ __forceinline__ void reduce_items_one(const BatchDev& B, int env, int
     const size_t ep = (size_t)env * B.n_pairs + pair;
     const ForcePlanDev& P = B.plan[deriv ? 1 : 0];
     const int n_act = B.n_active[ep];
-    const int per_item = 32 * P.hdr[1];
+    const int per_item = 32 * P.hdr[3];
     const int n_items = (n_act + per_item - 1) / per_item;
     const bool nf = deriv && !dm;  // layout of the planner fast path: 13 columns x 2 halves x 12 entries
     const int npart = nf ? kNfCols * 12 : (deriv ? kPartialDerivDM : kPartialValue);
@@ -313,38 +313,21 @@ __device__ __forceinline__ int nth_set_bit(uint32_t w, int n) {
     return pos;
 }
 
-// The contacts of ranks [r0, r1) of the pair's mask row (set bits in word order), 32 at a time. The detection
-// tile that holds rank r0 comes from the per-tile contact counts (one load per lane and a warp scan); inside a
-// tile every lane finds ITS contact - rank c0 + lane - by a binary search over the scanned word counts
-// (shuffles) and a bit select: no serial bit loop, no shared-memory id list.
+// The contacts of ranks [r0, r1) of the pair's mask row (set bits in word order), 32 at a time, starting in the
+// detection tile whose first 64 mask words are `row` (wa / wb: this lane's two words of it, already loaded; base:
+// the pair's contacts in front of the tile; nw: the pair's mask words from `row` on). Every lane finds ITS
+// contact - rank c0 + lane - by a binary search over the scanned word counts (shuffles) and a bit select: no
+// serial bit loop, no shared-memory id list. id0: point index of the first word of `row`.
 template <bool F32, bool DERIV, bool FRIC, bool DAMP, bool NF, class Sink>
-__device__ __forceinline__ void force_item(const ForceWarpShared<NF>& S, const BatchDev& B, int env, int r0, int r1, int lane, Sink& sink) {
-    const uint32_t* __restrict__ row = B.mask + (size_t)env * B.words_per_env + S.pd.word_offset;
-    const int32_t* __restrict__ tcnt = B.tile_count + (size_t)env * B.n_tiles + S.pd.tile_offset;
-    const int nw = S.pd.n_words;
-    const int nt = (nw + kDetectTileWords - 1) / kDetectTileWords;
-    int t0 = 0, base = 0;
-    for (;;) {   // 32 tiles at a time (65 536 points)
-        const int c = (t0 + lane < nt) ? __ldg(tcnt + t0 + lane) : 0;
-        const int incl = warp_inclusive_scan(c, lane);
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        if (base + tot > r0) {
-            const int k = __popc(__ballot_sync(0xffffffffu, base + incl <= r0));   // tiles that end at or before r0
-            const int b = __shfl_sync(0xffffffffu, incl, max(k - 1, 0));
-            base += k ? b : 0;
-            t0 += k;
-            break;
-        }
-        base += tot;
-        t0 += 32;
-        if (t0 >= nt) return;   // counts and item table disagree: nothing to evaluate
-    }
+__device__ __forceinline__ void force_item(const ForceWarpShared<NF>& S, const uint32_t* __restrict__ row, int nw, int id0, uint32_t wa,
+                                           uint32_t wb, int base, int r0, int r1, int lane, Sink& sink) {
     int c0 = r0, id = 0;
-    for (int t = t0; t < nt; ++t) {
-        const int w = t * kDetectTileWords;
+    for (int w = 0; w < nw; w += kDetectTileWords) {
         static_assert(kDetectTileWords == 64, "two words per lane and tile");
-        const uint32_t wa = (w + lane < nw) ? __ldg(row + w + lane) : 0u;
-        const uint32_t wb = (w + 32 + lane < nw) ? __ldg(row + w + 32 + lane) : 0u;
+        if (w) {
+            wa = (w + lane < nw) ? __ldg(row + w + lane) : 0u;
+            wb = (w + 32 + lane < nw) ? __ldg(row + w + 32 + lane) : 0u;
+        }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const uint32_t word = half ? wb : wa;
@@ -367,11 +350,11 @@ __device__ __forceinline__ void force_item(const ForceWarpShared<NF>& S, const B
                 }
                 const uint32_t ws = __shfl_sync(0xffffffffu, word, src);
                 const int es = __shfl_sync(0xffffffffu, incl - cnt, src);
-                if (here) id = (w + 32 * half + src) * 32 + nth_set_bit(ws, relc - es);
+                if (here) id = id0 + (w + 32 * half + src) * 32 + nth_set_bit(ws, relc - es);
                 if (base < wend) break;   // the round continues in the next 32 words
                 const bool valid = tgt < wend;
-                const int id0 = __shfl_sync(0xffffffffu, id, 0);
-                force_round<F32, DERIV, FRIC, DAMP, NF>(S, valid ? id : id0, valid, sink);
+                const int idf = __shfl_sync(0xffffffffu, id, 0);
+                force_round<F32, DERIV, FRIC, DAMP, NF>(S, valid ? id : idf, valid, sink);
                 c0 = wend;
                 if (c0 >= r1) return;
             }
@@ -402,75 +385,77 @@ __global__ void __launch_bounds__(kForceThreads, force_min_blocks<DERIV, ANYFRIC
 
     typename std::conditional<NF, ColSink, WarpSink<DERIV, DM>>::type sink;
     if constexpr (NF) sink.init(S.tile, S.acc, lane); else sink.init(lane);
-    auto claim = [&]() {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(P.hdr + 2, 1);
-        return __shfl_sync(0xffffffffu, it, 0);
-    };
-    int cur_ep = -1;
-    int item = claim();
-    int4 tab = make_int4(0, 0, 0, 0);
-    if (item < n_items) tab = __ldg(P.items + item);
+    // Items are claimed from the list's counter by lane 0. The claim of the NEXT item is issued before this one is
+    // evaluated and only read afterwards, so the atomic's round trip is off the critical path - except near the end
+    // of the list, where holding an item in reserve would leave other warps idle.
+    auto claim_raw = [&]() { return lane == 0 ? atomicAdd(P.hdr + 1, 1) : 0; };
+    int cur_pair = -1;
+    int item = __shfl_sync(0xffffffffu, claim_raw(), 0);
     while (item < n_items) {
-        // the next item is claimed (and its table entry requested) before this one is evaluated, so that the
-        // atomic and the load are off the critical path - except near the end of the list, where holding an
-        // item in reserve would leave other warps idle
-        int next = -1;
-        int4 ntab = make_int4(0, 0, 0, 0);
-        if (item + total_warps < n_items) {
-            next = claim();
-            if (next < n_items) ntab = __ldg(P.items + next);
+        const int4 ta = __ldg(P.items + 2 * (size_t)item), tb = __ldg(P.items + 2 * (size_t)item + 1);
+        const bool ahead = item + 2 * total_warps < n_items;
+        int next_raw = 0;
+        if (ahead) next_raw = claim_raw();
+        const int ep = ta.x, r0 = ta.y, r1 = ta.z;
+        const int pair = ep % B.n_pairs;
+        // everything the item needs from global memory, requested at once: its tile's mask words, the two poses
+        // (one element per lane), the pair record when it changes
+        const uint32_t* row = B.mask + (unsigned)tb.x;
+        const uint32_t wa = (lane < tb.y) ? __ldg(row + lane) : 0u;
+        const uint32_t wb = (32 + lane < tb.y) ? __ldg(row + 32 + lane) : 0u;
+        double pose_el = 0.0;
+        if (lane < 24) {
+            const int t = lane < 12 ? lane : lane - 12;   // element (r, c) of the top 3 x 4, column-major pose
+            pose_el = __ldg(E + (size_t)(lane < 12 ? tb.z : tb.w) * 16 + (t % 3) + 4 * (t / 3));
         }
-        const int ep = tab.x;
-        const int env = ep / B.n_pairs, pair = ep - env * B.n_pairs;
-        if (ep != cur_ep) {
-            cur_ep = ep;
-            __syncwarp();
-            {
-                const int* src = reinterpret_cast<const int*>(B.pairs + pair);
-                int* dst = reinterpret_cast<int*>(&S.pd);
-                for (int i = lane; i < (int)(sizeof(PairDev) / sizeof(int)); i += 32) dst[i] = __ldg(src + i);
+        double phi_el = 0.0;
+        if constexpr (!NF) {
+            if (lane < 12) phi_el = __ldg(phi + (size_t)(lane < 6 ? tb.z : tb.w) * 6 + (lane < 6 ? lane : lane - 6));
+        }
+        __syncwarp();   // the previous item's reads of the warp's workspace are done
+        if (pair != cur_pair) {
+            cur_pair = pair;
+            const int* src = reinterpret_cast<const int*>(B.pairs + pair);
+            int* dst = reinterpret_cast<int*>(&S.pd);
+            for (int i = lane; i < (int)(sizeof(PairDev) / sizeof(int)); i += 32) dst[i] = __ldg(src + i);
+        }
+        if (lane < 24) {
+            const int t = lane < 12 ? lane : lane - 12, r = t % 3, c = t / 3;
+            double* R = lane < 12 ? S.pose.R1 : S.pose.R2;
+            double* p = lane < 12 ? S.pose.p1 : S.pose.p2;
+            if (c < 3) R[r * 3 + c] = pose_el; else p[r] = pose_el;
+        }
+        if constexpr (!NF) {
+            if (lane < 6) S.pose.phi1[lane] = phi_el; else if (lane < 12) S.pose.phi2[lane - 6] = phi_el;
+        }
+        __syncwarp();
+        if constexpr (NF) {
+            if (lane < 9) {
+                const int r = lane / 3, c = lane % 3;  // R21 = R2^T R1
+                S.pose.R21[lane] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
             }
             __syncwarp();
-            if constexpr (NF) {
-                if (lane < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, lane);
-                else if (lane < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, lane - 12);
-                __syncwarp();
-                if (lane < 9) {
-                    const int r = lane / 3, c = lane % 3;  // R21 = R2^T R1
-                    S.pose.R21[lane] = S.pose.R2[r] * S.pose.R1[c] + S.pose.R2[3 + r] * S.pose.R1[3 + c] + S.pose.R2[6 + r] * S.pose.R1[6 + c];
-                }
-            } else {
-                if (lane < 12) stage_pose(E, B.n_bodies, env, S.pd.body_a, S.pose.R1, S.pose.p1, lane);
-                else if (lane < 24) stage_pose(E, B.n_bodies, env, S.pd.body_b, S.pose.R2, S.pose.p2, lane - 12);
-                else if (lane < 30) S.pose.phi1[lane - 24] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_a) * 6 + lane - 24);
-                if (lane < 6) S.pose.phi2[lane] = __ldg(phi + ((size_t)env * B.n_bodies + S.pd.body_b) * 6 + lane);
-            }
-            __syncwarp();
         }
-        const int r0 = tab.y, r1 = tab.z;
+        const int id0 = (int)((unsigned)tb.x - (unsigned)((size_t)(ep / B.n_pairs) * B.words_per_env + S.pd.word_offset)) * 32;
         const bool f32 = S.pd.grid.f32();
         const bool fric = ANYFRIC && (S.pd.prm.mu > kEps);        // .cpp:200,352
         const bool damp = ANYDAMP && (S.pd.prm.damping != 0.0);
         // warp-uniform variant dispatch (template flags prune what cannot occur)
+#define SDFC_ITEM(F, D, FR, DA, N) force_item<F, D, FR, DA, N>(S, row, tb.y, id0, wa, wb, ta.w, r0, r1, lane, sink)
         if constexpr (NF) {
-            if (f32) force_item<true, true, false, false, true>(S, B, env, r0, r1, lane, sink);
-            else force_item<false, true, false, false, true>(S, B, env, r0, r1, lane, sink);
+            if (f32) SDFC_ITEM(true, true, false, false, true); else SDFC_ITEM(false, true, false, false, true);
         } else if (f32) {
-            if (fric) { if (damp) force_item<true, DERIV, ANYFRIC, ANYDAMP, false>(S, B, env, r0, r1, lane, sink); else force_item<true, DERIV, ANYFRIC, false, false>(S, B, env, r0, r1, lane, sink); }
-            else      { if (damp) force_item<true, DERIV, false, ANYDAMP, false>(S, B, env, r0, r1, lane, sink);  else force_item<true, DERIV, false, false, false>(S, B, env, r0, r1, lane, sink); }
+            if (fric) { if (damp) SDFC_ITEM(true, DERIV, ANYFRIC, ANYDAMP, false); else SDFC_ITEM(true, DERIV, ANYFRIC, false, false); }
+            else      { if (damp) SDFC_ITEM(true, DERIV, false, ANYDAMP, false);  else SDFC_ITEM(true, DERIV, false, false, false); }
         } else {
-            if (fric) { if (damp) force_item<false, DERIV, ANYFRIC, ANYDAMP, false>(S, B, env, r0, r1, lane, sink); else force_item<false, DERIV, ANYFRIC, false, false>(S, B, env, r0, r1, lane, sink); }
-            else      { if (damp) force_item<false, DERIV, false, ANYDAMP, false>(S, B, env, r0, r1, lane, sink);  else force_item<false, DERIV, false, false, false>(S, B, env, r0, r1, lane, sink); }
+            if (fric) { if (damp) SDFC_ITEM(false, DERIV, ANYFRIC, ANYDAMP, false); else SDFC_ITEM(false, DERIV, ANYFRIC, false, false); }
+            else      { if (damp) SDFC_ITEM(false, DERIV, false, ANYDAMP, false);  else SDFC_ITEM(false, DERIV, false, false, false); }
         }
+#undef SDFC_ITEM
         if constexpr (NF) flush_item(sink, S.pose.R21, P.partial + (size_t)item * P.stride, lane);
         else flush_item(sink, P.partial + (size_t)item * P.stride, lane);
-        if (next < 0) {
-            next = claim();
-            if (next < n_items) ntab = __ldg(P.items + next);
-        }
-        item = next;
-        tab = ntab;
+        if (!ahead) next_raw = claim_raw();
+        item = __shfl_sync(0xffffffffu, next_raw, 0);
     }
 }
 

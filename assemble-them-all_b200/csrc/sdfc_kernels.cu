@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_dete
     __syncthreads();
     if (threadIdx.x == 0) {
         B.tile_count[(size_t)env * B.n_tiles + tile] = s_count;   // the force kernel finds an item's contacts tile by tile
-        if (s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+        if (s_count) {
+            atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+            atomicAdd(B.plan[0].hdr + 2, (s_count + 31) >> 5);   // bound of the force kernels' 32-contact rounds
+        }
     }
 }
 
@@ -471,13 +474,19 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
     __syncthreads();
     if (threadIdx.x == 0) {
         B.tile_count[(size_t)env * B.n_tiles + tile] = s_count;   // the force kernel finds an item's contacts tile by tile
-        if (s_count) atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+        if (s_count) {
+            atomicAdd(B.n_active + (size_t)env * B.n_pairs + pair, s_count);
+            atomicAdd(B.plan[0].hdr + 2, (s_count + 31) >> 5);   // bound of the force kernels' 32-contact rounds
+        }
     }
 }
 
 void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream, bool reset_counts) {
-    if (reset_counts)
+    if (reset_counts) {
         cudaMemsetAsync(B.n_active + (size_t)B.env0 * B.n_pairs, 0, sizeof(int32_t) * (size_t)B.env_count * B.n_pairs, stream);
+        cudaMemsetAsync(B.plan[0].hdr, 0, sizeof(int) * 3, stream);   // work lists of the force kernels: empty
+        cudaMemsetAsync(B.plan[1].hdr, 0, sizeof(int) * 3, stream);
+    }
     if (B.n_tiles == 0 || B.env_count == 0) return;   // every pair has an empty point set: all counts stay 0
     dim3 grid(B.n_tiles, B.env_count);
     if (B.any_bricks && B.skin_margin == nullptr) {
@@ -496,84 +505,89 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
 // --------------------------------------------------------------------------
 // work list of the force kernels
 // --------------------------------------------------------------------------
-constexpr int kPlanThreads = 1024;
+constexpr int kPlanWarps = 8;
 
-// One CTA per list (blockIdx.x = 0: value-only, 1: derivative when the launch carries per-environment modes).
-// Pass 1: rounds (32-contact groups) and pairs with contacts -> G, the smallest power-of-two multiple of g_min
-// for which the list fits its capacity (items <= rounds / G + pairs). Pass 2: exclusive scan of the items per
-// pair in (env, pair) order -> first item of every pair, then the item table, filled by the whole CTA.
-__global__ void __launch_bounds__(kPlanThreads) k_force_plan(BatchDev B, int deriv_sel) {
-    __shared__ int s_warp[32];
-    __shared__ int s_off[kPlanThreads + 1];
-    __shared__ int s_bcast[2];
-    const int sel = (B.env_mode != nullptr) ? (int)blockIdx.x : deriv_sel;
-    const ForcePlanDev P = B.plan[sel];
-    const int want = sel ? 2 : 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ep0 = B.env0 * B.n_pairs, n_ep = B.env_count * B.n_pairs;
-    auto contacts_of = [&](int i) -> int {
-        if (i >= n_ep) return 0;
-        if (B.env_mode != nullptr && __ldg(B.env_mode + B.env0 + i / B.n_pairs) != want) return 0;
-        return B.n_active[ep0 + i];
-    };
-    // ---- pass 1
-    int rounds = 0, pairs = 0;
-    for (int i = tid; i < n_ep; i += kPlanThreads) {
-        const int n = contacts_of(i);
-        rounds += (n + 31) >> 5;
-        pairs += n > 0;
+// One warp per (environment, pair) with contacts. G = the smallest power-of-two multiple of g_min for which the
+// list is certain to fit (items <= rounds / G + pairs; the number of rounds is bounded by the sum detection
+// accumulated tile by tile, so every warp derives the same G without a grid-wide pass). The pair's items take
+// consecutive slots handed out by one atomic - their position in the list varies from run to run, the sums do
+// not: a pair's partials are added in item order (reduce_items_one). Lane k fills item k, k + 32, ...: its
+// contact range, the detection tile that holds its first contact (binary search over the scanned tile counts)
+// and the addresses the force kernel starts from.
+__global__ void __launch_bounds__(kPlanWarps * 32) k_force_plan(BatchDev B, int deriv_sel) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kPlanWarps + (threadIdx.x >> 5);
+    if (i >= B.env_count * B.n_pairs) return;
+    const int env = B.env0 + i / B.n_pairs, pair = i % B.n_pairs;
+    int sel = deriv_sel;
+    if (B.env_mode != nullptr) {
+        const int m = __ldg(B.env_mode + env);
+        if (m == 0) return;
+        sel = (m == 2) ? 1 : 0;
     }
-    rounds = __reduce_add_sync(0xffffffffu, rounds);
-    pairs = __reduce_add_sync(0xffffffffu, pairs);
-    if (lane == 0) { s_warp[warp] = rounds; s_off[warp] = pairs; }
-    __syncthreads();
-    if (tid == 0) {
-        long long R = 0; int Np = 0;
-        for (int w = 0; w < kPlanThreads / 32; ++w) { R += s_warp[w]; Np += s_off[w]; }
-        int G = P.g_min;
-        while ((R + G - 1) / G + Np > P.cap) G *= 2;
-        s_bcast[0] = G;
+    const int ep = env * B.n_pairs + pair;
+    const int n_act = B.n_active[ep];
+    if (n_act == 0) return;
+    const ForcePlanDev& P = B.plan[sel];
+    int G = P.g_min;
+    {
+        const long long bound = B.plan[0].hdr[2];
+        const int n_ep = B.env_count * B.n_pairs;
+        while ((bound + G - 1) / G + n_ep > P.cap) G *= 2;
     }
-    __syncthreads();
-    const int G = s_bcast[0];
-    // ---- pass 2
-    int run = 0;
-    for (int i0 = 0; i0 < n_ep; i0 += kPlanThreads) {
-        const int i = i0 + tid;
-        const int n = contacts_of(i);
-        const int items = (((n + 31) >> 5) + G - 1) / G;
-        int incl = items;
+    const int per_item = 32 * G;
+    const int n_items = (n_act + per_item - 1) / per_item;
+    int item0 = 0;
+    if (lane == 0) {
+        item0 = atomicAdd(P.hdr, n_items);
+        P.pair_item0[ep] = item0;
+        P.hdr[3] = G;
+    }
+    item0 = __shfl_sync(0xffffffffu, item0, 0);
+    const PairDev& pd = B.pairs[pair];
+    const int32_t* tc = B.tile_count + (size_t)env * B.n_tiles + pd.tile_offset;
+    const int nt = (pd.n_words + kDetectTileWords - 1) / kDetectTileWords;
+    const unsigned row0 = (unsigned)((size_t)env * B.words_per_env + pd.word_offset);
+    const int slot_a = env * B.n_bodies + pd.body_a, slot_b = env * B.n_bodies + pd.body_b;
+    int k0 = 0, base = 0;   // items below k0 are written; contacts in front of tile chunk t0
+    for (int t0 = 0; t0 < nt && k0 < n_items; t0 += 32) {
+        const int c = (t0 + lane < nt) ? tc[t0 + lane] : 0;
+        int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        __syncthreads();   // s_warp / s_off of the previous chunk consumed
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        int off = incl - items;
-        for (int w = 0; w < warp; ++w) off += s_warp[w];
-        s_off[tid] = off;
-        if (tid == kPlanThreads - 1) s_off[kPlanThreads] = off + items;
-        if (items > 0) P.pair_item0[ep0 + i] = run + off;
-        __syncthreads();
-        const int chunk_items = s_off[kPlanThreads];
-        for (int t = tid; t < chunk_items; t += kPlanThreads) {
-            int lo = 0, hi = kPlanThreads;   // last entry with s_off[entry] <= t
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_off[mid] <= t) lo = mid; else hi = mid;
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        // items whose first contact lies in these 32 tiles: k0 <= k < k1
+        const int k1 = min(n_items, (base + tot + per_item - 1) / per_item);
+        for (int kb = k0; kb < k1; kb += 32) {
+            const int k = kb + lane;
+            const bool mine = k < k1;
+            const int rel = mine ? k * per_item - base : 0;   // 0 <= rel < tot
+            int src = 0;   // first tile of the chunk whose inclusive count exceeds rel
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                if (v <= rel) src += step;
             }
-            const int k = t - s_off[lo], n_act = B.n_active[ep0 + i0 + lo];
-            P.items[run + t] = make_int4(ep0 + i0 + lo, k * 32 * G, min(n_act, (k + 1) * 32 * G), 0);
+            const int before = __shfl_sync(0xffffffffu, incl - c, src);
+            if (mine) {
+                const int r0 = k * per_item, t = t0 + src;
+                P.items[2 * (size_t)(item0 + k)] = make_int4(ep, r0, min(n_act, r0 + per_item), base + before);
+                P.items[2 * (size_t)(item0 + k) + 1] =
+                    make_int4((int)(row0 + (unsigned)t * kDetectTileWords), pd.n_words - t * kDetectTileWords, slot_a, slot_b);
+            }
         }
-        run += chunk_items;
+        k0 = k1;
+        base += tot;
     }
-    if (tid == 0) { P.hdr[0] = run; P.hdr[1] = G; P.hdr[2] = 0; }
 }
 
 void launch_force_plan(const BatchDev& B, bool deriv, cudaStream_t stream) {
-    k_force_plan<<<B.env_mode != nullptr ? 2 : 1, kPlanThreads, 0, stream>>>(B, deriv ? 1 : 0);
+    const int n_ep = B.env_count * B.n_pairs;
+    if (n_ep == 0) return;
+    k_force_plan<<<(n_ep + kPlanWarps - 1) / kPlanWarps, kPlanWarps * 32, 0, stream>>>(B, deriv ? 1 : 0);
 }
 
 int device_sm_count() {

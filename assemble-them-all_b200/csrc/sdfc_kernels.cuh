@@ -65,9 +65,16 @@ constexpr int kPartialNF = kNfCols * kNfLanes;         // 312 doubles
 // consecutive. Written by k_force_plan after detection, consumed by k_force (one warp per item, taken from the
 // `next` counter) and by reduce_items_one (fixed-order sum of a pair's item partials).
 struct ForcePlanDev {
-    int4* items;       // [cap]  x: env * n_pairs + pair, y / z: the item's contacts [y, z) in mask order (z - y <= 32 G)
+    // [cap][2]  entry 0: x = env * n_pairs + pair, y / z = the item's contacts [y, z) in mask order (z - y <= 32 G),
+    //                     w = contacts of the pair in front of the detection tile that holds contact y;
+    //           entry 1: x = index in `mask` of that tile's first word, y = mask words of the pair from there on,
+    //                     z / w = pose slots env * n_bodies + body_a / body_b
+    int4* items;
     int* pair_item0;   // [n_envs * n_pairs]  first item of the pair (meaningful while it has active contacts)
-    int* hdr;          // [4]  0: number of items, 1: G, 2: next item to hand out
+    // [4]  0: number of items (handed out by atomics while planning), 1: next item to evaluate, 2: upper bound of the
+    // 32-contact rounds of the evaluation (detection adds every tile's share to plan[0]'s), 3: G. 0..2 are cleared
+    // before every detection (launch_detect_mask / the stepper's round kernel), 3 always holds a valid G.
+    int* hdr;
     double* partial;   // [cap][stride]  one slot per item
     int cap;           // item capacity: G doubles until the list fits
     int stride;        // doubles per slot
@@ -165,8 +172,9 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
 void launch_skin_decide(const BatchDev& B, const double* E, cudaStream_t stream);
 void launch_force(const BatchDev& B, const double* E, const double* phi, bool deriv, bool any_fric, bool any_damp,
                   cudaStream_t stream);
-// Work lists of the force kernels from the contact counts of a finished detection. B.env_mode == nullptr: the
-// list `deriv` for every environment of the launch; else both lists, environments sorted by their mode.
+// Work lists of the force kernels from the contact counts of a finished detection (one warp per (environment,
+// pair)). B.env_mode == nullptr: the list `deriv` for every environment of the launch; else both lists,
+// environments sorted by their mode.
 void launch_force_plan(const BatchDev& B, bool deriv, cudaStream_t stream);
 int device_sm_count();
 // Sums the item partials in fixed order into per-pair blocks (overwrite):

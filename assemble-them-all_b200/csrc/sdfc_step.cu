@@ -30,6 +30,9 @@
 #ifndef SDFC_SKIN_DEFAULT
 #define SDFC_SKIN_DEFAULT 1
 #endif
+#ifndef SDFC_TAIL_TEAM
+#define SDFC_TAIL_TEAM 128
+#endif
 
 namespace sdfc {
 
@@ -103,20 +106,24 @@ __device__ __forceinline__ void w_candidate(const WarpExec& wx, const SimDev& S,
     WSYNC();
 }
 
-// One round of one environment per WARP (workspace in shared memory, sdfc_step_math.cuh):
+// One round of one environment per TEAM (TEAM = 32: a warp, kSimWarps environments per CTA; TEAM > 32: the whole
+// CTA works on one environment - the tail of a forward, where a handful of environments are still iterating and
+// the latency of one round of one environment is the whole cost; same statements, same operands, same bits).
+// Workspace in shared memory, sdfc_step_math.cuh:
 //   1. "post": the contact kernels have evaluated the candidate of the previous round; assemble the BDF1
 //      residual g (and H), solve, advance the Newton / line-search / step state machine
 //      (Simulation.cpp:999-1079, 955-966, 1259);
 //   2. "pre": poses E_0i and twists phi of the next candidate for the contact kernels, its evaluation mode,
 //      and the zeroed contact counters of the next detection.
 // ROUND_FIRST skips 1 (first round of a forward), ROUND_POSES only writes the poses of the current state.
-__global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind) {
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM == 32 ? kSimWarps * 32 : TEAM) k_sim_round(SimDev S, int kind) {
     extern __shared__ __align__(16) unsigned char ws_raw[];
-    const int warp = threadIdx.x >> 5;
-    const int env = S.env0 + blockIdx.x * kSimWarps + warp;
-    if (env >= S.env0 + S.env_count) return;   // whole warps leave together
+    const int warp = (TEAM == 32) ? (threadIdx.x >> 5) : 0;
+    const int env = S.env0 + ((TEAM == 32) ? blockIdx.x * kSimWarps + warp : blockIdx.x);
+    if (env >= S.env0 + S.env_count) return;   // whole teams leave together
     EnvW& W = reinterpret_cast<EnvW*>(ws_raw)[warp];
-    const WarpExec wx{(int)(threadIdx.x & 31), 1};
+    const WarpExec wx{(int)(TEAM == 32 ? (threadIdx.x & 31) : threadIdx.x), 1, TEAM};
     const int nr = S.nr;
     const double h = S.h;
     const size_t o = (size_t)env * nr;
@@ -128,6 +135,8 @@ __global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind
         return;
     }
 
+    // work lists of this round's force kernels: empty (detection and k_force_plan fill them)
+    if (blockIdx.x == 0 && threadIdx.x < 6) S.B.plan[threadIdx.x / 3].hdr[threadIdx.x % 3] = 0;
     const int mode = (kind == ROUND_FULL) ? S.env_mode[env] : 0;
     if (mode != 0) {
         const bool deriv = (mode == 2);
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(kSimWarps * 32) k_sim_round(SimDev S, int kind
             if (S.g_n_active[(size_t)env * S.n_grounds + gi] > 0) S.touched_ground[(size_t)env * S.n_grounds + gi] = 1;
         // item partials of the force kernels -> per-pair blocks (what k_reduce_items does outside the stepper)
         for (int p = 0; p < S.n_pairs; ++p)
-            reduce_items_one(S.B, env, p, deriv ? 1 : 0, S.dm, wx.lane, 32, S.fm_sub, S.Km_sub, S.Dm_sub);
+            reduce_items_one(S.B, env, p, deriv ? 1 : 0, S.dm, wx.lane, TEAM, S.fm_sub, S.Km_sub, S.Dm_sub);
         WSYNC();
         EvalIn in;
         in.bodies = S.bodies; in.n_bodies = S.n_bodies; in.n_pairs = S.n_pairs; in.n_dyn = S.n_dyn; in.nr = nr;
@@ -290,8 +299,9 @@ struct sdfc_sim {
     // fork / join streams and events of a lane's contact kernels, and the captured steady-state round
     cudaStream_t lane_aux[kMaxLanes][2] = {};
     cudaEvent_t lane_ev[kMaxLanes][4] = {};
-    cudaGraphExec_t lane_graph[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
-    uint64_t lane_graph_key[kMaxLanes] = {0, 0, 0, 0};
+    cudaGraphExec_t lane_graph[kMaxLanes][2] = {};   // [lane][0: warp per environment, 1: tail variant (CTA per environment)]
+    uint64_t lane_graph_key[kMaxLanes][2] = {};
+    int tail_envs = 0;   // a lane switches to the tail variant once this few of its environments are unfinished
     bool use_graph = true;
     bool use_active = false;
     double* d_fext = nullptr;
@@ -304,15 +314,22 @@ struct sdfc_sim {
 };
 
 namespace {
-sdfc_status launch_round(sdfc_sim* s, const SimDev& D, int kind, cudaStream_t st) {
+constexpr int kTailTeam = SDFC_TAIL_TEAM;   // threads per environment of the tail variant of the round kernel
+
+sdfc_status launch_round(sdfc_sim* s, const SimDev& D, int kind, cudaStream_t st, bool tail = false) {
     const size_t smem = sizeof(EnvW) * kSimWarps;
     static bool configured = false;
     if (!configured) {
-        SDFC_CUDA(cudaFuncSetAttribute(k_sim_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SDFC_CUDA(cudaFuncSetAttribute(k_sim_round<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SDFC_CUDA(cudaFuncSetAttribute(k_sim_round<kTailTeam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvW)));
         configured = true;
     }
-    const int blocks = (D.env_count + kSimWarps - 1) / kSimWarps;
-    k_sim_round<<<blocks, kSimWarps * 32, smem, st>>>(D, kind);
+    if (tail) {
+        k_sim_round<kTailTeam><<<D.env_count, kTailTeam, sizeof(EnvW), st>>>(D, kind);
+    } else {
+        const int blocks = (D.env_count + kSimWarps - 1) / kSimWarps;
+        k_sim_round<32><<<blocks, kSimWarps * 32, smem, st>>>(D, kind);
+    }
     s->ctx->launches += 1;
     return SDFC_OK;
 }
@@ -378,6 +395,10 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
             for (int a = 0; a < 4 && e == cudaSuccess; ++a) e = cudaEventCreateWithFlags(&s->lane_ev[l][a], cudaEventDisableTiming);
         }
         if (const char* g = std::getenv("SDFC_SIM_GRAPH")) s->use_graph = std::atoi(g) != 0;   // 0: launch every round kernel by kernel
+        // tail variant of the round kernel: worth it once the teams of the unfinished environments no longer fill the
+        // device (2 per SM); SDFC_SIM_TAIL overrides (0 = never)
+        s->tail_envs = (nr >= 6) ? 2 * sdfc::device_sm_count() : 0;   // 3-dof statements are too small for a CTA
+        if (const char* t = std::getenv("SDFC_SIM_TAIL")) s->tail_envs = std::max(0, std::atoi(t));
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_bodies, hb.data(), sizeof(BodyDev) * nb, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_pair_a, batch->body_a.data(), sizeof(int) * np, cudaMemcpyHostToDevice);
@@ -428,7 +449,7 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
     for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) {
-        if (s->lane_graph[l]) cudaGraphExecDestroy(s->lane_graph[l]);
+        for (int v = 0; v < 2; ++v) if (s->lane_graph[l][v]) cudaGraphExecDestroy(s->lane_graph[l][v]);
         if (s->lane_stream[l]) cudaStreamDestroy(s->lane_stream[l]);
         if (s->lane_event[l]) cudaEventDestroy(s->lane_event[l]);
         for (int a = 0; a < 2; ++a) if (s->lane_aux[l][a]) cudaStreamDestroy(s->lane_aux[l][a]);
@@ -556,6 +577,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     // is only waited for before round r + 2 is issued, so the device always has queued work while
     // the host looks at an older answer (a finished lane runs at most two empty rounds).
     bool lane_pending[sdfc_sim::kMaxLanes] = {false, false, false, false};
+    bool lane_tail[sdfc_sim::kMaxLanes] = {false, false, false, false};
     int64_t lane_round[sdfc_sim::kMaxLanes] = {0, 0, 0, 0};
     for (int64_t round = 0; round < guard && rc == SDFC_OK; ++round) {
         bool any = false;
@@ -566,6 +588,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
                 if (cudaEventSynchronize(s->lane_event[l]) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: lane sync failed"); break; }
                 lane_pending[l] = false;
                 if (s->h_unfinished[l] <= 0) { lane_live[l] = false; continue; }
+                lane_tail[l] = s->h_unfinished[l] <= s->tail_envs;
             }
             any = true;
             SimDev Dl = D;
@@ -576,7 +599,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             // the contact kernels that evaluate it. The steady-state round is captured once into a CUDA graph
             // (fork / join: value and derivative force kernels and the ground kernels side by side) and replayed.
             auto issue = [&](int kind) -> sdfc_status {
-                sdfc_status r = launch_round(s, Dl, kind, ls);
+                sdfc_status r = launch_round(s, Dl, kind, ls, lane_tail[l]);
                 if (r != SDFC_OK) return r;
                 return sdfc_host::batch_run_stepper(s->batch, D.E, D.phi, D.env_mode, lane_env0[l], lane_cnt[l], l, ls, s->lane_aux[l][0],
                                                     s->lane_aux[l][1], s->lane_ev[l]);
@@ -584,8 +607,9 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             if (lane_round[l] == 0 || !s->use_graph) {
                 rc = issue(lane_round[l] == 0 ? ROUND_FIRST : ROUND_FULL);
             } else {
-                if (s->lane_graph[l] == nullptr || s->lane_graph_key[l] != graph_key) {
-                    if (s->lane_graph[l]) { cudaGraphExecDestroy(s->lane_graph[l]); s->lane_graph[l] = nullptr; }
+                const int v = lane_tail[l] ? 1 : 0;
+                if (s->lane_graph[l][v] == nullptr || s->lane_graph_key[l][v] != graph_key) {
+                    if (s->lane_graph[l][v]) { cudaGraphExecDestroy(s->lane_graph[l][v]); s->lane_graph[l][v] = nullptr; }
                     cudaGraph_t g = nullptr;
                     const int64_t launches0 = s->ctx->launches;
                     if (cudaStreamBeginCapture(ls, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph capture failed to start"); break; }
@@ -593,12 +617,12 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
                     const cudaError_t ce = cudaStreamEndCapture(ls, &g);
                     s->ctx->launches = launches0;   // captured, not launched
                     if (rc == SDFC_OK && (ce != cudaSuccess || g == nullptr)) rc = fail(SDFC_ERR_CUDA, std::string("sdfc_sim_forward: graph capture: ") + cudaGetErrorString(ce));
-                    if (rc == SDFC_OK && cudaGraphInstantiate(&s->lane_graph[l], g, 0) != cudaSuccess) rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph instantiation failed");
+                    if (rc == SDFC_OK && cudaGraphInstantiate(&s->lane_graph[l][v], g, 0) != cudaSuccess) rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph instantiation failed");
                     if (g) cudaGraphDestroy(g);
                     if (rc != SDFC_OK) break;
-                    s->lane_graph_key[l] = graph_key;
+                    s->lane_graph_key[l][v] = graph_key;
                 }
-                if (cudaGraphLaunch(s->lane_graph[l], ls) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph launch failed"); break; }
+                if (cudaGraphLaunch(s->lane_graph[l][v], ls) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: graph launch failed"); break; }
                 s->ctx->launches += 5 + (s->n_grounds ? 2 : 0);
             }
             if (rc != SDFC_OK) break;

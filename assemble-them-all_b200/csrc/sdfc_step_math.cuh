@@ -1,8 +1,9 @@
 // sdfc_step_math.cuh — the per-environment arithmetic of the batched BDF1 stepper, written for
-// ONE WARP PER ENVIRONMENT with the environment's 6 x n / 12 x 12 blocks in SHARED MEMORY.
+// ONE TEAM OF THREADS PER ENVIRONMENT (a warp; a whole CTA when few environments are left and the latency of
+// one environment is all there is) with the environment's 6 x n / 12 x 12 blocks in SHARED MEMORY.
 //
 // Every routine is a sequence of data-parallel statements WFOR(e, N) { one output element } separated by
-// WSYNC(): the 32 lanes of the warp split the N independent outputs of a statement (an element of a 3 x 3
+// WSYNC(): the threads of the team split the N independent outputs of a statement (an element of a 3 x 3
 // product, a column of a Jacobian, an entry of the reduced matrix ...), all operands live in the warp's
 // workspace, and nothing is kept in per-thread local memory. The per-environment work is 10^3 - 10^4
 // dependent flops (exponential-map kinematics with second derivatives, reduced assembly, pivoted LU):
@@ -30,13 +31,14 @@
 namespace sdfc {
 
 struct WarpExec {
-    int lane;   // device: lane id; host: unused
-    int dir;    // host: +1 forward / -1 backward element order
+    int lane;       // device: index of the thread in its team; host: unused
+    int dir;        // host: +1 forward / -1 backward element order
+    int nth = 32;   // device: threads of the team (32 = a warp; otherwise the whole CTA)
 };
 
 #if defined(__CUDA_ARCH__)
-#define WFOR(e, N) for (int e = wx.lane; e < (N); e += 32)
-#define WSYNC() __syncwarp()
+#define WFOR(e, N) for (int e = wx.lane; e < (N); e += wx.nth)
+#define WSYNC() do { if (wx.nth > 32) __syncthreads(); else __syncwarp(); } while (0)
 #define WLANE0 (wx.lane == 0)
 #else
 #define WFOR(e, N) for (int e##_i = 0, e = (wx.dir > 0 ? 0 : (N)-1); e##_i < (N); ++e##_i, e += wx.dir)
