@@ -104,17 +104,25 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
         launch_force(dev, E_dev, phi_dev, deriv != 0, b->any_fric, b->any_damp, s);
     }
     c->end();
-    c->begin(2); launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s); c->end();
+    // per-pair blocks (always) and, on request, the system arrays: one fused launch unless per-environment modes
+    // are in play (the stepper sums the blocks itself and never asks for system arrays)
+    const bool fused = scatter && env_mode_dev == nullptr;
+    c->begin(2);
+    if (fused) launch_reduce_scatter(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
+    else launch_finalize_pairs(dev, deriv != 0, dm, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, s);
+    c->end();
     c->launches += 4;
     if (b->gset) {
         st = sdfc_host::ground_set_run(b->gset, E_dev, phi_dev, deriv, env_mode_dev, env0, env_count);
         if (st != SDFC_OK) return st;
     }
     if (scatter) {
-        c->begin(3);
-        launch_scatter_system(dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
-        c->end();
-        c->launches += 1;
+        if (!fused) {
+            c->begin(3);
+            launch_scatter_system(dev, deriv != 0, b->d_fm_sub, b->d_Km_sub, b->d_Dm_sub, fm_dev, Km_dev, Dm_dev, s);
+            c->end();
+            c->launches += 1;
+        }
         if (b->gset) {
             st = sdfc_host::ground_set_scatter(b->gset, deriv, fm_dev, Km_dev, Dm_dev);
             if (st != SDFC_OK) return st;

@@ -944,35 +944,97 @@ __device__ __forceinline__ void stencil_reduce_on_cell(const double c[8], const 
 #undef SDFC_ST3
 }
 
-// One-face crossing: every sample on its own cell (base c or neighbour c2). Rare; kept out of line so that
-// its registers do not count against the common path.
-static __device__ __noinline__ void stencil_crossing(const double* c, const double* c2, const double* fi, const double* fj, const double* fk,
-                                              const int* oi, const int* oj, const int* ok_, double col_th, double* d, double* g, double* H) {
-    auto S = [&](int vi, int vj, int vk) {
-        const bool nb = (oi[vi] + oj[vj] + ok_[vk]) != 0;
-        double q[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) q[t] = nb ? c2[t] : c[t];
-        return lerp8(q, fi[vi], fj[vj], fk[vk]);
-    };
+// One-face crossing: the stencil straddles ONE cell face, so every sample lies either in the base cell (corners c)
+// or in its neighbour across that face (corners c2) - decided by the sample's variant on the crossing axis alone
+// (bit v of mx / my / mz: variant v of that axis is in the neighbour; at most one mask is non-zero). Same staged
+// evaluation as stencil_reduce_on_cell with both cells carried through the stages that come before the crossing
+// axis and a select where a stage consumes the crossing axis' variant: the x-lerps run on the cell picked by the
+// x variant (x crossing) or on both cells, the y-lerps pick the x-lerps of their cell (y crossing) or run on both,
+// the z-lerp picks its pair (z crossing). Each sample is the reference's lerp sequence on the reference's cell:
+// same bits as 19 separate query_SDF calls (118 lerps and 140 selects instead of 133 lerps and 152 selects per
+// crossing lane PLUS the 65 lerps of the other lanes of the warp, which now take this path together).
+__device__ __forceinline__ void stencil_reduce_two_cells(const double c[8], const double c2[8], const double fi[5], const double fj[5],
+                                                         const double fk[5], unsigned mx, unsigned my, unsigned mz, double col_th,
+                                                         double& d, double g[3], double H[9]) {
     constexpr double kTwoEps = 2 * kFdEps, kRTwoEps = 1.0 / kTwoEps;
     constexpr double kEps2 = kFdEps * kFdEps, kREps2 = 1.0 / kEps2;
-    const double s0 = S(0, 0, 0), two_s0 = __dmul_rn(2.0, s0);
-    *d = __dadd_rn(s0, col_th);
-    { const double a = S(1, 0, 0), b = S(2, 0, 0); g[0] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[0] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
-    { const double a = S(0, 1, 0), b = S(0, 2, 0); g[1] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[4] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
-    { const double a = S(0, 0, 1), b = S(0, 0, 2); g[2] = exact_div(__dsub_rn(a, b), kTwoEps, kRTwoEps); H[8] = exact_div(__dsub_rn(__dadd_rn(a, b), two_s0), kEps2, kREps2); }
-    H[1] = H[3] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(3, 3, 0), S(4, 4, 0)), S(3, 4, 0)), S(4, 3, 0)), kEps2, kREps2);
-    H[2] = H[6] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(3, 0, 3), S(4, 0, 4)), S(3, 0, 4)), S(4, 0, 3)), kEps2, kREps2);
-    H[5] = H[7] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(S(0, 3, 3), S(0, 4, 4)), S(0, 3, 4)), S(0, 4, 3)), kEps2, kREps2);
+    double a00, a10, a01, a11, b00, b10, b01, b11, wa0, wa1, wb0, wb1;
+    // x-lerps of variant vi: a* on the cell the x variant selects, b* on the neighbour (used by y / z crossings)
+#define SDFC_TC1(vi)                                                                                   \
+    {                                                                                                  \
+        const bool nb = (mx >> (vi)) & 1u;                                                             \
+        a00 = lerp1(fi[vi], nb ? c2[0] : c[0], nb ? c2[1] : c[1]);                                     \
+        a10 = lerp1(fi[vi], nb ? c2[2] : c[2], nb ? c2[3] : c[3]);                                     \
+        a01 = lerp1(fi[vi], nb ? c2[4] : c[4], nb ? c2[5] : c[5]);                                     \
+        a11 = lerp1(fi[vi], nb ? c2[6] : c[6], nb ? c2[7] : c[7]);                                     \
+        b00 = lerp1(fi[vi], c2[0], c2[1]); b10 = lerp1(fi[vi], c2[2], c2[3]);                          \
+        b01 = lerp1(fi[vi], c2[4], c2[5]); b11 = lerp1(fi[vi], c2[6], c2[7]);                          \
+    }
+    // y-lerps of variant vj: wa* on the cell the y variant selects, wb* on the neighbour (used by z crossings)
+#define SDFC_TC2(vj)                                                                                   \
+    {                                                                                                  \
+        const bool nb = (my >> (vj)) & 1u;                                                             \
+        wa0 = lerp1(fj[vj], nb ? b00 : a00, nb ? b10 : a10);                                           \
+        wa1 = lerp1(fj[vj], nb ? b01 : a01, nb ? b11 : a11);                                           \
+        wb0 = lerp1(fj[vj], b00, b10); wb1 = lerp1(fj[vj], b01, b11);                                  \
+    }
+#define SDFC_TC3(vk) lerp1(fk[vk], ((mz >> (vk)) & 1u) ? wb0 : wa0, ((mz >> (vk)) & 1u) ? wb1 : wa1)
+    // ---- x variant 0: centre, y / z axis samples, yz diagonals
+    SDFC_TC1(0);
+    SDFC_TC2(0);
+    const double s0 = SDFC_TC3(0), s5 = SDFC_TC3(1), s6 = SDFC_TC3(2);
+    SDFC_TC2(1);
+    const double s3 = SDFC_TC3(0);
+    SDFC_TC2(2);
+    const double s4 = SDFC_TC3(0);
+    SDFC_TC2(3);
+    const double s15 = SDFC_TC3(3), s17 = SDFC_TC3(4);
+    SDFC_TC2(4);
+    const double s16 = SDFC_TC3(4), s18 = SDFC_TC3(3);
+    const double two_s0 = __dmul_rn(2.0, s0);
+    d = __dadd_rn(s0, col_th);
+    g[1] = exact_div(__dsub_rn(s3, s4), kTwoEps, kRTwoEps);
+    g[2] = exact_div(__dsub_rn(s5, s6), kTwoEps, kRTwoEps);
+    H[4] = exact_div(__dsub_rn(__dadd_rn(s3, s4), two_s0), kEps2, kREps2);
+    H[8] = exact_div(__dsub_rn(__dadd_rn(s5, s6), two_s0), kEps2, kREps2);
+    H[5] = H[7] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s15, s16), s17), s18), kEps2, kREps2);
+    // ---- x variants 1, 2: x axis samples
+    SDFC_TC1(1);
+    SDFC_TC2(0);
+    const double s1 = SDFC_TC3(0);
+    SDFC_TC1(2);
+    SDFC_TC2(0);
+    const double s2 = SDFC_TC3(0);
+    g[0] = exact_div(__dsub_rn(s1, s2), kTwoEps, kRTwoEps);
+    H[0] = exact_div(__dsub_rn(__dadd_rn(s1, s2), two_s0), kEps2, kREps2);
+    // ---- x variants 3, 4: xy and xz diagonals
+    SDFC_TC1(3);
+    SDFC_TC2(3);
+    const double s7 = SDFC_TC3(0);
+    SDFC_TC2(4);
+    const double s9 = SDFC_TC3(0);
+    SDFC_TC2(0);
+    const double s11 = SDFC_TC3(3), s13 = SDFC_TC3(4);
+    SDFC_TC1(4);
+    SDFC_TC2(4);
+    const double s8 = SDFC_TC3(0);
+    SDFC_TC2(3);
+    const double s10 = SDFC_TC3(0);
+    SDFC_TC2(0);
+    const double s12 = SDFC_TC3(4), s14 = SDFC_TC3(3);
+    H[1] = H[3] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s7, s8), s9), s10), kEps2, kREps2);
+    H[2] = H[6] = exact_div(__dsub_rn(__dsub_rn(__dadd_rn(s11, s12), s13), s14), kEps2, kREps2);
+#undef SDFC_TC1
+#undef SDFC_TC2
+#undef SDFC_TC3
 }
 
 // Must be called by all 32 lanes of a warp (uses a warp vote).
 // Three paths, all bit-identical to the reference's 26 query_SDF calls:
-//   * the stencil lies in one cell (almost always): stencil_reduce_on_cell;
-//   * it crosses one cell face along one axis: every sample is evaluated on its own cell (base or neighbour),
-//     sample by sample without sharing (133 lerps; ~0.1 % of the contacts, so the cost is irrelevant and the
-//     second cell does not inflate the register footprint of the common path);
+//   * the stencil of every lane lies in one cell (almost always with scanned meshes): stencil_reduce_on_cell;
+//   * some lane's stencil crosses one cell face along one axis (a vertex on a grid plane - common with the
+//     axis-aligned synthetic parts, where whole rows of vertices sit on cell faces): the whole warp takes
+//     stencil_reduce_two_cells, the lanes without a crossing with the neighbour set to the base cell;
 //   * anything else (outside the box, two crossings): the sample-by-sample generic sequence.
 template <bool F32>
 __device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3], double& d, double g[3], double H[9]) {
@@ -983,24 +1045,6 @@ __device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3],
     ok = axis_variants(x[2], G.mn[2], G.mx[2], G.dz, G.rdz, bk, ok_, fk, cz) && ok;
     ok = ok && (cx + cy + cz <= 1);
     const bool crossing = ok && (cx + cy + cz == 1);
-    // the rare paths come first: what only they need (cell offsets per variant, the second cell) is dead
-    // before the common path starts, and only copies have their address taken
-    if (__any_sync(0xffffffffu, crossing)) {
-        if (crossing) {
-            double cc[16], ff[15], dd, gg[3], HH[9];
-            int oo[15];
-            load_cell<F32>(G, bi, bj, bk, cc);
-            load_cell<F32>(G, bi + cx, bj + cy, bk + cz, cc + 8);
-#pragma unroll
-            for (int t = 0; t < 5; ++t) { ff[t] = fi[t]; ff[5 + t] = fj[t]; ff[10 + t] = fk[t]; oo[t] = oi[t]; oo[5 + t] = oj[t]; oo[10 + t] = ok_[t]; }
-            stencil_crossing(cc, cc + 8, ff, ff + 5, ff + 10, oo, oo + 5, oo + 10, G.col_th, &dd, gg, HH);
-            d = dd;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) g[t] = gg[t];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) H[t] = HH[t];
-        }
-    }
     if (!ok) {
         double xx[3] = {x[0], x[1], x[2]}, dd, gg[3], HH[9];
         sdf_stencil_generic<F32>(G, xx, dd, gg, HH);
@@ -1010,7 +1054,17 @@ __device__ __forceinline__ void sdf_stencil(const GridDev& G, const double x[3],
 #pragma unroll
         for (int t = 0; t < 9; ++t) H[t] = HH[t];
     }
-    if (ok && !crossing) {
+    if (__any_sync(0xffffffffu, crossing)) {
+        if (ok) {
+            unsigned mx = 0, my = 0, mz = 0;
+#pragma unroll
+            for (int v = 0; v < 5; ++v) { mx |= (unsigned)oi[v] << v; my |= (unsigned)oj[v] << v; mz |= (unsigned)ok_[v] << v; }
+            double c[8], c2[8];
+            load_cell<F32>(G, bi, bj, bk, c);
+            load_cell<F32>(G, bi + cx, bj + cy, bk + cz, c2);   // the base cell again for a lane without a crossing
+            stencil_reduce_two_cells(c, c2, fi, fj, fk, mx, my, mz, G.col_th, d, g, H);
+        }
+    } else if (ok) {
         double c[8];
         load_cell<F32>(G, bi, bj, bk, c);
         stencil_reduce_on_cell(c, fi, fj, fk, G.col_th, d, g, H);

@@ -628,13 +628,11 @@ __global__ void k_reduce_items(BatchDev B, int deriv, int dm, double* __restrict
 
 // Gather form of the reference's scatter (.cpp:60-61,88-99): one thread per system
 // entry walks the pairs in force order, so the accumulation order is the reference's.
-__global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict__ fm_sub,
-                                 const double* __restrict__ Km_sub, const double* __restrict__ Dm_sub,
-                                 double* __restrict__ fm, double* __restrict__ Km, double* __restrict__ Dm) {
-    const int env = blockIdx.x + B.env0;
+__device__ __forceinline__ void scatter_env(const BatchDev& B, int env, int deriv, const double* fm_sub, const double* Km_sub,
+                                            const double* Dm_sub, double* fm, double* Km, double* Dm, int tid, int nthreads) {
     const int nm = 6 * B.n_bodies;
     const size_t e0 = (size_t)env * B.n_pairs;
-    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+    for (int i = tid; i < nm; i += nthreads) {
         const int body = i / 6, r = i % 6;
         double s = 0.0;
         for (int p = 0; p < B.n_pairs; ++p) {
@@ -645,7 +643,7 @@ __global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict
         fm[(size_t)env * nm + i] = s;
     }
     if (!deriv) return;
-    for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) {
+    for (int i = tid; i < nm * nm; i += nthreads) {
         const int R = i % nm, C = i / nm;  // column-major
         const int bR = R / 6, r = R % 6, bC = C / 6, c = C % 6;
         double sk = 0.0, sd = 0.0;
@@ -665,10 +663,30 @@ __global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict
     }
 }
 
+__global__ void k_scatter_system(BatchDev B, int deriv, const double* __restrict__ fm_sub,
+                                 const double* __restrict__ Km_sub, const double* __restrict__ Dm_sub,
+                                 double* __restrict__ fm, double* __restrict__ Km, double* __restrict__ Dm) {
+    scatter_env(B, blockIdx.x + B.env0, deriv, fm_sub, Km_sub, Dm_sub, fm, Km, Dm, threadIdx.x, blockDim.x);
+}
+
+// Both steps in one launch, a CTA per environment: the pair blocks of the environment, then its system arrays.
+__global__ void __launch_bounds__(256) k_reduce_scatter(BatchDev B, int deriv, int dm, double* fm_sub, double* Km_sub, double* Dm_sub,
+                                                        double* fm, double* Km, double* Dm) {
+    const int env = blockIdx.x + B.env0;
+    for (int p = 0; p < B.n_pairs; ++p) reduce_items_one(B, env, p, deriv, dm, threadIdx.x, blockDim.x, fm_sub, Km_sub, Dm_sub);
+    __syncthreads();   // this CTA wrote the blocks it reads next
+    scatter_env(B, env, deriv, fm_sub, Km_sub, Dm_sub, fm, Km, Dm, threadIdx.x, blockDim.x);
+}
+
 void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub,
                            cudaStream_t stream) {
     dim3 grid(B.n_pairs, B.env_count);
     k_reduce_items<<<grid, 128, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub);
+}
+
+void launch_reduce_scatter(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub, double* fm,
+                           double* Km, double* Dm, cudaStream_t stream) {
+    k_reduce_scatter<<<B.env_count, 256, 0, stream>>>(B, deriv ? 1 : 0, dm ? 1 : 0, fm_sub, Km_sub, Dm_sub, fm, Km, Dm);
 }
 
 void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,

@@ -184,6 +184,9 @@ void launch_finalize_pairs(const BatchDev& B, bool deriv, bool dm, double* fm_su
 // Gathers the pair blocks into per-environment system arrays in force order
 // (overwrite): fm [env][6*n_bodies], Km / Dm [env][(6*n_bodies)^2] column-major.
 // Dm may be nullptr.
+// launch_finalize_pairs + launch_scatter_system in one kernel (a CTA per environment); B.env_mode must be nullptr
+void launch_reduce_scatter(const BatchDev& B, bool deriv, bool dm, double* fm_sub, double* Km_sub, double* Dm_sub, double* fm,
+                           double* Km, double* Dm, cudaStream_t stream);
 void launch_scatter_system(const BatchDev& B, bool deriv, const double* fm_sub, const double* Km_sub,
                            const double* Dm_sub, double* fm, double* Km, double* Dm, cudaStream_t stream);
 // Per-point outputs in ORIGINAL order for one pair, one environment.

@@ -962,7 +962,7 @@ def run_ours(args):
                                    "algorithmic_bytes_per_launch": q_rank * unit_b, "avg_launch_ms": det_ms,
                                    "share_of_step": det_ms / ms_step},
             "peaks_measured_live": live,
-            "kernels_ms": {"k_detect_mask": det_ms, "k_force": frc_ms, "k_reduce_items+k_scatter_system": red_ms,
+            "kernels_ms": {"k_detect_mask": det_ms, "k_force": frc_ms, "k_reduce_scatter": red_ms,
                            "step": ms_step},
             "env_evals_per_sec": world * scene.n_envs / (ms_max * 1e-3),
             "env_steps": env_steps,

@@ -2,7 +2,7 @@
 # round-2 GPU call 8: rolled column loop in the planner force kernel (instruction-cache footprint)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-T=${TAG:-r2n}
+T=${TAG:-r2o}
 timeout 900 python -m pytest tests/test_contact_gpu.py tests/test_parity_r2_gpu.py tests/test_sim_gpu.py tests/test_plugin_gpu.py -m gpu -q -x > gpurun_out/${T}_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_tests.log
 tail -3 gpurun_out/${T}_tests.log
 for lib in assemble-them-all_b200/libsdfcontact_b200.so; do
