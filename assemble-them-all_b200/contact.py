@@ -143,8 +143,9 @@ class SdfGrid:
 
     @property
     def layout(self):
-        """Device storage: "fp64", "records" (fp32 cell records) or "bricks" (fp32 4x4x4 bricks, TMA-staged)."""
-        return ("fp64", "records", "bricks")[int(self._lib.sdfc_sdf_layout_kind(self._h))]
+        """Device storage: "fp64", "records" (fp32 cell records), "bricks" (fp32 4x4x4 bricks, TMA-staged by
+        detection) or "bricks+records" (large grids: bricks for detection, records for per-point gathers)."""
+        return ("fp64", "records", "bricks", "bricks+records")[int(self._lib.sdfc_sdf_layout_kind(self._h))]
 
     def set_col_th(self, col_th):
         self.col_th = float(col_th)

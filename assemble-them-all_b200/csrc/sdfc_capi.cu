@@ -375,10 +375,16 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
     // fp32-lossless grids: cell records (32 B per cell, one sector per query) while they stay cache-resident,
     // bricks (4 B per node, staged per tile with TMA) for grids whose records would be several times the L2.
     // SDFC_GRID_LAYOUT = records | bricks overrides the size rule.
+    // Large grids keep BOTH while the records fit a budget (6 GiB; 512^3 = 4.3 GB of the 180 GB): detection
+    // stages bricks, every per-point gather (SDFMesh::distance on caller-ordered points, the force stencil, tiles
+    // whose brick region is too large for shared memory) reads one 32-byte record instead of 2-4 brick sectors.
+    // SDFC_GRID_LAYOUT = records | bricks | both overrides the size rule.
     bool want_bricks = s->count * 32 > ((size_t)96 << 20);
+    bool want_records = !want_bricks || s->count * 32 <= ((size_t)6 << 30);
     if (const char* lay = std::getenv("SDFC_GRID_LAYOUT")) {
-        if (std::string(lay) == "bricks") want_bricks = true;
-        else if (std::string(lay) == "records") want_bricks = false;
+        if (std::string(lay) == "bricks") { want_bricks = true; want_records = false; }
+        else if (std::string(lay) == "records") { want_bricks = false; want_records = true; }
+        else if (std::string(lay) == "both") { want_bricks = true; want_records = true; }
     }
     const int nbx = (ni + 1 + 3) / 4, nby = (nj + 1 + 3) / 4, nbz = (nk + 1 + 3) / 4;   // + 1: replicated node layer
     if (e == cudaSuccess && lossless && want_bricks) {
@@ -426,7 +432,8 @@ sdfc_status sdfc_sdf_create(sdfc_context* ctx, int ni, int nj, int nk, const dou
             cudaFree(s->d_tmaps); s->d_tmaps = nullptr;
         }
         cudaFree(d_g32);
-    } else if (e == cudaSuccess && lossless) {
+    }
+    if (e == cudaSuccess && lossless && want_records) {
         float* d_g32 = nullptr;
         // cell records need 8x the plain fp32 grid; if that does not fit, stay on the fp64 path
         if (cudaMalloc((void**)&d_g32, s->count * sizeof(float)) == cudaSuccess &&
@@ -495,7 +502,7 @@ sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th) {
     return SDFC_OK;
 }
 int sdfc_sdf_is_fp32(const sdfc_sdf* sdf) { return (sdf && (sdf->d_c32 || sdf->d_b32)) ? 1 : 0; }
-int sdfc_sdf_layout_kind(const sdfc_sdf* sdf) { return !sdf ? -1 : (sdf->d_b32 ? 2 : (sdf->d_c32 ? 1 : 0)); }
+int sdfc_sdf_layout_kind(const sdfc_sdf* sdf) { return !sdf ? -1 : (sdf->d_b32 ? (sdf->d_c32 ? 3 : 2) : (sdf->d_c32 ? 1 : 0)); }
 sdfc_status sdfc_sdf_destroy(sdfc_sdf* s) {
     if (!s) return SDFC_OK;
     cudaSetDevice(s->ctx->device);

