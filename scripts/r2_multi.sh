@@ -4,6 +4,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 T=r2p
+if [ -z "$SKIP_BENCH" ]; then
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/${T}_bench_n$N.json 2> gpurun_out/${T}_bench_n$N.err; echo "bench rc=$?"; tail -2 gpurun_out/${T}_bench_n$N.err
 python - <<PY
 import json
@@ -13,6 +14,7 @@ es = d['env_steps']; print('env_steps', es['value'], es['ms_per_forward'])
 for k in ('c2_strong_scaling', 'c4_candidate_removals'):
     x = d.get(k, {}); print(k, x.get('value'), x.get('ms_per_stage'), x.get('ms_per_forward'), x.get('scaling'))
 PY
+fi
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench_sweep.py --points ${POINTS:-1e4,1e5,1e6,1e7,1e8} --grids ${GRIDS:-64,128,256,512} --reps 5 --out gpurun_out/${T}_sweep_n$N.jsonl > gpurun_out/${T}_sweep_n$N.log 2>&1; echo "sweep rc=$?"
 python - <<PY
 import json
