@@ -169,18 +169,20 @@ sdfc_status batch_run_stepper(sdfc_batch* b, const double* E_dev, const double* 
 sdfc_status batch_ensure_plan_slots(sdfc_batch* b, int n) {
     if (n > sdfc_batch::kMaxPlanSlots) return fail(SDFC_ERR_INVALID, "batch_ensure_plan_slots: too many concurrent evaluations");
     const size_t ep = (size_t)b->n_envs * b->n_pairs;
-    int g_min = 1;
-    if (const char* g = std::getenv("SDFC_FORCE_G")) g_min = std::max(1, std::atoi(g));
+    // smallest number of 32-contact rounds per item: SDFC_FORCE_G (both lists), SDFC_FORCE_GV (value-only list)
+    int g_min = 1, g_min_value = 1;
+    if (const char* g = std::getenv("SDFC_FORCE_G")) g_min = g_min_value = std::max(1, std::atoi(g));
+    if (const char* g = std::getenv("SDFC_FORCE_GV")) g_min_value = std::max(1, std::atoi(g));
     for (; b->n_plan_slots < n; ++b->n_plan_slots) {
         for (int m = 0; m < 2; ++m) {
             ForcePlanDev& P = b->plan_slot[b->n_plan_slots][m];
-            P.cap = b->plan_cap; P.stride = m ? kPartialDerivDM : kPartialValue; P.g_min = g_min;
+            P.cap = b->plan_cap; P.stride = m ? kPartialDerivDM : kPartialValue; P.g_min = m ? g_min : g_min_value;
             sdfc_status st = dev_alloc(&P.items, (size_t)P.cap * 2);
             if (st == SDFC_OK) st = dev_alloc(&P.pair_item0, ep);
             if (st == SDFC_OK) st = dev_alloc(&P.hdr, (size_t)4);
             if (st == SDFC_OK) st = dev_alloc(&P.partial, (size_t)P.cap * P.stride);
             if (st != SDFC_OK) return st;
-            const int hdr0[4] = {0, 0, 0, g_min};
+            const int hdr0[4] = {0, 0, 0, P.g_min};
             SDFC_CUDA(cudaMemcpy(P.hdr, hdr0, sizeof(hdr0), cudaMemcpyHostToDevice));
         }
     }
@@ -899,7 +901,9 @@ sdfc_status sdfc_batch_create(sdfc_context* ctx, int n_envs, int n_bodies, int n
     // capacity of the force work lists: one item per 32-contact round while they fit, every pair gets at least one
     {
         const int64_t rounds_possible = (int64_t)words * n_envs;
-        b->plan_cap = (int)std::min<int64_t>((int64_t)1 << 30, std::min<int64_t>(16384, std::max<int64_t>(1024, rounds_possible)) + (int64_t)n_envs * n_pairs);
+        int64_t base = std::min<int64_t>(16384, std::max<int64_t>(1024, rounds_possible));
+        if (const char* c = std::getenv("SDFC_FORCE_CAP")) base = std::max(1, std::atoi(c));   // tests: small lists, G > 1
+        b->plan_cap = (int)std::min<int64_t>((int64_t)1 << 30, base + (int64_t)n_envs * n_pairs);
     }
     const size_t ep = (size_t)n_envs * n_pairs;
     const int nm = 6 * n_bodies;

@@ -37,6 +37,13 @@ def run(lanes, tail, n_envs, joint_type, n_vertices=10000):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    if len(sys.argv) > 2 and sys.argv[2] == "gv":   # rounds per item of the value-only force list
+        for jt in ("translational", "free3d-exp"):
+            for gv in ("1", "2", "4", "8"):
+                os.environ["SDFC_FORCE_GV"] = gv
+                ms, chk = run("2", None, n, jt)
+                print(f"{jt:14s} SDFC_FORCE_GV={gv}: {ms:8.2f} ms  ({n * 100 / ms * 1e3:,.0f} env-steps/s) checksum {chk:.12e}", flush=True)
+        sys.exit(0)
     for jt in ("translational", "free3d-exp"):
         for tail in ("0", None, "100000"):
             for lanes in ("1", "2", "3", "4"):

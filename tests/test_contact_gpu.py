@@ -183,6 +183,37 @@ def test_against_oracle_on_analytic_sphere(cuda_ctx, mu, damping):
     pair.close(); cp.close(); sdf.close()
 
 
+@pytest.mark.parametrize("knobs", [{"SDFC_FORCE_G": "4"}, {"SDFC_FORCE_CAP": "4"}, {"SDFC_FORCE_CAP": "1", "SDFC_FORCE_G": "3"}])
+@pytest.mark.parametrize("mu,damping", [(0.0, 0.0), (0.5, 10.0)])
+def test_force_work_list_with_grouped_rounds(cuda_ctx, monkeypatch, knobs, mu, damping):
+    """The force kernels' work list when one item holds several 32-contact rounds: G forced up by a larger
+    minimum (SDFC_FORCE_G) or by a list capacity the evaluation overflows (SDFC_FORCE_CAP, read when the
+    batch is created). Same contacts, other grouping of the partial sums: the oracle bar, not bit equality."""
+    from assemble_them_all_b200 import contact, synth
+    from oracle import sdfc_oracle as O
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(7)
+    spec, pts = _oracle_scene(rng, 9000, 64, col_th=0.02)
+    og = O.Grid.from_spec(spec)
+    sdf = contact.SdfGrid.from_spec(cuda_ctx, spec)
+    cp = contact.ContactPoints(cuda_ctx, pts)
+    pair = contact.ForceGeneralSDFContact(cuda_ctx, cp, sdf, 1e5, 1e3, mu, damping)
+    for trial in range(2):
+        E1 = synth.make_E(synth.random_rotation(rng), rng.uniform(-0.3, 0.3, 3))
+        E2 = synth.make_E(synth.random_rotation(rng), rng.uniform(-0.3, 0.3, 3))
+        phi1, phi2 = rng.normal(size=6), rng.normal(size=6)
+        fm, Km, Dm, cnt = O.pair_force(og, E1, phi1, E2, phi2, pts, 1e5, 1e3, mu, damping, True)
+        assert cnt[0] > 700   # more than 20 rounds
+        gfm, gKm, gDm, n = pair.force_deriv_sub(E1, phi1, E2, phi2)
+        assert n == cnt[0]
+        assert_close(fm, gfm, "fm"); assert_close(Km, gKm, "Km"); assert_close(Dm, gDm, "Dm")
+        fmv, _, _, _ = O.pair_force(og, E1, phi1, E2, phi2, pts, 1e5, 1e3, mu, damping, False)
+        gfmv, _ = pair.force_sub(E1, phi1, E2, phi2)
+        assert_close(fmv, gfmv, "fm (value)")
+    pair.close(); cp.close(); sdf.close()
+
+
 def test_fp64_grid_storage_path(cuda_ctx):
     """Grids that are not fp32-representable (reloaded .sdf text caches,
     BodySDFObj.cpp:86-103) stay fp64 and still match the oracle bit for bit."""
