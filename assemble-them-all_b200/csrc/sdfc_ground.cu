@@ -391,6 +391,8 @@ static sdfc_status ground_set_refresh(sdfc_ground_set* s) {
     return SDFC_OK;
 }
 
+sdfc_status ground_set_prepare(sdfc_ground_set* s) { return ground_set_refresh(s); }
+
 // deriv / env_mode_dev as in batch_run. Results stay in the set's buffers.
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
                            const int* env_mode_dev, int env0, int env_count, cudaStream_t stream_override,

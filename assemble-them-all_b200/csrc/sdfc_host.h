@@ -134,6 +134,11 @@ struct sdfc_batch {
     double* h_in = nullptr;   // pinned: E then phi
     double* h_out = nullptr;  // pinned: fm, Km, Dm
     int32_t* h_nact = nullptr;
+    // the evaluation sequence of batch_run as a CUDA graph (captured at the second call with the same signature)
+    cudaGraphExec_t run_graph = nullptr;
+    uint64_t run_graph_key = 0, run_pending_key = 0;
+    int64_t run_graph_launches = 0;
+    bool run_graph_ok = true;
     double* h_blocks = nullptr;   // pinned: per-pair / per-ground blocks of sdfc_batch_eval_blocks
     size_t h_blocks_bytes = 0;
     // optional temporal-coherence culling of the detection kernel (BatchDev::skin_*), switched on by the stepper
@@ -173,6 +178,9 @@ namespace sdfc_host {
 sdfc_status ground_set_create(sdfc_context* ctx, int n_envs, int n_bodies, int n, sdfc_ground* const* grounds,
                               const int32_t* body, sdfc_ground_set** out);
 void ground_set_destroy(sdfc_ground_set* s);
+// Uploads the ground table if parameters changed (ground_set_run does it on every call; separately callable so that
+// the upload - which synchronises - happens before a stream capture).
+sdfc_status ground_set_prepare(sdfc_ground_set* s);
 sdfc_status ground_set_run(sdfc_ground_set* s, const double* E_dev, const double* phi_dev, int deriv,
                            const int* env_mode_dev, int env0, int env_count, cudaStream_t stream_override = nullptr,
                            bool counts_zeroed = false);

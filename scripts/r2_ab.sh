@@ -6,5 +6,5 @@ for lib in assemble-them-all_b200/libsdfcontact_b200.so tune_libs/*.so; do
   SDFC_LIB_PATH=$PWD/$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --skip-env-steps > gpurun_out/ab_$(basename $lib .so).json 2>/dev/null
   python -c "
 import json,sys
-d=json.load(open('gpurun_out/ab_$(basename $lib .so).json')); print('$lib', round(d['ms_per_step'],4), {k: round(v,4) for k,v in d['kernels_ms'].items()})"
+d=json.load(open('gpurun_out/ab_$(basename $lib .so).json')); print('$lib', round(d['ms_per_step'],4), {k: (round(v,4) if isinstance(v, float) else '') for k,v in d['kernels_ms'].items() if k != 'note'})"
 done
