@@ -84,8 +84,8 @@ static sdfc_status batch_run_body(sdfc_batch* b, const double* E_dev, const doub
 
 // One evaluation = a fixed sequence of 3 memsets and 4 - 8 small kernels: launched one by one, a third of a short
 // evaluation (the per-substep call of the plug-in path, a 1024-rollout bench step) is launch gaps. The second
-// call with the same signature (buffers, flags, kernel variants) captures the sequence into a CUDA graph; every
-// later one replays it. Parameter changes go through the pair / ground tables in device memory (refreshed
+// call with a signature (buffers, flags, kernel variants) captures the sequence into a CUDA graph; every later one
+// replays it (up to 4 signatures per batch: value-only and derivative evaluations alternate). Parameter changes go through the pair / ground tables in device memory (refreshed
 // before the graph runs), so they do not invalidate it. SDFC_RUN_GRAPH=0 switches the replay off; per-kernel
 // timing (sdfc_context_enable_timing) bypasses it.
 sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
@@ -113,17 +113,25 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
         if (key == 0) key = 1;
     }
     cudaStream_t s = c->stream;
-    if (b->run_graph != nullptr && b->run_graph_key == key) {
-        SDFC_CUDA(cudaGraphLaunch(b->run_graph, s));
-        c->launches += b->run_graph_launches;
-        return SDFC_OK;
-    }
-    if (b->run_pending_key != key) {   // first sighting of this signature: plain launches
-        b->run_pending_key = key;
+    b->run_clock += 1;
+    for (auto& rg : b->run_graphs)
+        if (rg.exec != nullptr && rg.key == key) {
+            SDFC_CUDA(cudaGraphLaunch(rg.exec, s));
+            rg.last_use = b->run_clock;
+            c->launches += rg.launches;
+            return SDFC_OK;
+        }
+    bool seen = false;
+    for (uint64_t k : b->run_seen) seen = seen || k == key;
+    if (!seen) {   // first sighting of this signature: plain launches, remembered
+        b->run_seen[b->run_clock % sdfc_batch::kRunGraphs] = key;
         return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
     }
-    // second call in a row with this signature: capture, instantiate, launch
-    if (b->run_graph) { cudaGraphExecDestroy(b->run_graph); b->run_graph = nullptr; }
+    // second sighting: capture, instantiate (into the least recently used slot), launch
+    sdfc_batch::RunGraph* slot = &b->run_graphs[0];
+    for (auto& rg : b->run_graphs)
+        if (rg.exec == nullptr || rg.last_use < slot->last_use) { slot = &rg; if (rg.exec == nullptr) break; }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
     const int64_t launches0 = c->launches;
     cudaGraph_t g = nullptr;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
@@ -135,17 +143,18 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     const cudaError_t ce = cudaStreamEndCapture(s, &g);
     const int64_t n_launch = c->launches - launches0;
     c->launches = launches0;
-    if (st != SDFC_OK || ce != cudaSuccess || g == nullptr || cudaGraphInstantiate(&b->run_graph, g, 0) != cudaSuccess) {
+    if (st != SDFC_OK || ce != cudaSuccess || g == nullptr || cudaGraphInstantiate(&slot->exec, g, 0) != cudaSuccess) {
         cudaGetLastError();
         if (g) cudaGraphDestroy(g);
-        b->run_graph = nullptr;
+        slot->exec = nullptr;
         b->run_graph_ok = false;   // this batch stays on plain launches
         return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
     }
     cudaGraphDestroy(g);
-    b->run_graph_key = key;
-    b->run_graph_launches = n_launch;
-    SDFC_CUDA(cudaGraphLaunch(b->run_graph, s));
+    slot->key = key;
+    slot->launches = n_launch;
+    slot->last_use = b->run_clock;
+    SDFC_CUDA(cudaGraphLaunch(slot->exec, s));
     c->launches += n_launch;
     return SDFC_OK;
 }
@@ -1039,7 +1048,7 @@ sdfc_status sdfc_batch_destroy(sdfc_batch* b) {
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_blocks) cudaFreeHost(b->h_blocks);
-    if (b->run_graph) cudaGraphExecDestroy(b->run_graph);
+    for (auto& rg : b->run_graphs) if (rg.exec) cudaGraphExecDestroy(rg.exec);
     if (b->h_nact) cudaFreeHost(b->h_nact);
     sdfc_host::ground_set_destroy(b->gset);
     delete b;
@@ -1210,7 +1219,7 @@ sdfc_status sdfc_batch_eval_blocks(sdfc_batch* b, const double* E_host, const do
     const size_t bytes = n_dbl * sizeof(double) + (ep + eg) * sizeof(int32_t);
     if (b->h_blocks_bytes < bytes) {
         if (b->h_blocks) cudaFreeHost(b->h_blocks);
-    if (b->run_graph) cudaGraphExecDestroy(b->run_graph);
+    for (auto& rg : b->run_graphs) if (rg.exec) cudaGraphExecDestroy(rg.exec);
         b->h_blocks = nullptr; b->h_blocks_bytes = 0;
         SDFC_CUDA(cudaMallocHost((void**)&b->h_blocks, bytes));
         b->h_blocks_bytes = bytes;

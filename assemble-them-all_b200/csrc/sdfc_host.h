@@ -135,9 +135,11 @@ struct sdfc_batch {
     double* h_out = nullptr;  // pinned: fm, Km, Dm
     int32_t* h_nact = nullptr;
     // the evaluation sequence of batch_run as a CUDA graph (captured at the second call with the same signature)
-    cudaGraphExec_t run_graph = nullptr;
-    uint64_t run_graph_key = 0, run_pending_key = 0;
-    int64_t run_graph_launches = 0;
+    static constexpr int kRunGraphs = 4;   // e.g. value-only and derivative evaluations alternate on the plug-in path
+    struct RunGraph { cudaGraphExec_t exec = nullptr; uint64_t key = 0; int64_t launches = 0; uint64_t last_use = 0; };
+    RunGraph run_graphs[kRunGraphs];
+    uint64_t run_seen[kRunGraphs] = {0, 0, 0, 0};   // signatures seen once (launched plainly), next sighting captures
+    uint64_t run_clock = 0;
     bool run_graph_ok = true;
     double* h_blocks = nullptr;   // pinned: per-pair / per-ground blocks of sdfc_batch_eval_blocks
     size_t h_blocks_bytes = 0;
