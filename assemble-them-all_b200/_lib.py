@@ -130,6 +130,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
         fn.restype = res
         fn.argtypes = args
+    # the same entry with untyped pointer arguments: callers that already hold addresses (PinnedArray.ptr) skip the
+    # per-call construction of typed ctypes pointers (several microseconds each)
+    proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+    lib.sdfc_batch_eval_addr = proto(("sdfc_batch_eval", lib))
     _lib = lib
     return lib
 

@@ -52,6 +52,7 @@ class PinnedArray:
         check(self._lib.sdfc_pinned_alloc(n, C.byref(self._p)))
         buf = (C.c_char * max(n, 1)).from_address(self._p.value)
         self.a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        self.ptr = int(self._p.value)   # address of a[0]: eval_into takes it without building a ctypes pointer
 
     def close(self):
         if self._p:
@@ -486,10 +487,11 @@ class ContactBatch:
     def eval_into(self, E_col, phi, deriv, fm, Km, Dm, nact=None):
         """The host-buffer C-ABI call without any Python-side copies: E_col is
         (n_envs, n_bodies, 16) COLUMN-major poses, outputs are written in the library's
-        layout (Km, Dm column-major per environment). Pass PinnedArray buffers for direct DMA."""
-        check(self._lib.sdfc_batch_eval(self._h, _dp(E_col), _dp(phi), int(bool(deriv)), _dp(fm),
-                                        _dp(Km) if deriv else None, _dp(Dm) if deriv else None,
-                                        nact.ctypes.data_as(_lib.c_int32_p) if nact is not None else None))
+        layout (Km, Dm column-major per environment). Pass PinnedArray objects (or their `.a` views) for direct DMA."""
+        def addr(x):   # PinnedArray: its stored address; numpy array: looked up
+            return x.ptr if isinstance(x, PinnedArray) else (None if x is None else x.ctypes.data)
+        check(self._lib.sdfc_batch_eval_addr(self._h, addr(E_col), addr(phi), int(bool(deriv)), addr(fm),
+                                             addr(Km) if deriv else None, addr(Dm) if deriv else None, addr(nact)))
 
     def eval_device(self, E_ptr, phi_ptr, deriv, fm_ptr, Km_ptr, Dm_ptr, nact_ptr):
         """Raw device pointers (ints). E is column-major per pose. Asynchronous."""

@@ -82,6 +82,63 @@ static sdfc_status batch_run_body(sdfc_batch* b, const double* E_dev, const doub
                                   bool scatter, double* fm_dev, double* Km_dev, double* Dm_dev, int32_t* n_active_dev, int env0,
                                   int env_count, bool counts_zeroed);
 
+// Runs `body` (which issues work on the context's stream, possibly forking to other streams and joining back):
+// plainly at the first sighting of `key`, captured into a CUDA graph at the second, replayed afterwards.
+template <class Body>
+static sdfc_status run_graphed(sdfc_batch* b, uint64_t key, Body&& body) {
+    sdfc_context* c = b->ctx;
+    cudaStream_t s = c->stream;
+    b->run_clock += 1;
+    for (auto& rg : b->run_graphs)
+        if (rg.exec != nullptr && rg.key == key) {
+            SDFC_CUDA(cudaGraphLaunch(rg.exec, s));
+            rg.last_use = b->run_clock;
+            c->launches += rg.launches;
+            return SDFC_OK;
+        }
+    bool seen = false;
+    for (uint64_t k : b->run_seen) seen = seen || k == key;
+    if (!seen) {   // first sighting of this signature: plain launches, remembered
+        b->run_seen[b->run_clock % sdfc_batch::kRunGraphs] = key;
+        return body();
+    }
+    // second sighting: capture, instantiate (into the least recently used slot), launch
+    sdfc_batch::RunGraph* slot = &b->run_graphs[0];
+    for (auto& rg : b->run_graphs)
+        if (rg.exec == nullptr || rg.last_use < slot->last_use) { slot = &rg; if (rg.exec == nullptr) break; }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    const int64_t launches0 = c->launches;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        b->run_graph_ok = false;
+        return body();
+    }
+    sdfc_status st = body();
+    const cudaError_t ce = cudaStreamEndCapture(s, &g);
+    const int64_t n_launch = c->launches - launches0;
+    c->launches = launches0;
+    if (st != SDFC_OK || ce != cudaSuccess || g == nullptr || cudaGraphInstantiate(&slot->exec, g, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        slot->exec = nullptr;
+        b->run_graph_ok = false;   // this batch stays on plain launches
+        return body();
+    }
+    cudaGraphDestroy(g);
+    slot->key = key;
+    slot->launches = n_launch;
+    slot->last_use = b->run_clock;
+    SDFC_CUDA(cudaGraphLaunch(slot->exec, s));
+    c->launches += n_launch;
+    return SDFC_OK;
+}
+
+static bool run_graphs_enabled(const sdfc_batch* b) {
+    static const bool on = [] { const char* e = std::getenv("SDFC_RUN_GRAPH"); return !(e && std::atoi(e) == 0); }();
+    return on && !b->ctx->timing && b->run_graph_ok;
+}
+
 // One evaluation = a fixed sequence of 3 memsets and 4 - 8 small kernels: launched one by one, a third of a short
 // evaluation (the per-substep call of the plug-in path, a 1024-rollout bench step) is launch gaps. The second
 // call with a signature (buffers, flags, kernel variants) captures the sequence into a CUDA graph; every later one
@@ -99,8 +156,7 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
     }
     if (env_count < 0) { env0 = 0; env_count = b->n_envs; }
     sdfc_context* c = b->ctx;
-    static const bool graphs_on = [] { const char* e = std::getenv("SDFC_RUN_GRAPH"); return !(e && std::atoi(e) == 0); }();
-    if (!graphs_on || c->timing || !b->run_graph_ok)
+    if (!run_graphs_enabled(b))
         return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
     uint64_t key = 1469598103934665603ull;
     {
@@ -112,51 +168,9 @@ sdfc_status batch_run(sdfc_batch* b, const double* E_dev, const double* phi_dev,
         for (uint64_t v : parts) { key ^= v; key *= 1099511628211ull; }
         if (key == 0) key = 1;
     }
-    cudaStream_t s = c->stream;
-    b->run_clock += 1;
-    for (auto& rg : b->run_graphs)
-        if (rg.exec != nullptr && rg.key == key) {
-            SDFC_CUDA(cudaGraphLaunch(rg.exec, s));
-            rg.last_use = b->run_clock;
-            c->launches += rg.launches;
-            return SDFC_OK;
-        }
-    bool seen = false;
-    for (uint64_t k : b->run_seen) seen = seen || k == key;
-    if (!seen) {   // first sighting of this signature: plain launches, remembered
-        b->run_seen[b->run_clock % sdfc_batch::kRunGraphs] = key;
+    return run_graphed(b, key, [&]() {
         return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
-    }
-    // second sighting: capture, instantiate (into the least recently used slot), launch
-    sdfc_batch::RunGraph* slot = &b->run_graphs[0];
-    for (auto& rg : b->run_graphs)
-        if (rg.exec == nullptr || rg.last_use < slot->last_use) { slot = &rg; if (rg.exec == nullptr) break; }
-    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-    const int64_t launches0 = c->launches;
-    cudaGraph_t g = nullptr;
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
-        cudaGetLastError();
-        b->run_graph_ok = false;
-        return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
-    }
-    st = batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
-    const cudaError_t ce = cudaStreamEndCapture(s, &g);
-    const int64_t n_launch = c->launches - launches0;
-    c->launches = launches0;
-    if (st != SDFC_OK || ce != cudaSuccess || g == nullptr || cudaGraphInstantiate(&slot->exec, g, 0) != cudaSuccess) {
-        cudaGetLastError();
-        if (g) cudaGraphDestroy(g);
-        slot->exec = nullptr;
-        b->run_graph_ok = false;   // this batch stays on plain launches
-        return batch_run_body(b, E_dev, phi_dev, deriv, env_mode_dev, scatter, fm_dev, Km_dev, Dm_dev, n_active_dev, env0, env_count, counts_zeroed);
-    }
-    cudaGraphDestroy(g);
-    slot->key = key;
-    slot->launches = n_launch;
-    slot->last_use = b->run_clock;
-    SDFC_CUDA(cudaGraphLaunch(slot->exec, s));
-    c->launches += n_launch;
-    return SDFC_OK;
+    });
 }
 
 static sdfc_status batch_run_body(sdfc_batch* b, const double* E_dev, const double* phi_dev, int deriv, const int* env_mode_dev,
@@ -1144,9 +1158,20 @@ sdfc_status sdfc_batch_get_active(sdfc_batch* b, int env, int pair, uint8_t* act
 }
 
 static bool is_pinned(const void* p) {
+    // the callers pass the same few buffers again and again: the last answers are remembered per thread (a stale
+    // "pinned" is harmless: cudaMemcpyAsync stages pageable memory itself; a stale "pageable" costs a staging copy)
+    struct Entry { const void* p; bool pinned; };
+    thread_local Entry cache[8] = {};
+    thread_local int next = 0;
+    for (const Entry& e : cache)
+        if (e.p == p && p != nullptr) return e.pinned;
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) cudaGetLastError();
+    else pinned = a.type == cudaMemoryTypeHost;
+    cache[next] = Entry{p, pinned};
+    next = (next + 1) % 8;
+    return pinned;
 }
 
 sdfc_status sdfc_pinned_alloc(size_t bytes, void** out) {
@@ -1175,15 +1200,19 @@ sdfc_status sdfc_batch_eval(sdfc_batch* b, const double* E_host, const double* p
     const double* srcP = phi_host;
     if (!is_pinned(E_host)) { std::memcpy(b->h_in, E_host, nE * sizeof(double)); srcE = b->h_in; }
     if (!is_pinned(phi_host)) { std::memcpy(b->h_in + nE, phi_host, nP * sizeof(double)); srcP = b->h_in + nE; }
+    // without friction, damping and ground contact Dm is identically zero
+    // (ForceGeneralSDFContact.cpp:352-445 is skipped): filled on the host, no transfer
+    {
+        sdfc_status pr = batch_refresh(b);   // any_fric / any_damp follow the pairs' current parameters
+        if (pr != SDFC_OK) return pr;
+    }
+    const bool dm_zero = deriv && !b->any_fric && !b->any_damp && b->gset == nullptr;
+    const bool pf = is_pinned(fm_out), pk = deriv && is_pinned(Km_out), pd = deriv && is_pinned(Dm_out);
+    const bool pa = n_active_out && is_pinned(n_active_out);
     SDFC_CUDA(cudaMemcpyAsync(b->d_E, srcE, nE * sizeof(double), cudaMemcpyHostToDevice, s));
     SDFC_CUDA(cudaMemcpyAsync(b->d_phi, srcP, nP * sizeof(double), cudaMemcpyHostToDevice, s));
     sdfc_status st = batch_run(b, b->d_E, b->d_phi, deriv, nullptr, /*scatter=*/true, b->d_fm, b->d_Km, deriv ? b->d_Dm : nullptr, nullptr);
     if (st != SDFC_OK) return st;
-    // without friction, damping and ground contact Dm is identically zero
-    // (ForceGeneralSDFContact.cpp:352-445 is skipped): filled on the host, no transfer
-    const bool dm_zero = deriv && !b->any_fric && !b->any_damp && b->gset == nullptr;
-    const bool pf = is_pinned(fm_out), pk = deriv && is_pinned(Km_out), pd = deriv && is_pinned(Dm_out);
-    const bool pa = n_active_out && is_pinned(n_active_out);
     SDFC_CUDA(cudaMemcpyAsync(pf ? fm_out : b->h_out, b->d_fm, nF * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (deriv) {
         SDFC_CUDA(cudaMemcpyAsync(pk ? Km_out : b->h_out + nF, b->d_Km, nK * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -874,7 +874,7 @@ def run_ours(args):
     pin["phi"].a[:] = scene.phi
 
     def e2e_step():
-        batch.eval_into(pin["E"].a, pin["phi"].a, True, pin["fm"].a, pin["Km"].a, pin["Dm"].a, pin["na"].a)
+        batch.eval_into(pin["E"], pin["phi"], True, pin["fm"], pin["Km"], pin["Dm"], pin["na"])
 
     for _ in range(3):
         e2e_step()
