@@ -369,11 +369,11 @@ __device__ __forceinline__ void force_item(const ForceWarpShared<NF>& S, const u
 #define SDFC_FORCE_NF_MIN_BLOCKS 3  // planner fast path: 168 registers, 12 warps / SM
 #endif
 #ifndef SDFC_FORCE_VALUE_MIN_BLOCKS
-#define SDFC_FORCE_VALUE_MIN_BLOCKS 4  // value-only kernels (line-search evaluations): 128 registers, 240 B of spills; 50.3 -> 47.6 ms per forward(100) of C2
+#define SDFC_FORCE_VALUE_MIN_BLOCKS 4  // value-only kernel without friction / damping (line-search evaluations): 128 registers, 240 B of spills; 50.3 -> 47.6 ms per forward(100) of C2
 #endif
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
 constexpr int force_min_blocks() {
-    return !DERIV ? SDFC_FORCE_VALUE_MIN_BLOCKS : ((!ANYFRIC && !ANYDAMP) ? SDFC_FORCE_NF_MIN_BLOCKS : SDFC_FORCE_MIN_BLOCKS);
+    return (ANYFRIC || ANYDAMP) ? SDFC_FORCE_MIN_BLOCKS : (DERIV ? SDFC_FORCE_NF_MIN_BLOCKS : SDFC_FORCE_VALUE_MIN_BLOCKS);
 }
 
 template <bool DERIV, bool ANYFRIC, bool ANYDAMP>
