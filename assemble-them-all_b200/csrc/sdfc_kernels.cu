@@ -174,7 +174,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     int cnt = 0;
     // software pipeline: the coordinates of the warp's next group are requested before the current group is
     // evaluated, so a warp never sits on an exposed global load between two words
-    constexpr int kStep = (kDetectThreads / 32) * U;
+    const int kStep = (int)(blockDim.x >> 5) * U;   // warps of this CTA x words in flight per warp
     int nws[U];
     double npx[U], npy[U], npz[U];
     bool ninr[U];
@@ -232,7 +232,9 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
 // SKIN = false is the plain kernel (every batch evaluation outside the stepper); SKIN = true adds the
 // stepper's margin test / margin rebuild, compiled out of the plain instantiation.
 template <bool SKIN>
-__global__ void __launch_bounds__(kDetectThreads, SDFC_DETECT_MIN_BLOCKS) k_detect_mask(BatchDev B, const double* __restrict__ E) {
+__global__ void __launch_bounds__(SKIN ? kDetectThreadsSkin : kDetectThreadsPlain,
+                                  SDFC_DETECT_MIN_BLOCKS * kDetectThreads / (SKIN ? kDetectThreadsSkin : kDetectThreadsPlain))
+    k_detect_mask(BatchDev B, const double* __restrict__ E) {
     __shared__ PairDev pd;
     __shared__ double R1[9], p1[3], R2[9], p2[3];
     __shared__ int s_count;
@@ -498,8 +500,8 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
         k_detect_brick<<<grid, kDetectThreads, B.brick_cap + 128, stream>>>(B, E);
         return;
     }
-    if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreads, 0, stream>>>(B, E);
-    else k_detect_mask<false><<<grid, kDetectThreads, 0, stream>>>(B, E);
+    if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreadsSkin, 0, stream>>>(B, E);
+    else k_detect_mask<false><<<grid, kDetectThreadsPlain, 0, stream>>>(B, E);
 }
 
 // --------------------------------------------------------------------------

@@ -40,9 +40,22 @@ struct PairDev {
 #endif
 constexpr int kNumWarps = SDFC_FORCE_WARPS;   // force kernel: warps per CTA
 constexpr int kForceThreads = 32 * kNumWarps;
-constexpr int kDetectThreads = 256;
-constexpr int kDetectWordsPerWarp = 8; // 256 points per warp per tile (2048 per CTA)
-constexpr int kDetectTileWords = (kDetectThreads / 32) * kDetectWordsPerWarp;
+constexpr int kDetectThreads = 256;     // widest detection CTA (plain and brick kernels)
+constexpr int kDetectTileWords = 64;    // mask words (2048 points) per detection tile, whatever the CTA width
+// The stepper's detection (k_detect_mask<true>) runs on narrower CTAs: after the margin test most tiles have a
+// few live words, the kernel is a per-CTA latency chain (pair record -> poses / skin state -> broad phase -> live
+// words) times the number of waves, and at 4 warps per CTA twice as many chains are in flight per SM
+// (ncu: 42.8 % of the stalls were warps waiting at the CTA barriers while 2 of 8 warps ran the broad phase):
+// 47.8 -> 45.2 ms per forward(100) of C2. The plain kernel gains 4 % the same way (0.1116 -> 0.1064 ms on C2;
+// 64 threads: 0.117 ms); the brick kernel stays at 256 threads (3 CTAs per SM by shared memory).
+#ifndef SDFC_DETECT_THREADS_SKIN
+#define SDFC_DETECT_THREADS_SKIN 128
+#endif
+#ifndef SDFC_DETECT_THREADS_PLAIN
+#define SDFC_DETECT_THREADS_PLAIN 128
+#endif
+constexpr int kDetectThreadsSkin = SDFC_DETECT_THREADS_SKIN;
+constexpr int kDetectThreadsPlain = SDFC_DETECT_THREADS_PLAIN;
 
 constexpr int tr_out(int n) {  // values left per lane after the 5 halving steps
     for (int s = 0; s < 5; ++s) n = (n + 1) / 2;
