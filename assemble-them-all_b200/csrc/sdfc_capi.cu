@@ -762,16 +762,20 @@ sdfc_status sdfc_points_create(sdfc_context* ctx, int n, const double* xyz_host,
         }
         st = dev_alloc(&p->d_wsphere, sph.size());
         if (st == SDFC_OK) e = cudaMemcpy(p->d_wsphere, sph.data(), sizeof(double) * sph.size(), cudaMemcpyHostToDevice);
-        {   // box of every detection tile (PairDev::tile_box)
+        {   // boxes of every detection tile (PairDev::tile_box): the tile, its two halves, its four quarters
             const int per = kDetectTileWords * 32, nt = (n + per - 1) / per;
-            std::vector<double> box((size_t)6 * nt);
-            for (int t = 0; t < nt; ++t) {
-                const int i0 = t * per, i1 = std::min(n, i0 + per);
-                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-                for (int i = i0; i < i1; ++i)
-                    for (int a = 0; a < 3; ++a) { const double v = src[(size_t)a * n + i]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
-                for (int a = 0; a < 3; ++a) { box[6 * (size_t)t + a] = lo[a]; box[6 * (size_t)t + 3 + a] = hi[a]; }
-            }
+            std::vector<double> box((size_t)6 * 7 * nt);
+            for (int t = 0; t < nt; ++t)
+                for (int sidx = 0; sidx < 7; ++sidx) {
+                    const int len = sidx == 0 ? per : (sidx < 3 ? per / 2 : per / 4);
+                    const int off = sidx == 0 ? 0 : (sidx < 3 ? (sidx - 1) * len : (sidx - 3) * len);
+                    const int i0 = std::min(n, t * per + off), i1 = std::min(n, i0 + len);
+                    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                    for (int i = i0; i < i1; ++i)
+                        for (int a = 0; a < 3; ++a) { const double v = src[(size_t)a * n + i]; lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+                    double* o = &box[6 * ((size_t)t * 7 + sidx)];
+                    for (int a = 0; a < 3; ++a) { o[a] = lo[a]; o[3 + a] = hi[a]; }
+                }
             if (st == SDFC_OK) st = dev_alloc(&p->d_tile_box, box.size());
             if (st == SDFC_OK && e == cudaSuccess) e = cudaMemcpy(p->d_tile_box, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice);
         }

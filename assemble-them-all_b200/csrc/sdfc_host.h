@@ -89,7 +89,7 @@ struct sdfc_points {
     double* d_s = nullptr;  // sorted SoA (== d_o when not sorted)
     double* d_wsphere = nullptr;  // (cx, cy, cz, r) per 32-point word of the sorted copy
     double bsphere[4] = {0, 0, 0, 0};  // (cx, cy, cz, r) of the whole set
-    double* d_tile_box = nullptr;  // (lo[3], hi[3]) per detection tile of the sorted copy
+    double* d_tile_box = nullptr;  // 7 x (lo[3], hi[3]) per detection tile of the sorted copy: tile, halves, quarters
     std::vector<int32_t> perm;     // sorted position -> original index (empty: identity)
     bool sorted = false;
 };

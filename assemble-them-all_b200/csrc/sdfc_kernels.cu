@@ -89,7 +89,8 @@ struct GlobalSampler {
 template <bool F32, bool SKIN, class Sampler>
 __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1, const double* p1, const double* R2,
                                             const double* p2, int word0, uint32_t* mask_row, int* s_live, int* s_nlive,
-                                            int* s_count, const SkinCta& sk, Sampler& smp, bool all_live = false) {
+                                            int* s_count, const SkinCta& sk, Sampler& smp, bool all_live = false, int word_end = -1) {
+    if (word_end < 0) word_end = pd.n_words;   // first word past the range this call covers (a tile, or a part of one)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifndef SDFC_DETECT_U
 #define SDFC_DETECT_U 1
@@ -104,13 +105,13 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
     // warps of a CTA finish together even when the contact region covers a few words only.
     if (all_live) {
         // the whole tile lies inside the grid box (CTA-uniform): every word is live, in word order
-        const int nl = min(kDetectTileWords, pd.n_words - word0);
+        const int nl = max(0, min(kDetectTileWords, word_end - word0));
         if (threadIdx.x < kDetectTileWords) s_live[kDetectTileWords + threadIdx.x] = word0 + threadIdx.x;
         if (threadIdx.x == 0) { s_nlive[0] = min(nl, 32); s_nlive[1] = max(nl - 32, 0); }
     } else if (threadIdx.x < kDetectTileWords) {
         const int w = word0 + threadIdx.x;
         bool keep = false, culled = false, used_up = false, elig_out = false;
-        if (w < pd.n_words) {
+        if (w < word_end) {
             const double* sp = pd.wsphere + 4 * (size_t)w;
             double cw[3], cl[3];
             to_world(R1, p1, __ldg(sp), __ldg(sp + 1), __ldg(sp + 2), cw);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void detect_tile(const PairDev& pd, const double* R1,
         }
         if (SKIN && sk.rebuild) {
             const unsigned eb = __ballot_sync(0xffffffffu, elig_out);
-            const unsigned ob = __ballot_sync(0xffffffffu, w < pd.n_words && !keep);
+            const unsigned ob = __ballot_sync(0xffffffffu, w < word_end && !keep);
             if (lane == 0 && eb) atomicAdd(sk.elig, __popc(eb));
             // signed-int order == float order on {-1} u [0, inf): one word without a margin makes the pair's -1
             if (lane == 0 && ob) atomicMin(sk.pair_margin, __float_as_int(sk.out_margin));
@@ -336,6 +337,7 @@ struct BrickSampler {
     int bx0, by0, bz0, nbx, nby, nbz;
     bool waited;
     bool all_inside;     // the image of the tile's box lies inside [mn, mx]: every point samples the grid
+    uint32_t parity;     // phase of the mbarrier this stage completes
     __device__ __forceinline__ double eval(const GridDev& G, const double* R1, const double* p1, const double* R2,
                                            const double* p2, double x0, double x1, double x2) {
         double xw[3], x[3];
@@ -355,7 +357,7 @@ struct BrickSampler {
         // the brick covers the image of the tile's box, so this always holds for a staged tile; checked anyway
         const bool staged = sb != 0u && rx0 >= 0 && rx1 < nbx && ry0 >= 0 && ry1 < nby && rz0 >= 0 && rz1 < nbz;
         if (staged) {
-            if (!waited) { mbar_wait(bar, 0); waited = true; }
+            if (!waited) { mbar_wait(bar, parity); waited = true; }
             const int sy = nbx * 64, sz = sy * nby;
             const int ox0 = rx0 * 64 + (i & 3), ox1 = rx1 * 64 + (i1 & 3);
             const int oy0 = ry0 * sy + (j & 3) * 4, oy1 = ry1 * sy + (j1 & 3) * 4;
@@ -374,7 +376,10 @@ struct BrickSampler {
     }
 };
 
-__global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, const double* __restrict__ E) {
+#ifndef SDFC_BRICK_MIN_BLOCKS
+#define SDFC_BRICK_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kDetectThreads, SDFC_BRICK_MIN_BLOCKS) k_detect_brick(BatchDev B, const double* __restrict__ E) {
     extern __shared__ __align__(128) unsigned char brick_raw[];
     __shared__ PairDev pd;
     __shared__ double R1[9], p1[3], R2[9], p2[3];
@@ -406,72 +411,99 @@ __global__ void __launch_bounds__(kDetectThreads, 3) k_detect_brick(BatchDev B, 
         const uint32_t bytes = (uint32_t)(cnt * 8) & ~15u;
         if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + i0), "r"(bytes) : "memory");
     }
-    if (bricks && threadIdx.x < 32) {
-        // image of the tile's box in the SDF frame: min / max over its 8 corners (lanes 0..7)
-        const double* tb = pd.tile_box + 6 * (size_t)(word0 / kDetectTileWords);
-        const int c = threadIdx.x & 7;
-        double cw[3], cl[3];
-        to_world(R1, p1, __ldg(tb + ((c & 1) ? 3 : 0)), __ldg(tb + ((c & 2) ? 4 : 1)), __ldg(tb + ((c & 4) ? 5 : 2)), cw);
-        to_local(R2, p2, cw, cl);
-        double lo[3] = {cl[0], cl[1], cl[2]}, hi[3] = {cl[0], cl[1], cl[2]};
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-                hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-            }
-        if (threadIdx.x == 0) {
-            // only points inside [mn, mx] sample the grid; 1e-7 covers the rounding of the transforms (as the broad phase)
-            const GridDev& G = pd.grid;
-            const double dd[3] = {G.dx, G.dy, G.dz}, rd[3] = {G.rdx, G.rdy, G.rdz};
-            const int nn[3] = {G.ni, G.nj, G.nk}, nbr[3] = {G.nbx, G.nby, G.nbz};
-            int b0[3], nb[3];
-            bool any = true, inside = true;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double l = fmax(lo[a] - 1e-7, G.mn[a]), h = fmin(hi[a] + 1e-7, G.mx[a]);
-                any = any && (l <= h);
-                inside = inside && (lo[a] - 1e-7 >= G.mn[a]) && (hi[a] + 1e-7 <= G.mx[a]);
-                // cell index is monotonic in the coordinate (correctly rounded quotient, then floor)
-                int c0 = (int)floor(exact_div(__dsub_rn(l, G.mn[a]), dd[a], rd[a]));
-                int c1 = (int)floor(exact_div(__dsub_rn(h, G.mn[a]), dd[a], rd[a]));
-                c0 = max(0, min(c0, nn[a] - 1)); c1 = max(0, min(c1, nn[a] - 1));
-                b0[a] = c0 >> 2;
-                nb[a] = min(((c1 + 1) >> 2), nbr[a] - 1) - b0[a] + 1;   // + 1: upper neighbour node
-            }
-            const bool fits = any && nb[0] <= kBrickMaxXY && nb[1] <= kBrickMaxXY &&
-                              (size_t)nb[0] * nb[1] * nb[2] * 256 <= (size_t)B.brick_cap;
-            if (B.brick_stats != nullptr) atomicAdd(B.brick_stats + (fits ? 0 : (any ? 1 : 2)), 1ull);
-            s_brick[0] = b0[0]; s_brick[1] = b0[1]; s_brick[2] = b0[2];
-            s_brick[3] = nb[0]; s_brick[4] = nb[1]; s_brick[5] = nb[2];
-            s_brick[6] = fits ? 1 : 0;
-            s_brick[7] = (any && inside) ? 1 : 0;
-            if (fits) {
-                const uint32_t slice = (uint32_t)nb[0] * nb[1] * 256;
-                mbar_arrive_expect_tx(&s_bar, slice * nb[2]);
-                const unsigned char* tm = static_cast<const unsigned char*>(G.tmaps) +
-                                          (size_t)((nb[0] - 1) * kBrickMaxXY + (nb[1] - 1)) * 128;
-                for (int z = 0; z < nb[2]; ++z)
-                    tma_load_bricks(tm, &s_bar, reinterpret_cast<unsigned char*>(sb) + (size_t)z * slice, 0, b0[0], b0[1], b0[2] + z);
-            }
-        }
-    }
-    __syncthreads();
     uint32_t* mask_row = B.mask + (size_t)env * B.words_per_env;
     SkinCta sk_unused;
-    const bool staged = s_brick[6] != 0;
-    if (pd.grid.b32 != nullptr) {
-        BrickSampler smp{staged ? smem_u32(sb) : 0u, &s_bar, s_brick[0], s_brick[1], s_brick[2], s_brick[3], s_brick[4], s_brick[5], false,
-                         s_brick[7] != 0};
-        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp, s_brick[7] != 0);
-        if (staged && !smp.waited) mbar_wait(&s_bar, 0);   // the CTA must not retire under an in-flight bulk copy
-    } else if (pd.grid.f32()) {
-        GlobalSampler<true> smp;
-        detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+    if (!bricks) {
+        if (pd.grid.f32()) {
+            GlobalSampler<true> smp;
+            detect_tile<true, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+        } else {
+            GlobalSampler<false> smp;
+            detect_tile<false, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+        }
     } else {
-        GlobalSampler<false> smp;
-        detect_tile<false, false>(pd, R1, p1, R2, p2, word0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp);
+        // The tile, or - when the bricks under its box exceed the shared-memory cap (sparse point sets: 2048 points
+        // spread over many cells) - its two halves, or their quarters, one after the other: part `s` of the tile
+        // (PairDev::tile_box holds 7 boxes per tile: 0 = all 64 words, 1..2 = halves, 3..6 = quarters) stages the
+        // bricks under ITS box and is evaluated from shared memory; only a quarter that still does not fit gathers
+        // from global memory. One mbarrier, one phase per staged part.
+        uint32_t stage = 0;
+        // returns false when part s has to be split (nothing evaluated)
+        auto run_part = [&](int s, bool leaf) -> bool {
+            const int len = s == 0 ? kDetectTileWords : (s < 3 ? kDetectTileWords / 2 : kDetectTileWords / 4);
+            const int w0 = word0 + (s == 0 ? 0 : (s < 3 ? (s - 1) * len : (s - 3) * len));
+            const int w1 = min(pd.n_words, w0 + len);
+            if (w0 >= pd.n_words) return true;   // CTA-uniform: the part lies past the last word
+            if (threadIdx.x < 32) {
+                // image of the part's box in the SDF frame: min / max over its 8 corners (lanes 0..7)
+                const double* tb = pd.tile_box + 6 * ((size_t)(word0 / kDetectTileWords) * 7 + s);
+                const int c = threadIdx.x & 7;
+                double cw[3], cl[3];
+                to_world(R1, p1, __ldg(tb + ((c & 1) ? 3 : 0)), __ldg(tb + ((c & 2) ? 4 : 1)), __ldg(tb + ((c & 4) ? 5 : 2)), cw);
+                to_local(R2, p2, cw, cl);
+                double lo[3] = {cl[0], cl[1], cl[2]}, hi[3] = {cl[0], cl[1], cl[2]};
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                        hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+                    }
+                if (threadIdx.x == 0) {
+                    // only points inside [mn, mx] sample the grid; 1e-7 covers the rounding of the transforms (as the broad phase)
+                    const GridDev& G = pd.grid;
+                    const double dd[3] = {G.dx, G.dy, G.dz}, rd[3] = {G.rdx, G.rdy, G.rdz};
+                    const int nn[3] = {G.ni, G.nj, G.nk}, nbr[3] = {G.nbx, G.nby, G.nbz};
+                    int b0[3], nb[3];
+                    bool any = true, inside = true;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double l = fmax(lo[a] - 1e-7, G.mn[a]), h = fmin(hi[a] + 1e-7, G.mx[a]);
+                        any = any && (l <= h);
+                        inside = inside && (lo[a] - 1e-7 >= G.mn[a]) && (hi[a] + 1e-7 <= G.mx[a]);
+                        // cell index is monotonic in the coordinate (correctly rounded quotient, then floor)
+                        int c0 = (int)floor(exact_div(__dsub_rn(l, G.mn[a]), dd[a], rd[a]));
+                        int c1 = (int)floor(exact_div(__dsub_rn(h, G.mn[a]), dd[a], rd[a]));
+                        c0 = max(0, min(c0, nn[a] - 1)); c1 = max(0, min(c1, nn[a] - 1));
+                        b0[a] = c0 >> 2;
+                        nb[a] = min(((c1 + 1) >> 2), nbr[a] - 1) - b0[a] + 1;   // + 1: upper neighbour node
+                    }
+                    const bool fits = any && nb[0] <= kBrickMaxXY && nb[1] <= kBrickMaxXY &&
+                                      (size_t)nb[0] * nb[1] * nb[2] * 256 <= (size_t)B.brick_cap;
+                    const bool split = any && !fits && !leaf;
+                    if (B.brick_stats != nullptr && !split) atomicAdd(B.brick_stats + (fits ? 0 : (any ? 1 : 2)), 1ull);
+                    s_brick[0] = b0[0]; s_brick[1] = b0[1]; s_brick[2] = b0[2];
+                    s_brick[3] = nb[0]; s_brick[4] = nb[1]; s_brick[5] = nb[2];
+                    s_brick[6] = fits ? 1 : (split ? 2 : 0);
+                    s_brick[7] = (any && inside) ? 1 : 0;
+                    if (fits) {
+                        const uint32_t slice = (uint32_t)nb[0] * nb[1] * 256;
+                        mbar_arrive_expect_tx(&s_bar, slice * nb[2]);
+                        const unsigned char* tm = static_cast<const unsigned char*>(G.tmaps) +
+                                                  (size_t)((nb[0] - 1) * kBrickMaxXY + (nb[1] - 1)) * 128;
+                        for (int z = 0; z < nb[2]; ++z)
+                            tma_load_bricks(tm, &s_bar, reinterpret_cast<unsigned char*>(sb) + (size_t)z * slice, 0, b0[0], b0[1], b0[2] + z);
+                    }
+                }
+            }
+            __syncthreads();
+            const int how = s_brick[6];
+            if (how == 2) { __syncthreads(); return false; }   // every thread has read the verdict before it is rewritten
+            const bool staged = how == 1;
+            BrickSampler smp{staged ? smem_u32(sb) : 0u, &s_bar, s_brick[0], s_brick[1], s_brick[2], s_brick[3], s_brick[4], s_brick[5], false,
+                             s_brick[7] != 0, stage & 1u};
+            detect_tile<true, false>(pd, R1, p1, R2, p2, w0, mask_row, s_live, s_nlive, &s_count, sk_unused, smp, s_brick[7] != 0, w1);
+            if (staged) {
+                if (!smp.waited) mbar_wait(&s_bar, stage & 1u);   // no part (and not the CTA) ends under an in-flight bulk copy
+                stage += 1;
+            }
+            __syncthreads();   // bricks, live-word lists and the verdict are consumed
+            return true;
+        };
+        if (!run_part(0, false))
+            for (int h = 0; h < 2; ++h)
+                if (!run_part(1 + h, false))
+                    for (int q = 0; q < 2; ++q) run_part(3 + 2 * h + q, true);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

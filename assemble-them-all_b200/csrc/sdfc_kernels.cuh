@@ -17,9 +17,10 @@ struct PairDev {
     // in the contact body's frame: lets detection skip whole words that cannot
     // reach the SDF's box (they would all return FLT_MAX, BodySDFObj.cpp:170)
     const double* wsphere;
-    // axis-aligned box (lo[3], hi[3]) of every detection tile (kDetectTileWords words) of the sorted copy,
-    // in the contact body's frame: the voxel brick a tile stages in shared memory is the grid region under
-    // the image of this box (sdfc_kernels.cu, k_detect_brick)
+    // axis-aligned boxes (lo[3], hi[3]) of every detection tile (kDetectTileWords words) of the sorted copy, in the
+    // contact body's frame, 7 per tile: the tile, its two halves, its four quarters. The voxel bricks a tile (or
+    // a part of it, when the whole does not fit) stages in shared memory are the grid region under the image of
+    // the box (sdfc_kernels.cu, k_detect_brick)
     const double* tile_box;
     double bsphere[4];   // bounding sphere of the whole point set (pair-level culling of the stepper)
     int n;            // number of contact points
