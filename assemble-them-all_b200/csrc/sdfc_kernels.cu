@@ -379,13 +379,17 @@ struct BrickSampler {
 #ifndef SDFC_BRICK_MIN_BLOCKS
 #define SDFC_BRICK_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(kDetectThreads, SDFC_BRICK_MIN_BLOCKS) k_detect_brick(BatchDev B, const double* __restrict__ E) {
+#ifndef SDFC_BRICK_THREADS
+#define SDFC_BRICK_THREADS 256
+#endif
+constexpr int kBrickThreads = SDFC_BRICK_THREADS;
+__global__ void __launch_bounds__(kBrickThreads, SDFC_BRICK_MIN_BLOCKS) k_detect_brick(BatchDev B, const double* __restrict__ E) {
     extern __shared__ __align__(128) unsigned char brick_raw[];
     __shared__ PairDev pd;
     __shared__ double R1[9], p1[3], R2[9], p2[3];
     __shared__ int s_count;
     __shared__ int s_live[2 * kDetectTileWords];
-    __shared__ int s_nlive[kDetectThreads / 32];
+    __shared__ int s_nlive[kBrickThreads / 32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_brick[8];   // bx0, by0, bz0, nbx, nby, nbz, staged, tile image inside the grid box
     const int tile = blockIdx.x, env = blockIdx.y + B.env0;
@@ -529,7 +533,7 @@ void launch_detect_mask(const BatchDev& B, const double* E, cudaStream_t stream,
             cudaFuncSetAttribute(k_detect_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrickSmemMax + 128);
             configured = true;
         }
-        k_detect_brick<<<grid, kDetectThreads, B.brick_cap + 128, stream>>>(B, E);
+        k_detect_brick<<<grid, kBrickThreads, B.brick_cap + 128, stream>>>(B, E);
         return;
     }
     if (B.skin_margin != nullptr) k_detect_mask<true><<<grid, kDetectThreadsSkin, 0, stream>>>(B, E);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# brick kernel: CTAs per SM (launch bounds) x shared-memory cap per CTA, detection of 1e7 / 3e7 / 1e8 points vs 512^3
+# brick kernel: CTA width x CTAs per SM (launch bounds) x shared-memory cap per CTA, detection of 1e7 / 3e7 / 1e8 points vs 512^3
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 run() {  # lib cap
@@ -14,9 +14,6 @@ print('$1 cap $2 |', ' | '.join(out))
 "
 }
 run assemble-them-all_b200/libsdfcontact_b200.so 73728
-run tune_libs/libbrick_mb4.so 57344
-run tune_libs/libbrick_mb4.so 49152
-run tune_libs/libbrick_mb5.so 45056
-run tune_libs/libbrick_mb5.so 36864
-run tune_libs/libbrick_mb6.so 36864
-run tune_libs/libbrick_mb6.so 30720
+for lib in $(ls tune_libs/*.so 2>/dev/null); do
+  for cap in $CAPS; do run $lib $cap; done
+done
