@@ -1,4 +1,5 @@
-"""Generate tests/golden/run_joint_plan_bfs.npz by running the reference's OWN planner script, unchanged.
+"""Generate tests/golden/run_joint_plan_bfs.npz and run_multi_plan_queue.npz by running the reference's OWN planner
+scripts, unchanged.
 
 TEST INFRASTRUCTURE ONLY. `examples/run_joint_plan.py --planner bfs` of the reference is executed (a) as the
 command-line script and (b) through its unmodified module object (to read the path it found), on the stock CPU
@@ -77,6 +78,43 @@ def plan_in_process(view, module_dir):
     return status, np.array(path)
 
 
+def make_view_multi(parts, assembly_id="00000"):
+    """Same view with the assembly under assets/multi_assembly (run_multi_plan.py's default --dir)."""
+    from assemble_them_all_b200 import synth
+    view = make_view(parts, assembly_id)
+    os.makedirs(os.path.join(view, "assets", "multi_assembly"))
+    synth.write_assembly(parts, os.path.join(view, "assets", "multi_assembly", assembly_id))
+    return view
+
+
+def run_multi_script(view, module_dir, path_max_time=20.0):
+    """examples/run_multi_plan.py --seq-planner queue --path-planner bfs, unchanged -> (result status, sequence,
+    [(move id, succeeded)] per trial, stdout). A path plan that cannot succeed runs into --path-max-time (status
+    Timeout; the BFS has no depth limit), so only success / failure per trial is machine independent."""
+    r = subprocess.run([sys.executable, os.path.join(view, "examples", "run_multi_plan.py"), "--id", "00000", "--seq-planner", "queue",
+                        "--path-planner", "bfs", "--sdf-dx", "0.1", "--path-max-time", str(path_max_time), "--seq-max-time", "100000"],
+                       capture_output=True, text=True, env=script_env(module_dir), cwd=view, timeout=1800)
+    res = re.search(r"Result: (\w+) \| Disassembled: (\d+)/(\d+)", r.stdout)
+    seq = re.search(r"Sequence: \[(.*)\]", r.stdout)
+    if r.returncode != 0 or not res or not seq:
+        raise RuntimeError("run_multi_plan.py failed:\n" + r.stdout + r.stderr)
+    trials = [(m, st in ("Success", "Start with goal")) for m, st in re.findall(r"Move id: (\w+) \| Status: ([\w ]+?) \|", r.stdout)]
+    sequence = [t.strip().strip("'\"") for t in seq.group(1).split(",") if t.strip()]
+    return res.group(1), sequence, trials, r.stdout
+
+
+def main_multi():
+    from assemble_them_all_b200 import synth
+    module_dir = os.path.join(ROOT, "oracle", "_ref")
+    view = make_view_multi(synth.l_channel_with_plug())
+    status, sequence, trials, out = run_multi_script(view, module_dir)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "run_multi_plan_queue.npz"), status=np.array(status),
+                        sequence=np.array(sequence), trial_ids=np.array([m for m, _ in trials]),
+                        trial_ok=np.array([ok for _, ok in trials]), sdf_dx=np.array(0.1), seed=np.array(1))
+    print(f"run_multi_plan_queue: {status}, sequence {sequence}, trials {trials}")
+    shutil.rmtree(view, ignore_errors=True)
+
+
 def main():
     from assemble_them_all_b200 import synth
     module_dir = os.path.join(ROOT, "oracle", "_ref")
@@ -92,3 +130,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_multi()

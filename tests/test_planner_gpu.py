@@ -171,3 +171,35 @@ def test_plan_matches_the_reference_script(cuda_ctx):
     assert r.path.shape == z["path"].shape
     assert rel_err(z["path"], r.path) <= 1e-9
     sim.close()
+
+
+def test_sequence_matches_the_reference_multi_plan_script(cuda_ctx):
+    """tests/golden/run_multi_plan_queue.npz is what the reference's own examples/run_multi_plan.py (queue + bfs,
+    unchanged, stock CPU redmax_py) printed for the three-part assembly (oracle/make_golden_planner.py). The
+    repo's SequencePlanner over batched BFS plans on the CUDA stepper must visit the parts in the same order,
+    succeed / fail on the same trials and end with the same removal sequence."""
+    import os
+    from assemble_them_all_b200 import contact
+    from oracle import ref_scene
+    from tests.helpers import GOLDEN
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    z = np.load(os.path.join(GOLDEN, "run_multi_plan_queue.npz"))
+    parts = synth.l_channel_with_plug()
+
+    def plan_cuda(move_id, still_ids, rotation, max_depth):
+        sub = {k: parts[k] for k in [move_id, *still_ids]}
+        p = ref_scene.probe_from_assembly(sub, move_id, list(still_ids), "translational", sdf_dx=float(z["sdf_dx"]))
+        names = [f"part{i}" for i in [move_id, *still_ids]]
+        still_v = np.vstack([np.array(p.get_body_vertices(n, True)).T for n in names[1:]])
+        hulls = PL.HullPair(np.array(p.get_body_vertices(names[0])).T, still_v)
+        sim = contact.build_simulation(cuda_ctx, ref_scene.extract_scene(p), 12)
+        try:
+            return PL.BatchedBFSPlanner(sim, 0, hulls).plan(max_depth=12).status   # depth bound instead of a clock
+        finally:
+            sim.close()
+
+    r = PL.SequencePlanner(["0", "1", "2"], plan_cuda).plan_sequence("queue", False, int(z["seed"]))
+    assert r.status == str(z["status"]) and r.sequence == [str(x) for x in z["sequence"]]
+    assert [m for m, _, _, _ in r.log] == [str(x) for x in z["trial_ids"]]
+    assert [s in PL.SUCCESS_STATUS for _, _, _, s in r.log] == [bool(x) for x in z["trial_ok"]]

@@ -50,3 +50,46 @@ def test_reference_script_runs_unchanged_with_shims():
     view = MG.make_view(synth.l_channel())
     status, out = MG.run_script(view, os.path.join(MG.ROOT, "oracle", "_ref"))
     assert status == str(golden()["cli_status"]) and "planning time" in out
+
+
+def golden_multi():
+    return np.load(os.path.join(GOLDEN, "run_multi_plan_queue.npz"))
+
+
+def test_multi_plan_script_runs_unchanged_with_shims():
+    """examples/run_multi_plan.py --seq-planner queue --path-planner bfs of the reference, unchanged (symlink view,
+    tests/shims), on the stock CPU redmax_py: trial order, success / failure per trial and the removal sequence equal
+    the golden (a path plan that cannot succeed ends by --path-max-time, so only success / failure is compared)."""
+    if not os.path.isdir("/root/reference/examples"):
+        pytest.skip("/root/reference is not present on this machine")
+    from oracle import make_golden_planner as MG, ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    z = golden_multi()
+    view = MG.make_view_multi(synth.l_channel_with_plug())
+    status, sequence, trials, out = MG.run_multi_script(view, os.path.join(MG.ROOT, "oracle", "_ref"), path_max_time=15.0)
+    assert status == str(z["status"]) and sequence == [str(x) for x in z["sequence"]]
+    assert [m for m, _ in trials] == [str(x) for x in z["trial_ids"]] and [ok for _, ok in trials] == [bool(x) for x in z["trial_ok"]]
+
+
+def test_sequence_planner_reproduces_the_multi_plan_script():
+    """The repo's SequencePlanner ("queue" variant, same use of numpy's legacy RNG) over path plans on the reference's
+    CPU simulator visits the parts in the script's order and ends with the script's sequence."""
+    from oracle import ref_scene
+    if not ref_scene.available():
+        pytest.skip("oracle/_ref not built")
+    z = golden_multi()
+    parts = synth.l_channel_with_plug()
+
+    def plan_ref(move_id, still_ids, rotation, max_depth):
+        sub = {k: parts[k] for k in [move_id, *still_ids]}
+        p = ref_scene.probe_from_assembly(sub, move_id, list(still_ids), "translational", sdf_dx=float(z["sdf_dx"]))
+        names = [f"part{i}" for i in [move_id, *still_ids]]
+        still_v = np.vstack([np.array(p.get_body_vertices(n, True)).T for n in names[1:]])
+        hulls = PL.HullPair(np.array(p.get_body_vertices(names[0])).T, still_v)
+        return SP.SequentialBFSPlanner(p, names[0], hulls).plan(PL.TRANS_ACTIONS, max_depth=12)[0]   # depth bound instead of a clock (the last removal takes 10 moves)
+
+    r = PL.SequencePlanner(["0", "1", "2"], plan_ref).plan_sequence("queue", False, int(z["seed"]))
+    assert r.status == str(z["status"]) and r.sequence == [str(x) for x in z["sequence"]]
+    assert [m for m, _, _, _ in r.log] == [str(x) for x in z["trial_ids"]]
+    assert [s in PL.SUCCESS_STATUS for _, _, _, s in r.log] == [bool(x) for x in z["trial_ok"]]
