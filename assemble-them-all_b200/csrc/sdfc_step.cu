@@ -384,7 +384,7 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
     if (st == SDFC_OK) {
         // SDFC_SIM_LANES overrides the lane count (1 = everything on the context's stream)
         const char* lanes_env = std::getenv("SDFC_SIM_LANES");
-        s->n_lanes = lanes_env ? std::max(1, std::min((int)sdfc_sim::kMaxLanes, std::atoi(lanes_env))) : (ne >= 512 ? 2 : 1);
+        s->n_lanes = lanes_env ? std::max(1, std::min((int)sdfc_sim::kMaxLanes, std::atoi(lanes_env))) : (ne >= 128 ? 2 : 1);
         s->n_lanes = std::min(s->n_lanes, std::max(1, ne / 32));
         A(sdfc_host::batch_ensure_plan_slots(batch, s->n_lanes));   // every lane plans its own force work lists
         cudaError_t e = cudaMallocHost((void**)&s->h_unfinished, sizeof(int) * sdfc_sim::kMaxLanes);
