@@ -299,9 +299,13 @@ struct sdfc_sim {
     // fork / join streams and events of a lane's contact kernels, and the captured steady-state round
     cudaStream_t lane_aux[kMaxLanes][2] = {};
     cudaEvent_t lane_ev[kMaxLanes][4] = {};
-    cudaGraphExec_t lane_graph[kMaxLanes][2] = {};   // [lane][0: warp per environment, 1: tail variant (CTA per environment)]
-    uint64_t lane_graph_key[kMaxLanes][2] = {};
-    int tail_envs = 0;   // a lane switches to the tail variant once this few of its environments are unfinished
+    cudaGraphExec_t lane_graph[kMaxLanes][3] = {};   // [lane][round-kernel variant: 0 warp, 1 / 2 CTA of 128 / 256 threads per environment]
+    uint64_t lane_graph_key[kMaxLanes][3] = {};
+    int tail_envs = 0;   // a lane switches to the CTA-per-environment variants once this few of its environments are unfinished
+    int team_variant(int unfinished) const {   // 256 threads while one CTA per SM covers them, 128 up to tail_envs, else a warp
+        if (unfinished > tail_envs) return 0;
+        return unfinished <= tail_envs / 4 ? 2 : 1;
+    }
     bool use_graph = true;
     bool use_active = false;
     double* d_fext = nullptr;
@@ -314,17 +318,20 @@ struct sdfc_sim {
 };
 
 namespace {
-constexpr int kTailTeam = SDFC_TAIL_TEAM;   // threads per environment of the tail variant of the round kernel
+constexpr int kTailTeam = SDFC_TAIL_TEAM;   // threads per environment of the CTA-per-environment variants: this and twice this
 
-sdfc_status launch_round(sdfc_sim* s, const SimDev& D, int kind, cudaStream_t st, bool tail = false) {
+sdfc_status launch_round(sdfc_sim* s, const SimDev& D, int kind, cudaStream_t st, int variant = 0) {
     const size_t smem = sizeof(EnvW) * kSimWarps;
     static bool configured = false;
     if (!configured) {
         SDFC_CUDA(cudaFuncSetAttribute(k_sim_round<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SDFC_CUDA(cudaFuncSetAttribute(k_sim_round<kTailTeam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvW)));
+        SDFC_CUDA(cudaFuncSetAttribute(k_sim_round<2 * kTailTeam>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvW)));
         configured = true;
     }
-    if (tail) {
+    if (variant == 2) {
+        k_sim_round<2 * kTailTeam><<<D.env_count, 2 * kTailTeam, sizeof(EnvW), st>>>(D, kind);
+    } else if (variant == 1) {
         k_sim_round<kTailTeam><<<D.env_count, kTailTeam, sizeof(EnvW), st>>>(D, kind);
     } else {
         const int blocks = (D.env_count + kSimWarps - 1) / kSimWarps;
@@ -399,7 +406,9 @@ sdfc_status sdfc_sim_create(sdfc_batch* batch, const sdfc_body_desc* bodies, con
         // so while the teams of a lane's unfinished environments still fit the device side by side (4 CTAs per SM)
         // its duration is the latency of ONE environment and four warps per environment shorten it (measured on
         // 1024 rollouts in 2 lanes: 62.3 -> 58.2 ms translational, 66.3 -> 58.8 ms free3d-exp per forward(100));
-        // larger lanes start on the warp-per-environment variant and switch when enough environments are done.
+        // eight warps per environment while one CTA per SM covers the lane (128 rollouts: 18.8 -> 17.9 ms; at 1024
+        // they cost 45.2 -> 49.6 ms); larger lanes start on the warp-per-environment variant and switch when enough
+        // environments are done.
         // SDFC_SIM_TAIL overrides the threshold (0 = never).
         s->tail_envs = 4 * sdfc::device_sm_count();
         if (const char* t = std::getenv("SDFC_SIM_TAIL")) s->tail_envs = std::max(0, std::atoi(t));
@@ -453,7 +462,7 @@ sdfc_status sdfc_sim_destroy(sdfc_sim* s) {
     cudaFree(s->d_counters); cudaFree(s->d_traj_q); cudaFree(s->d_traj_qd);
     if (s->h_unfinished) cudaFreeHost(s->h_unfinished);
     for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) {
-        for (int v = 0; v < 2; ++v) if (s->lane_graph[l][v]) cudaGraphExecDestroy(s->lane_graph[l][v]);
+        for (int v = 0; v < 3; ++v) if (s->lane_graph[l][v]) cudaGraphExecDestroy(s->lane_graph[l][v]);
         if (s->lane_stream[l]) cudaStreamDestroy(s->lane_stream[l]);
         if (s->lane_event[l]) cudaEventDestroy(s->lane_event[l]);
         for (int a = 0; a < 2; ++a) if (s->lane_aux[l][a]) cudaStreamDestroy(s->lane_aux[l][a]);
@@ -581,8 +590,8 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
     // is only waited for before round r + 2 is issued, so the device always has queued work while
     // the host looks at an older answer (a finished lane runs at most two empty rounds).
     bool lane_pending[sdfc_sim::kMaxLanes] = {false, false, false, false};
-    bool lane_tail[sdfc_sim::kMaxLanes];
-    for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) lane_tail[l] = l < L && lane_cnt[l] <= s->tail_envs;
+    int lane_tail[sdfc_sim::kMaxLanes];   // round-kernel variant of the lane (sdfc_sim::team_variant)
+    for (int l = 0; l < sdfc_sim::kMaxLanes; ++l) lane_tail[l] = l < L ? s->team_variant(lane_cnt[l]) : 0;
     int64_t lane_round[sdfc_sim::kMaxLanes] = {0, 0, 0, 0};
     for (int64_t round = 0; round < guard && rc == SDFC_OK; ++round) {
         bool any = false;
@@ -593,7 +602,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
                 if (cudaEventSynchronize(s->lane_event[l]) != cudaSuccess) { rc = fail(SDFC_ERR_CUDA, "sdfc_sim_forward: lane sync failed"); break; }
                 lane_pending[l] = false;
                 if (s->h_unfinished[l] <= 0) { lane_live[l] = false; continue; }
-                lane_tail[l] = s->h_unfinished[l] <= s->tail_envs;
+                lane_tail[l] = s->team_variant(s->h_unfinished[l]);
             }
             any = true;
             SimDev Dl = D;
@@ -612,7 +621,7 @@ sdfc_status sdfc_sim_forward(sdfc_sim* s, int n_steps, double* q_traj_host, doub
             if (lane_round[l] == 0 || !s->use_graph) {
                 rc = issue(lane_round[l] == 0 ? ROUND_FIRST : ROUND_FULL);
             } else {
-                const int v = lane_tail[l] ? 1 : 0;
+                const int v = lane_tail[l];
                 if (s->lane_graph[l][v] == nullptr || s->lane_graph_key[l][v] != graph_key) {
                     if (s->lane_graph[l][v]) { cudaGraphExecDestroy(s->lane_graph[l][v]); s->lane_graph[l][v] = nullptr; }
                     cudaGraph_t g = nullptr;
